@@ -1,0 +1,143 @@
+/* promptir_b200 -- C ABI of the B200 (sm_100a) kernels behind the PromptIR restoration forward.
+ *
+ * The reference (kongwanbianjinyu/PromptIR) is pure PyTorch: its "operator API" for this path is the
+ * nn.Module net/model.py:PromptIR, which dispatches ~1800 ATen/cuDNN/cuBLAS kernels per forward.  This
+ * library is what a maintainer binds instead (ctypes stub in INTEGRATION.md): plain pointers, sizes and a
+ * cudaStream_t -- no torch types.  Each entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative PIR_ERR_* code; pir_last_error() returns a
+ *     thread-local human-readable message.  No exceptions cross the boundary, nothing is allocated,
+ *     nothing synchronises: kernels are enqueued on the stream that is passed in.
+ *   - activations are NHWC ("channels last") 16-bit: element (b, y, x, c) of a tensor with `pitch`
+ *     elements per pixel lives at base + b*bstride + (y*W + x)*pitch + c.  A tensor may be a channel slice
+ *     of a wider buffer (pitch > C): that is how torch.cat is folded away (model.py:341,347,353,359,365,370).
+ *   - dtype selects the 16-bit storage/operand type: PIR_DTYPE_BF16 or PIR_DTYPE_FP16; all accumulation,
+ *     LayerNorm statistics, softmax and norms are fp32.
+ *   - channel counts and pitches of 16-bit tensors are multiples of 8 (16-byte rows for TMA).
+ */
+#ifndef PROMPTIR_B200_H_
+#define PROMPTIR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIR_ABI_VERSION 1
+
+enum { PIR_DTYPE_FP16 = 0, PIR_DTYPE_BF16 = 1 };
+enum { PIR_OK = 0, PIR_ERR_ARG = -1, PIR_ERR_CUDA = -2, PIR_ERR_DRIVER = -3, PIR_ERR_UNSUPPORTED = -4 };
+
+/* epilogue store modes of pir_gemm */
+enum {
+  PIR_OUT_NHWC16 = 0,       /* 16-bit NHWC rows (optional residual add)                                  */
+  PIR_OUT_UNSHUFFLE16 = 1,  /* nn.PixelUnshuffle(2) folded into the store        (model.py:165)          */
+  PIR_OUT_SHUFFLE16 = 2,    /* nn.PixelShuffle(2) folded into the store          (model.py:175)          */
+  PIR_OUT_FINAL_NCHW32 = 3, /* fp32 NCHW, "+ inp_img"                            (model.py:377)          */
+  PIR_OUT_NHWC32 = 4        /* fp32 NHWC rows                                                            */
+};
+enum { PIR_LN_NONE = 0, PIR_LN_WITHBIAS = 1, PIR_LN_BIASFREE = 2 };
+
+int pir_abi_version(void);
+const char* pir_last_error(void);
+/* device sanity: returns 0 iff the current device is compute capability 10.x */
+int pir_check_device(void);
+
+/* ---- pointwise / dense-3x3 convolution as a tcgen05 GEMM ----------------------------------------
+ * Replaces nn.Conv2d(k=1) (model.py:88,92,111,113,294-313), the preceding LayerNorm (model.py:39-41,
+ * 60-63; folded: weights carry gamma, ln_s/vec_t carry the mean/bias terms), nn.Conv2d(k=3)
+ * (model.py:164,174,223,320) and the residual adds (model.py:193-194,377).
+ *   out[b,p,n] = epi( sum_{tap,k} a[b, p+tap, k] * w[b?, n, tap*Kpad + k] )
+ * w is packed [w_batched ? B : 1][N][taps*Kpad] 16-bit, Kpad = ceil(K/64)*64, zero padded.         */
+typedef struct PirGemm {
+  int32_t dtype;
+  int32_t B, H, W;          /* batch and spatial size of the A tensor                                     */
+  int32_t K, N, taps;       /* input channels, output channels, 1 or 9                                    */
+  int32_t w_batched;        /* 1: one weight matrix per image (attention fold)                            */
+  int32_t out_mode, ln_mode;
+  const void* a; int64_t a_pitch, a_bstride;
+  const void* w;
+  void* out; int64_t out_pitch, out_bstride;      /* bstride in elements of the output type             */
+  const void* res; int64_t res_pitch, res_bstride; /* optional residual (NHWC16 only), may alias out     */
+  const float* ln_s;        /* [N] row sums of the 16-bit gamma-scaled weights (ln_mode != 0)             */
+  const float* vec_t;       /* [N] additive per-channel vector (W.beta and/or conv bias) or NULL          */
+  const float* img;         /* fp32 NCHW network input (PIR_OUT_FINAL_NCHW32)                             */
+} PirGemm;
+int pir_gemm(const PirGemm* d, void* stream);
+
+/* ---- depthwise 3x3 (pad 1), optionally fused with the GDFN gate ----------------------------------
+ * gate == 0: out[b,p,c] = dw(in)[c] (+bias[c]),                c < C      (model.py:112,120  qkv_dwconv)
+ * gate == 1: out[b,p,c] = gelu_erf(dw(in)[c]) * dw(in)[C + c], c < C      (model.py:90,96-97 GDFN)
+ *            (in has 2*C channels).  w is [3][3][Cin] 16-bit (tap-major), bias fp32 [Cin] or NULL.     */
+typedef struct PirDwConv {
+  int32_t dtype, gate;
+  int32_t B, H, W, C;       /* C = output channels; input channels = C (gate 0) or 2*C (gate 1)           */
+  const void* in; int64_t in_pitch, in_bstride;
+  const void* w; const float* bias;
+  void* out; int64_t out_pitch, out_bstride;
+} PirDwConv;
+int pir_dwconv3x3(const PirDwConv* d, void* stream);
+
+/* ---- MDTA: transposed (channel) attention -----------------------------------------------------------
+ * Step 1, pir_mdta_gram: split-K tcgen05 Gram of q and k over the pixels of each image plus the squared
+ * L2 norms of every q/k channel (model.py:123-130).  qkv is the NHWC 16-bit output of the qkv dwconv
+ * (q = channels [0,C), k = [C,2C), v = [2C,3C)).  Partials go to `ws` (fp32, pir_mdta_ws_floats()).
+ * Step 2, pir_mdta_finalize: deterministic reduction of the partials, cosine logits * temperature,
+ * softmax over the key channels of each head (model.py:130-131), then the attention matrix is folded into
+ * project_out:  wfold[b][o][h*c + j] = sum_i Wo[o][h*c + i] * A[b,h][i][j]   (model.py:133-137), so that
+ * attn@v followed by project_out is ONE pir_gemm on v with per-image weights.  wo is fp32 [C][C].
+ * wfold is 16-bit [B][C][Kpad], Kpad = ceil(C/64)*64, zero padded.                                      */
+typedef struct PirMdta {
+  int32_t dtype;
+  int32_t B, HW, C, heads;
+  int32_t splits;           /* split-K factor chosen by pir_mdta_splits()                                 */
+  const void* qkv; int64_t qkv_pitch, qkv_bstride;
+  float* ws;                /* workspace                                                                   */
+  const float* temperature; /* [heads]                                                                     */
+  const float* wo;          /* [C][C] fp32 project_out weight                                              */
+  void* wfold;              /* [B][C][Kpad] 16-bit                                                         */
+} PirMdta;
+int pir_mdta_splits(int32_t B, int32_t HW, int32_t C);
+int64_t pir_mdta_ws_floats(int32_t B, int32_t C, int32_t splits);
+int pir_mdta_gram(const PirMdta* d, void* stream);
+int pir_mdta_finalize(const PirMdta* d, void* stream);
+
+/* ---- PromptGenBlock (model.py:226-232): pool -> linear -> softmax -> weighted prompt sum -> bilinear --
+ * x: NHWC 16-bit [B,H,W,C] feature; prompt: fp32 [L][S][S][D] (repacked prompt_param); lin_w fp32 [L][C],
+ * lin_b fp32 [L]; out: NHWC 16-bit [B,H,W,D] (the conv3x3 that follows is a pir_gemm with taps = 9).
+ * ws: fp32 workspace of pir_prompt_ws_floats() elements.  weights_out (optional) receives softmax [B][L]. */
+typedef struct PirPrompt {
+  int32_t dtype;
+  int32_t B, H, W, C;       /* feature map                                                                 */
+  int32_t L, D, S;          /* prompt components, channels, stored size                                    */
+  const void* x; int64_t x_pitch, x_bstride;
+  const float* prompt; const float* lin_w; const float* lin_b;
+  void* out; int64_t out_pitch, out_bstride;
+  float* ws; float* weights_out;
+} PirPrompt;
+int64_t pir_prompt_ws_floats(int32_t B, int32_t HW, int32_t C);
+int pir_prompt_gen(const PirPrompt* d, void* stream);
+
+/* ---- OverlapPatchEmbed (model.py:206): dense 3x3, fp32 NCHW image -> 16-bit NHWC ---------------------
+ * w: fp32 [Cout][Cin][3][3] (the parameter itself), bias fp32 [Cout] or NULL.  Cout % 8 == 0.            */
+typedef struct PirPatchEmbed {
+  int32_t dtype;
+  int32_t B, H, W, Cin, Cout;
+  const float* img; const float* w; const float* bias;
+  void* out; int64_t out_pitch, out_bstride;
+} PirPatchEmbed;
+int pir_patch_embed(const PirPatchEmbed* d, void* stream);
+
+/* ---- tile blend for tiled inference (demo.py:36-47) ----------------------------------------------------
+ * tiles: fp32 [ny*nx][C][th][tw] restored tiles in the reference's loop order (rows outer, columns inner);
+ * ys[ny], xs[nx]: DEVICE int32 arrays of tile origins (demo.py:32-34).  out[c,y,x] = clamp(sum of the
+ * tiles covering (y,x) / their count, 0, 1), fp32 [C][H][W].  Deterministic (gather, no atomics).          */
+int pir_tile_blend(const float* tiles, int32_t ny, int32_t nx, const int32_t* ys, const int32_t* xs, int32_t C,
+                   int32_t th, int32_t tw, float* out, int32_t H, int32_t W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROMPTIR_B200_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of libpromptir_b200.so (the C ABI declared in include/promptir_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised -- the product path never silently runs anything else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpromptir_b200.so")
+
+DTYPE_FP16, DTYPE_BF16 = 0, 1
+OUT_NHWC16, OUT_UNSHUFFLE16, OUT_SHUFFLE16, OUT_FINAL_NCHW32, OUT_NHWC32 = 0, 1, 2, 3, 4
+LN_NONE, LN_WITHBIAS, LN_BIASFREE = 0, 1, 2
+
+i32, i64, vp = C.c_int32, C.c_int64, C.c_void_p
+
+
+class PirGemm(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("K", i32), ("N", i32), ("taps", i32),
+                ("w_batched", i32), ("out_mode", i32), ("ln_mode", i32),
+                ("a", vp), ("a_pitch", i64), ("a_bstride", i64),
+                ("w", vp),
+                ("out", vp), ("out_pitch", i64), ("out_bstride", i64),
+                ("res", vp), ("res_pitch", i64), ("res_bstride", i64),
+                ("ln_s", vp), ("vec_t", vp), ("img", vp)]
+
+
+class PirDwConv(C.Structure):
+    _fields_ = [("dtype", i32), ("gate", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32),
+                ("in_", vp), ("in_pitch", i64), ("in_bstride", i64),
+                ("w", vp), ("bias", vp),
+                ("out", vp), ("out_pitch", i64), ("out_bstride", i64)]
+
+
+class PirMdta(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("HW", i32), ("C", i32), ("heads", i32), ("splits", i32),
+                ("qkv", vp), ("qkv_pitch", i64), ("qkv_bstride", i64),
+                ("ws", vp), ("temperature", vp), ("wo", vp), ("wfold", vp)]
+
+
+class PirPrompt(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32), ("L", i32), ("D", i32), ("S", i32),
+                ("x", vp), ("x_pitch", i64), ("x_bstride", i64),
+                ("prompt", vp), ("lin_w", vp), ("lin_b", vp),
+                ("out", vp), ("out_pitch", i64), ("out_bstride", i64),
+                ("ws", vp), ("weights_out", vp)]
+
+
+class PirPatchEmbed(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32),
+                ("img", vp), ("w", vp), ("bias", vp),
+                ("out", vp), ("out_pitch", i64), ("out_bstride", i64)]
+
+
+# every symbol include/promptir_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "pir_abi_version": (i32, []),
+    "pir_last_error": (C.c_char_p, []),
+    "pir_check_device": (i32, []),
+    "pir_gemm": (i32, [C.POINTER(PirGemm), vp]),
+    "pir_dwconv3x3": (i32, [C.POINTER(PirDwConv), vp]),
+    "pir_mdta_splits": (i32, [i32, i32, i32]),
+    "pir_mdta_ws_floats": (i64, [i32, i32, i32]),
+    "pir_mdta_gram": (i32, [C.POINTER(PirMdta), vp]),
+    "pir_mdta_finalize": (i32, [C.POINTER(PirMdta), vp]),
+    "pir_prompt_ws_floats": (i64, [i32, i32, i32]),
+    "pir_prompt_gen": (i32, [C.POINTER(PirPrompt), vp]),
+    "pir_patch_embed": (i32, [C.POINTER(PirPatchEmbed), vp]),
+    "pir_tile_blend": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, i32, vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0          # kernels enqueued through this binding (bench.py reports it as gpu_launches)
+
+
+def load() -> C.CDLL:
+    """Load the library once; raise loudly if it is not built (run `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"promptir_b200: native library not found at {LIB_PATH}. Build it with "
+                    "`make -C promptir_b200/csrc` (needs nvcc, sm_100a). There is no fallback path.")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(lib, name)           # AttributeError if the symbol is missing -> loud
+                fn.restype = res
+                fn.argtypes = args
+            if lib.pir_abi_version() != 1:
+                raise RuntimeError("promptir_b200: ABI version mismatch between _lib.py and the shared library")
+            _lib = lib
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().pir_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"promptir_b200.{what} failed ({code}): {msg}")

@@ -1,0 +1,201 @@
+// Shared device-side helpers for the sm_100a kernels: mbarrier, TMA, tcgen05/TMEM wrappers (inline PTX),
+// 16-bit packing helpers.  Everything here is original; encodings follow the PTX ISA (tcgen05 shared-memory
+// and instruction descriptors).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pir {
+
+// ---------------------------------------------------------------------------------------------------
+// element types: the whole pipeline is templated on a 16-bit storage type (bf16 or fp16)
+// ---------------------------------------------------------------------------------------------------
+struct BF16 { static constexpr int kFmt = 1; };   // tcgen05 kind::f16 a/b format code
+struct FP16 { static constexpr int kFmt = 0; };
+
+template <class T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<BF16>(float lo, float hi) {
+  uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r;
+}
+template <> __device__ __forceinline__ uint32_t pack2<FP16>(float lo, float hi) {
+  uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r;
+}
+template <class T> __device__ __forceinline__ float unpack_lo(uint32_t v);
+template <class T> __device__ __forceinline__ float unpack_hi(uint32_t v);
+template <> __device__ __forceinline__ float unpack_lo<BF16>(uint32_t v) { return __uint_as_float(v << 16); }
+template <> __device__ __forceinline__ float unpack_hi<BF16>(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+template <> __device__ __forceinline__ float unpack_lo<FP16>(uint32_t v) {
+  return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu)));
+}
+template <> __device__ __forceinline__ float unpack_hi<FP16>(uint32_t v) {
+  return __half2float(__ushort_as_half((unsigned short)(v >> 16)));
+}
+template <class T> __device__ __forceinline__ unsigned short to16(float f);
+template <> __device__ __forceinline__ unsigned short to16<BF16>(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+template <> __device__ __forceinline__ unsigned short to16<FP16>(float f) { return __half_as_ushort(__float2half_rn(f)); }
+template <class T> __device__ __forceinline__ float from16(unsigned short v);
+template <> __device__ __forceinline__ float from16<BF16>(unsigned short v) { return __uint_as_float(((uint32_t)v) << 16); }
+template <> __device__ __forceinline__ float from16<FP16>(unsigned short v) { return __half2float(__ushort_as_half(v)); }
+
+// mixed-precision FMA: d = a(16-bit half of a packed reg) * b(16-bit) + c(fp32).  SASS: FHFMA{.BF16}
+template <class T> __device__ __forceinline__ float fma16(unsigned short a, unsigned short b, float c);
+template <> __device__ __forceinline__ float fma16<BF16>(unsigned short a, unsigned short b, float c) {
+  float r; asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(r) : "h"(a), "h"(b), "f"(c)); return r;
+}
+template <> __device__ __forceinline__ float fma16<FP16>(unsigned short a, unsigned short b, float c) {
+  float r; asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r) : "h"(a), "h"(b), "f"(c)); return r;
+}
+__device__ __forceinline__ unsigned short lo16(uint32_t v) { return (unsigned short)(v & 0xffffu); }
+__device__ __forceinline__ unsigned short hi16(uint32_t v) { return (unsigned short)(v >> 16); }
+
+// ---------------------------------------------------------------------------------------------------
+// shared-memory addressing + mbarrier
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) { }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor), tile mode, completion on an mbarrier
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {    // same warp that allocated
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16/fp16 in, fp32 accumulate); issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (thread i <-> lane base+i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Instruction descriptor, kind::f16, fp32 accumulate.  fmt: 0=f16 1=bf16.  major: 0=K-major 1=MN-major.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int fmt, int M, int N, int a_major, int b_major) {
+  return (1u << 4)                      // c_format = F32
+         | ((uint32_t)fmt << 7)         // a_format
+         | ((uint32_t)fmt << 10)        // b_format
+         | ((uint32_t)a_major << 15) | ((uint32_t)b_major << 16)
+         | ((uint32_t)(N >> 3) << 17)   // n_dim
+         | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+// Shared-memory matrix descriptor (sm_100: version=1), 128-byte swizzle.
+//   K-major : rows of 128 B (64 x 16-bit along K), 8-row groups SBO bytes apart (1024 when dense)
+//   MN-major: rows of 128 B (64 x 16-bit along M/N), 8 K-rows per 1024 B atom, atoms along K SBO apart,
+//             64-element groups along M/N LBO apart
+__device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;               // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;               // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// misc math
+// ---------------------------------------------------------------------------------------------------
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7 + intrinsic error); 2 MUFU + ~10 FMA-class ops
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = __expf(-ax * ax);
+  const float r = fmaf(-p, e, 1.0f);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) {          // 0.5 x (1 + erf(x / sqrt 2))
+  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f));
+}
+
+}  // namespace pir

@@ -1,0 +1,295 @@
+// Depthwise 3x3 stencils (pad 1) on NHWC 16-bit tensors for sm_100a, shared-memory staged by TMA.
+//
+//   plain : out[c] = dw3x3(in)[c]                                  MDTA qkv_dwconv   (net/model.py:112,120)
+//   gated : out[c] = gelu_erf(dw3x3(in)[c]) * dw3x3(in)[C + c]     GDFN dwconv+gate  (net/model.py:90,96-97)
+//
+// One CTA = one (TH x 32 pixel) x (channel chunk) tile.  A single 4-D TMA box {chunk, 34, TH+2, 1} brings the
+// tile plus its halo into shared memory; the image border's zero padding is the TMA out-of-bounds fill.  Every
+// thread owns one pixel column and one vector of channels (8 for the plain kernel = LDS.128, 4 per half for
+// the gated kernel = LDS.64), walks down the TH+2 input rows and scatters each row into three rotating fp32
+// accumulator rows, so every input value is read from shared memory once per horizontal tap and the nine
+// taps are register-resident packed 16-bit pairs consumed directly by mixed-precision FMAs
+// (fma.rn.f32.{bf16,f16} -> SASS FHFMA): 9 FMAs per output element and no unpack instructions.
+// These kernels are HBM-bound: algorithmic bytes = (Cin + Cout) * 2 per pixel.
+#include "common.cuh"
+#include "host.h"
+
+namespace pir {
+
+constexpr int kDwTW = 32;          // tile width in pixels (one lane group per pixel column)
+
+struct DwArgs {
+  int H, W, C;                     // C = output channels
+  int tiles_x;
+  const void* w;                   // [9][Cin] 16-bit, tap-major
+  const float* bias;               // [Cin] or null
+  void* out;
+  long long out_pitch, out_bstride;
+};
+
+__device__ __forceinline__ void dw_tile_wait(uint32_t bar) { mbar_wait(bar, 0); }
+
+// ------------------------------------------------------------------------------------------------------
+// plain: CG channel groups of 8 channels per tile (CG = 8 -> 64 ch, CG = 6 -> 48 ch); block = CG * 32 threads
+// ------------------------------------------------------------------------------------------------------
+template <class T, int CG, int TH>
+__global__ void __launch_bounds__(CG * 32)
+dwconv_plain_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
+  constexpr int CC = CG * 8;
+  constexpr int ROW_BYTES = CC * 2;
+  constexpr int SW = kDwTW + 2;
+  extern __shared__ uint8_t dw_smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  uint8_t* dw_smem = dw_smem_raw + ((128u - (smem_u32(dw_smem_raw) & 127u)) & 127u);   // TMA destination alignment
+
+  const int tid = threadIdx.x;
+  const int cg = tid % CG;
+  const int tx = tid / CG;
+  const int c0 = blockIdx.y * CC;
+  const int x0 = (blockIdx.x % a.tiles_x) * kDwTW;
+  const int y0 = (blockIdx.x / a.tiles_x) * TH;
+  const int b = blockIdx.z;
+  const uint32_t bar_a = smem_u32(&bar);
+
+  if (tid == 0) {
+    mbar_init(bar_a, 1);
+    fence_barrier_init();
+    mbar_expect_tx(bar_a, (uint32_t)((TH + 2) * SW * ROW_BYTES));
+    tma_load_4d(smem_u32(dw_smem), &tmIn, bar_a, c0, x0 - 1, y0 - 1, b);
+  }
+  // taps for this thread's 8 channels, kept as packed 16-bit pairs (9 x 4 registers)
+  const int c = c0 + cg * 8;
+  const bool c_ok = c < a.C;
+  uint4 wt[9];
+  float binit[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) binit[i] = 0.f;
+  if (c_ok) {
+    const unsigned short* wp = reinterpret_cast<const unsigned short*>(a.w) + c;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wt[t] = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)t * a.C));
+    if (a.bias) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) binit[i] = __ldg(a.bias + c + i);
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wt[t] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();                 // barrier init visible to all waiters
+  dw_tile_wait(bar_a);
+
+  const int x = x0 + tx;
+  const bool x_ok = x < a.W;
+  unsigned short* outp = reinterpret_cast<unsigned short*>(a.out) + (size_t)b * a.out_bstride + c;
+  const uint8_t* col = dw_smem + (size_t)tx * ROW_BYTES + cg * 16;
+
+  float acc[3][8];
+#pragma unroll
+  for (int r = 0; r < TH + 2; ++r) {
+    // input row r feeds output rows r (tap row 0), r-1 (tap row 1), r-2 (tap row 2)
+    if (r < TH) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[r % 3][i] = binit[i];
+    }
+    uint4 v[3];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) v[kx] = *reinterpret_cast<const uint4*>(col + ((size_t)r * SW + kx) * ROW_BYTES);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int o = r - ky;
+      if (o >= 0 && o < TH) {
+        float* ac = acc[o % 3];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint4 w = wt[ky * 3 + kx];
+          const uint32_t vv[4] = {v[kx].x, v[kx].y, v[kx].z, v[kx].w};
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            ac[2 * q] = fma16<T>(lo16(vv[q]), lo16(ww[q]), ac[2 * q]);
+            ac[2 * q + 1] = fma16<T>(hi16(vv[q]), hi16(ww[q]), ac[2 * q + 1]);
+          }
+        }
+      }
+    }
+    const int o = r - 2;            // this output row is now complete
+    if (o >= 0) {
+      const int y = y0 + o;
+      if (c_ok && x_ok && y < a.H) {
+        const float* ac = acc[o % 3];
+        uint4 ov;
+        ov.x = pack2<T>(ac[0], ac[1]); ov.y = pack2<T>(ac[2], ac[3]);
+        ov.z = pack2<T>(ac[4], ac[5]); ov.w = pack2<T>(ac[6], ac[7]);
+        *reinterpret_cast<uint4*>(outp + ((size_t)y * a.W + x) * a.out_pitch) = ov;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// gated: 32 output channels per tile (two 32-channel boxes: x1 at c0, x2 at C + c0); 4 channels per thread
+// ------------------------------------------------------------------------------------------------------
+template <class T, int TH>
+__global__ void __launch_bounds__(256)
+dwconv_gate_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
+  constexpr int CC = 32;
+  constexpr int ROW_BYTES = CC * 2;
+  constexpr int SW = kDwTW + 2;
+  constexpr int HALF_BYTES = (TH + 2) * SW * ROW_BYTES;
+  extern __shared__ uint8_t dw_smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  uint8_t* dw_smem = dw_smem_raw + ((128u - (smem_u32(dw_smem_raw) & 127u)) & 127u);   // TMA destination alignment
+
+  const int tid = threadIdx.x;
+  const int cg = tid & 7;
+  const int tx = tid >> 3;
+  const int c0 = blockIdx.y * CC;
+  const int x0 = (blockIdx.x % a.tiles_x) * kDwTW;
+  const int y0 = (blockIdx.x / a.tiles_x) * TH;
+  const int b = blockIdx.z;
+  const uint32_t bar_a = smem_u32(&bar);
+
+  if (tid == 0) {
+    mbar_init(bar_a, 1);
+    fence_barrier_init();
+    mbar_expect_tx(bar_a, (uint32_t)(2 * HALF_BYTES));
+    tma_load_4d(smem_u32(dw_smem), &tmIn, bar_a, c0, x0 - 1, y0 - 1, b);
+    tma_load_4d(smem_u32(dw_smem) + HALF_BYTES, &tmIn, bar_a, a.C + c0, x0 - 1, y0 - 1, b);
+  }
+  const int c = c0 + cg * 4;
+  const bool c_ok = c < a.C;
+  uint2 w1[9], w2[9];
+  float b1[4] = {0.f, 0.f, 0.f, 0.f}, b2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c_ok) {
+    const unsigned short* wp = reinterpret_cast<const unsigned short*>(a.w) + c;
+    const size_t cin = (size_t)2 * a.C;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      w1[t] = __ldg(reinterpret_cast<const uint2*>(wp + (size_t)t * cin));
+      w2[t] = __ldg(reinterpret_cast<const uint2*>(wp + (size_t)t * cin + a.C));
+    }
+    if (a.bias) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { b1[i] = __ldg(a.bias + c + i); b2[i] = __ldg(a.bias + a.C + c + i); }
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { w1[t] = make_uint2(0, 0); w2[t] = make_uint2(0, 0); }
+  }
+  __syncthreads();
+  dw_tile_wait(bar_a);
+
+  const int x = x0 + tx;
+  const bool x_ok = x < a.W;
+  unsigned short* outp = reinterpret_cast<unsigned short*>(a.out) + (size_t)b * a.out_bstride + c;
+  const uint8_t* col = dw_smem + (size_t)tx * ROW_BYTES + cg * 8;
+
+  float p[3][4], q[3][4];
+#pragma unroll
+  for (int r = 0; r < TH + 2; ++r) {
+    if (r < TH) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { p[r % 3][i] = b1[i]; q[r % 3][i] = b2[i]; }
+    }
+    uint2 v1[3], v2[3];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const uint8_t* s = col + ((size_t)r * SW + kx) * ROW_BYTES;
+      v1[kx] = *reinterpret_cast<const uint2*>(s);
+      v2[kx] = *reinterpret_cast<const uint2*>(s + HALF_BYTES);
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int o = r - ky;
+      if (o >= 0 && o < TH) {
+        float* pp = p[o % 3];
+        float* qq = q[o % 3];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint2 wa = w1[ky * 3 + kx], wb = w2[ky * 3 + kx];
+          pp[0] = fma16<T>(lo16(v1[kx].x), lo16(wa.x), pp[0]);
+          pp[1] = fma16<T>(hi16(v1[kx].x), hi16(wa.x), pp[1]);
+          pp[2] = fma16<T>(lo16(v1[kx].y), lo16(wa.y), pp[2]);
+          pp[3] = fma16<T>(hi16(v1[kx].y), hi16(wa.y), pp[3]);
+          qq[0] = fma16<T>(lo16(v2[kx].x), lo16(wb.x), qq[0]);
+          qq[1] = fma16<T>(hi16(v2[kx].x), hi16(wb.x), qq[1]);
+          qq[2] = fma16<T>(lo16(v2[kx].y), lo16(wb.y), qq[2]);
+          qq[3] = fma16<T>(hi16(v2[kx].y), hi16(wb.y), qq[3]);
+        }
+      }
+    }
+    const int o = r - 2;
+    if (o >= 0) {
+      const int y = y0 + o;
+      if (c_ok && x_ok && y < a.H) {
+        const float* pp = p[o % 3];
+        const float* qq = q[o % 3];
+        uint2 ov;
+        ov.x = pack2<T>(gelu_erf(pp[0]) * qq[0], gelu_erf(pp[1]) * qq[1]);
+        ov.y = pack2<T>(gelu_erf(pp[2]) * qq[2], gelu_erf(pp[3]) * qq[3]);
+        *reinterpret_cast<uint2*>(outp + ((size_t)y * a.W + x) * a.out_pitch) = ov;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <class T>
+static int launch_dwconv(const PirDwConv* d, cudaStream_t stream) {
+  constexpr int TH = 8;
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0) return pir_fail(PIR_ERR_ARG, "pir_dwconv3x3: empty problem");
+  const int cin = d->gate ? 2 * d->C : d->C;
+  const int cmul = d->gate ? 4 : 8;
+  if ((d->C % cmul) || (cin % 8) || (d->in_pitch % 8) || (d->in_bstride % 8) || (d->out_pitch % cmul) ||
+      ((uintptr_t)d->in & 15) || ((uintptr_t)d->out & 15) || ((uintptr_t)d->w & 15))
+    return pir_fail(PIR_ERR_ARG, "pir_dwconv3x3: channel counts / pitches / pointers are not vector aligned");
+  if (d->gate && (d->C % 8)) return pir_fail(PIR_ERR_ARG, "pir_dwconv3x3: gated C must be a multiple of 8");
+
+  DwArgs a{};
+  a.H = d->H; a.W = d->W; a.C = d->C;
+  a.tiles_x = (d->W + kDwTW - 1) / kDwTW;
+  const int tiles_y = (d->H + TH - 1) / TH;
+  a.w = d->w; a.bias = d->bias; a.out = d->out; a.out_pitch = d->out_pitch; a.out_bstride = d->out_bstride;
+
+  const CUtensorMapDataType dt = T::kFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+  const uint64_t strides[3] = {(uint64_t)d->in_pitch * 2, (uint64_t)d->in_pitch * 2 * d->W, (uint64_t)d->in_bstride * 2};
+  CUtensorMap tm;
+  if (d->gate) {
+    const uint32_t box[4] = {32, kDwTW + 2, TH + 2, 1};
+    if (int e = pir_make_tmap(&tm, dt, 4, d->in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    const size_t smem = (size_t)2 * (TH + 2) * (kDwTW + 2) * 64 + 128;
+    static bool set[2] = {false, false};
+    if (!set[T::kFmt]) {
+      cudaFuncSetAttribute(dwconv_gate_kernel<T, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      set[T::kFmt] = true;
+    }
+    dim3 grid((unsigned)(a.tiles_x * tiles_y), (unsigned)((d->C + 31) / 32), (unsigned)d->B);
+    dwconv_gate_kernel<T, TH><<<grid, 256, smem, stream>>>(tm, a);
+  } else {
+    const bool use48 = (d->C % 64 != 0) && (d->C % 48 == 0);
+    const int cc = use48 ? 48 : 64;
+    const uint32_t box[4] = {(uint32_t)cc, kDwTW + 2, TH + 2, 1};
+    if (int e = pir_make_tmap(&tm, dt, 4, d->in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    const size_t smem = (size_t)(TH + 2) * (kDwTW + 2) * cc * 2 + 128;
+    dim3 grid((unsigned)(a.tiles_x * tiles_y), (unsigned)((d->C + cc - 1) / cc), (unsigned)d->B);
+    static bool set[2][2] = {{false, false}, {false, false}};
+    if (use48) {
+      if (!set[T::kFmt][0]) { cudaFuncSetAttribute(dwconv_plain_kernel<T, 6, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set[T::kFmt][0] = true; }
+      dwconv_plain_kernel<T, 6, TH><<<grid, 6 * 32, smem, stream>>>(tm, a);
+    } else {
+      if (!set[T::kFmt][1]) { cudaFuncSetAttribute(dwconv_plain_kernel<T, 8, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set[T::kFmt][1] = true; }
+      dwconv_plain_kernel<T, 8, TH><<<grid, 8 * 32, smem, stream>>>(tm, a);
+    }
+  }
+  return pir_check_launch("pir_dwconv3x3");
+}
+
+}  // namespace pir
+
+extern "C" int pir_dwconv3x3(const PirDwConv* d, void* stream) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_dwconv3x3: null descriptor");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return d->dtype == PIR_DTYPE_BF16 ? pir::launch_dwconv<pir::BF16>(d, s) : pir::launch_dwconv<pir::FP16>(d, s);
+}

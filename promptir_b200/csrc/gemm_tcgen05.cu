@@ -1,0 +1,375 @@
+// Pointwise (1x1) and dense 3x3 convolutions as tcgen05 GEMMs on sm_100a.
+//
+//   D[pixel, cout] = sum_{tap, cin} A[pixel + tap, cin] * Wt[cout, tap, cin]
+//
+// * activations are NHWC 16-bit (bf16 or fp16); a 128-pixel tile is the MMA M dimension, so one TMEM lane
+//   == one pixel and a thread of the epilogue owns a whole pixel row of output channels;
+// * A tiles arrive by TMA (3-D map {C, HW, B} for 1x1; 4-D map {C, W, H, B} for 3x3 -- the nine taps are nine
+//   shifted boxes, the zero padding is the TMA out-of-bounds fill), weights by TMA from a packed
+//   [batch][Cout][taps*Kpad] K-major matrix; both land in 128B-swizzled K-major stages;
+// * one elected thread issues tcgen05.mma (kind::f16, fp32 accumulate in TMEM), stages are recycled through
+//   mbarriers signalled by tcgen05.commit;
+// * WithBias/BiasFree LayerNorm of the input is folded in: the GEMM consumes the raw rows with weights
+//   pre-scaled by gamma, four otherwise idle epilogue warps accumulate per-pixel sum / sum-of-squares from the
+//   very same shared-memory stages, and the epilogue applies  rstd*(acc - mu*s[o]) + t[o];
+// * epilogue variants: residual add (in place is fine), PixelUnshuffle / PixelShuffle store addressing,
+//   fp32 NCHW "+ input image" for the last conv.
+//
+// Replaces, for the reference, nn.Conv2d(k=1) at net/model.py:88,92,111,113,294,296,303,305,313, the LayerNorm
+// at :60-63/:39-41 feeding them, nn.Conv2d(k=3) at :164,174,223,320 and PixelUnshuffle/PixelShuffle :165,175.
+#include "common.cuh"
+#include "host.h"
+
+namespace pir {
+
+constexpr int kGemmThreads = 192;        // warp0: TMA, warp1: TMEM alloc + MMA issue, warps 2-5: stats + epilogue
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;              // 64 x 16-bit = one 128-byte swizzle row
+constexpr int kMaxStages = 6;
+constexpr uint32_t kATileBytes = kBlockM * kBlockK * 2;
+
+struct GemmArgs {
+  int hw;            // pixels per image
+  int H, W;          // spatial dims of the A image (spatial mode)
+  int N, K;          // valid output channels, input channels per tap
+  int taps;          // 1 (pointwise) or 9 (3x3, pad 1)
+  int nkb;           // k-blocks per tap
+  int block_n;       // UMMA N of this launch
+  int stages;
+  int tmem_cols;
+  int spatial;       // 1: M tile = tile_h x tile_w rectangle (4-D TMA); 0: 128 consecutive pixels (3-D TMA)
+  int tile_w, tile_h, tiles_x;
+  int w_batched;     // weights differ per image (3rd TMA coordinate = image index)
+  int out_mode;      // PIR_OUT_*
+  int ln_mode;       // 0 none, 1 WithBias, 2 BiasFree
+  void* out;
+  long long out_pitch, out_bstride;
+  const void* res;
+  long long res_pitch, res_bstride;
+  const float* ln_s;     // [N] sum_c of the (rounded) gamma-scaled weights
+  const float* vec_t;    // [N] additive per-channel term (W.beta and/or conv bias), may be null
+  const float* img;      // fp32 NCHW input image (PIR_OUT_FINAL)
+};
+
+template <class T>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+  __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t bar_accum;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SW128 stages need 1024-B alignment
+  const uint32_t b_tile_bytes = (uint32_t)g.block_n * kBlockK * 2;
+  const uint32_t stage_bytes = kATileBytes + b_tile_bytes;                // block_n % 16 == 0 -> multiple of 1024? no: 2048
+  const int total_kb = g.taps * g.nkb;
+
+  const int n0 = blockIdx.x * g.block_n;
+  const int mt = blockIdx.y;
+  const int img_b = blockIdx.z;
+  int x0 = 0, y0 = 0;
+  if (g.spatial) {
+    y0 = (mt / g.tiles_x) * g.tile_h;
+    x0 = (mt % g.tiles_x) * g.tile_w;
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    const uint32_t empty_count = 1u + (g.ln_mode ? 4u : 0u);
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), empty_count);
+    }
+    mbar_init(smem_u32(&bar_accum), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)g.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================================== TMA producer ==========================================
+    // (whole warp walks the ring so it stays converged; lane 0 issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < total_kb; ++kb) {
+      mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+      if (lane == 0) {
+        const uint32_t full = smem_u32(&bar_full[stage]);
+        const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
+        const uint32_t b_dst = a_dst + kATileBytes;
+        mbar_expect_tx(full, stage_bytes);
+        const int tap = kb / g.nkb;
+        const int kc = (kb - tap * g.nkb) * kBlockK;
+        if (g.spatial) {
+          const int dy = (g.taps == 9) ? tap / 3 - 1 : 0;
+          const int dx = (g.taps == 9) ? tap % 3 - 1 : 0;
+          tma_load_4d(a_dst, &tmA, full, kc, x0 + dx, y0 + dy, img_b);
+        } else {
+          tma_load_3d(a_dst, &tmA, full, kc, mt * kBlockM, img_b);
+        }
+        tma_load_3d(b_dst, &tmB, full, kb * kBlockK, n0, g.w_batched ? img_b : 0);
+      }
+      __syncwarp();
+      if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ============================================
+    const uint32_t idesc = make_idesc_f16(T::kFmt, kBlockM, g.block_n, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < total_kb; ++kb) {
+      mbar_wait(smem_u32(&bar_full[stage]), phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_src = smem_base + (uint32_t)stage * stage_bytes;
+        const uint32_t b_src = a_src + kATileBytes;
+        const int kc = (kb % g.nkb) * kBlockK;
+        const int rem = g.K - kc;
+        const int ksteps = rem >= kBlockK ? 4 : (rem + 15) >> 4;           // skip all-zero K slices
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = make_sdesc_sw128(a_src + k * 32, 16, 1024);
+          const uint64_t bd = make_sdesc_sw128(b_src + k * 32, 16, 1024);
+          umma_f16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bar_empty[stage]));                          // frees the stage when the MMAs retire
+        if (kb == total_kb - 1) umma_commit(smem_u32(&bar_accum));         // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ============================ LN statistics (mainloop) + epilogue ============================
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;             // tile row == TMEM lane == pixel within the tile
+    float mu = 0.f, rstd = 1.f;
+    if (g.ln_mode) {
+      float s1 = 0.f, s2 = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        const uint8_t* a_src = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * stage_bytes + (size_t)row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 v = *reinterpret_cast<const uint4*>(a_src + ((j ^ (row & 7)) << 4));
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float a = unpack_lo<T>(w4[q]), b = unpack_hi<T>(w4[q]);
+            s1 += a + b;
+            s2 = fmaf(a, a, s2);
+            s2 = fmaf(b, b, s2);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_empty[stage]));
+        if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+      }
+      const float inv_k = 1.0f / (float)g.K;
+      mu = s1 * inv_k;
+      const float var = fmaxf(fmaf(s2, inv_k, -mu * mu), 0.f);
+      rstd = rsqrtf(var + 1e-5f);
+      if (g.ln_mode == 2) mu = 0.f;                  // BiasFree: variance about the mean, numerator not centred
+    }
+
+    // pixel coordinates of this row
+    int pix, py = 0, px = 0;
+    bool valid;
+    if (g.spatial) {
+      py = y0 + row / g.tile_w;
+      px = x0 + row % g.tile_w;
+      valid = (py < g.H) && (px < g.W);
+      pix = py * g.W + px;
+    } else {
+      pix = mt * kBlockM + row;
+      valid = pix < g.hw;
+    }
+
+    mbar_wait(smem_u32(&bar_accum), 0);
+    tc_fence_after();
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+    for (int c0 = 0; c0 < g.block_n; c0 += 16) {
+      uint32_t acc[16];
+      tmem_ld16(taddr_row + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      const int n = n0 + c0;
+      if (n >= g.N) break;                           // warp-uniform
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+      if (g.ln_mode) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float s = (n + i < g.N) ? __ldg(g.ln_s + n + i) : 0.f;
+          v[i] = rstd * fmaf(-mu, s, v[i]);
+        }
+      }
+      if (g.vec_t) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += (n + i < g.N) ? __ldg(g.vec_t + n + i) : 0.f;
+      }
+      if (!valid) {
+        // nothing to store for rows outside the image (keep the warp converged for the next tcgen05.ld)
+      } else if (g.out_mode == PIR_OUT_NHWC16) {
+        // N is a multiple of 8 for every 16-bit NHWC destination: 16-byte vectors
+        unsigned short* o = reinterpret_cast<unsigned short*>(g.out) + (size_t)img_b * g.out_bstride + (size_t)pix * g.out_pitch + n;
+        const unsigned short* r = g.res ? reinterpret_cast<const unsigned short*>(g.res) + (size_t)img_b * g.res_bstride + (size_t)pix * g.res_pitch + n : nullptr;
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          if (n + h8 * 8 < g.N) {
+            float* vv = v + h8 * 8;
+            if (r) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(r + h8 * 8);
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { vv[2 * q] += unpack_lo<T>(rw[q]); vv[2 * q + 1] += unpack_hi<T>(rw[q]); }
+            }
+            uint4 ov;
+            ov.x = pack2<T>(vv[0], vv[1]); ov.y = pack2<T>(vv[2], vv[3]);
+            ov.z = pack2<T>(vv[4], vv[5]); ov.w = pack2<T>(vv[6], vv[7]);
+            *reinterpret_cast<uint4*>(o + h8 * 8) = ov;
+          }
+        }
+      } else if (g.out_mode == PIR_OUT_UNSHUFFLE16) {
+        // PixelUnshuffle(2): out[b, y/2, x/2, 4n + 2(y&1) + (x&1)] = conv[b, y, x, n]
+        unsigned short* o = reinterpret_cast<unsigned short*>(g.out) + (size_t)img_b * g.out_bstride +
+                            ((size_t)(py >> 1) * (g.W >> 1) + (px >> 1)) * g.out_pitch + ((py & 1) * 2 + (px & 1));
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (n + i < g.N) o[(size_t)(n + i) * 4] = to16<T>(v[i]);
+      } else if (g.out_mode == PIR_OUT_SHUFFLE16) {
+        // PixelShuffle(2): out[b, 2y+i, 2x+j, c] = conv[b, y, x, 4c + 2i + j]
+        unsigned short* o = reinterpret_cast<unsigned short*>(g.out) + (size_t)img_b * g.out_bstride;
+        const size_t W2 = (size_t)g.W * 2;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int nn = n + i;
+          if (nn < g.N) {
+            const size_t dp = ((size_t)(2 * py + ((nn >> 1) & 1))) * W2 + (size_t)(2 * px + (nn & 1));
+            o[dp * g.out_pitch + (nn >> 2)] = to16<T>(v[i]);
+          }
+        }
+      } else if (g.out_mode == PIR_OUT_FINAL_NCHW32) {
+        float* o = reinterpret_cast<float*>(g.out) + (size_t)img_b * g.out_bstride;
+        const float* im = g.img + (size_t)img_b * g.out_bstride;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (n + i < g.N) {
+            const size_t off = (size_t)(n + i) * g.hw + pix;
+            o[off] = v[i] + im[off];
+          }
+      } else {  // PIR_OUT_NHWC32 (fp32 rows; used for checks and small fp32 consumers)
+        float* o = reinterpret_cast<float*>(g.out) + (size_t)img_b * g.out_bstride + (size_t)pix * g.out_pitch + n;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (n + i < g.N) o[i] = v[i];
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)g.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+template <class T>
+static int launch_gemm(const PirGemm* d, cudaStream_t stream) {
+  if (d->K <= 0 || d->N <= 0 || d->B <= 0 || d->H <= 0 || d->W <= 0) return pir_fail(PIR_ERR_ARG, "pir_gemm: empty problem");
+  if (d->taps != 1 && d->taps != 9) return pir_fail(PIR_ERR_ARG, "pir_gemm: taps must be 1 or 9");
+  if ((d->K % 8) || (d->a_pitch % 8) || (d->a_bstride % 8)) return pir_fail(PIR_ERR_ARG, "pir_gemm: A channels/pitch must be multiples of 8");
+  if (((uintptr_t)d->a & 15) || ((uintptr_t)d->w & 15)) return pir_fail(PIR_ERR_ARG, "pir_gemm: operands must be 16-byte aligned");
+  const bool out16 = d->out_mode == PIR_OUT_NHWC16;
+  if (out16 && ((d->N % 8) || (d->out_pitch % 8) || ((uintptr_t)d->out & 15))) return pir_fail(PIR_ERR_ARG, "pir_gemm: NHWC16 output needs N, pitch multiples of 8");
+  if (d->res && (!out16 || (d->res_pitch % 8) || ((uintptr_t)d->res & 15))) return pir_fail(PIR_ERR_ARG, "pir_gemm: residual requires NHWC16 output, aligned");
+  const bool needs_xy = d->out_mode == PIR_OUT_UNSHUFFLE16 || d->out_mode == PIR_OUT_SHUFFLE16;
+  if (d->out_mode == PIR_OUT_UNSHUFFLE16 && ((d->H | d->W) & 1)) return pir_fail(PIR_ERR_ARG, "pir_gemm: unshuffle needs even H, W");
+  if (d->out_mode == PIR_OUT_FINAL_NCHW32 && !d->img) return pir_fail(PIR_ERR_ARG, "pir_gemm: final mode needs the input image");
+  if (d->ln_mode && (d->taps != 1 || !d->ln_s)) return pir_fail(PIR_ERR_ARG, "pir_gemm: LN fold is for 1x1 with ln_s");
+
+  GemmArgs g{};
+  g.hw = d->H * d->W; g.H = d->H; g.W = d->W; g.N = d->N; g.K = d->K; g.taps = d->taps;
+  g.nkb = (d->K + kBlockK - 1) / kBlockK;
+  const int kpad = g.nkb * kBlockK;
+  const int total_kb = g.taps * g.nkb;
+  const int n16 = (d->N + 15) / 16 * 16;
+  const int max_bn = (d->K * d->taps >= 256) ? 256 : 128;
+  const int n_tiles = (n16 + max_bn - 1) / max_bn;
+  g.block_n = ((n16 + n_tiles - 1) / n_tiles + 15) / 16 * 16;
+  g.tmem_cols = pow2_ceil(g.block_n < 32 ? 32 : g.block_n);
+  g.stages = total_kb < 4 ? total_kb : 4;
+  g.spatial = (d->taps == 9 || needs_xy) ? 1 : 0;
+  g.w_batched = d->w_batched;
+  g.out_mode = d->out_mode; g.ln_mode = d->ln_mode;
+  g.out = d->out; g.out_pitch = d->out_pitch; g.out_bstride = d->out_bstride;
+  g.res = d->res; g.res_pitch = d->res_pitch; g.res_bstride = d->res_bstride;
+  g.ln_s = d->ln_s; g.vec_t = d->vec_t; g.img = d->img;
+
+  const CUtensorMapDataType dt = T::kFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tmA, tmB;
+  int m_tiles;
+  if (g.spatial) {
+    int tw = pow2_ceil(d->W);
+    if (tw > 128) tw = 128;
+    if (tw < 8) tw = 8;
+    g.tile_w = tw; g.tile_h = kBlockM / tw;
+    g.tiles_x = (d->W + tw - 1) / tw;
+    const int tiles_y = (d->H + g.tile_h - 1) / g.tile_h;
+    m_tiles = g.tiles_x * tiles_y;
+    const uint64_t dims[4] = {(uint64_t)d->K, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    const uint64_t strides[3] = {(uint64_t)d->a_pitch * 2, (uint64_t)d->a_pitch * 2 * d->W, (uint64_t)d->a_bstride * 2};
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)g.tile_w, (uint32_t)g.tile_h, 1};
+    if (int e = pir_make_tmap(&tmA, dt, 4, d->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  } else {
+    m_tiles = (g.hw + kBlockM - 1) / kBlockM;
+    const uint64_t dims[3] = {(uint64_t)d->K, (uint64_t)g.hw, (uint64_t)d->B};
+    const uint64_t strides[2] = {(uint64_t)d->a_pitch * 2, (uint64_t)d->a_bstride * 2};
+    const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)kBlockM, 1};
+    if (int e = pir_make_tmap(&tmA, dt, 3, d->a, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  }
+  {
+    const uint64_t ktot = (uint64_t)g.taps * kpad;
+    const uint64_t nb = d->w_batched ? (uint64_t)d->B : 1;
+    const uint64_t dims[3] = {ktot, (uint64_t)d->N, nb};
+    const uint64_t strides[2] = {ktot * 2, ktot * 2 * (uint64_t)d->N};
+    const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)g.block_n, 1};
+    if (int e = pir_make_tmap(&tmB, dt, 3, d->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  }
+
+  const size_t smem = (size_t)g.stages * (kATileBytes + (size_t)g.block_n * kBlockK * 2) + 1024;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[T::kFmt]) {
+    if (cudaFuncSetAttribute(gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return pir_fail(PIR_ERR_CUDA, "pir_gemm: cannot raise dynamic shared memory limit");
+    attr_set[T::kFmt] = true;
+  }
+  dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)d->B);
+  gemm_kernel<T><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, g);
+  return pir_check_launch("pir_gemm");
+}
+
+}  // namespace pir
+
+extern "C" int pir_gemm(const PirGemm* d, void* stream) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_gemm: null descriptor");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return d->dtype == PIR_DTYPE_BF16 ? pir::launch_gemm<pir::BF16>(d, s) : pir::launch_gemm<pir::FP16>(d, s);
+}

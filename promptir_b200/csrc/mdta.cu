@@ -1,0 +1,399 @@
+// MDTA (multi-DConv-head transposed attention) core for sm_100a.           Reference: net/model.py:121-137.
+//
+// The attention matrix of MDTA is c x c over CHANNELS (c = C / heads); the pixel axis (up to 65 536) is only
+// the contraction length.  So the work splits into
+//   (1) pir_mdta_gram     : G[b] = Q[b]^T K[b] over the pixels -- a split-K tcgen05 GEMM whose operands are
+//                           MN-major (channels contiguous) tiles of the NHWC qkv tensor, 64 pixels per stage,
+//                           fp32 accumulation in TMEM; the spare epilogue warps accumulate the squared L2
+//                           norms of every q / k channel from the same shared-memory stages.  Per-split
+//                           partials go to a workspace (no atomics -> deterministic).
+//   (2) pir_mdta_finalize : reduce partials, logits = G / (|q_i| |k_j|) * temperature, softmax over j,
+//                           then fold into project_out:  Wf[b][o][hc+j] = sum_i Wo[o][hc+i] A[b,h][i][j]
+//                           so that (attn @ v) and project_out become ONE pointwise GEMM on v (pir_gemm with
+//                           per-image weights) -- the attention output is never materialised.
+#include "common.cuh"
+#include "host.h"
+
+namespace pir {
+
+constexpr int kGramThreads = 192;          // warp0 TMA, warp1 MMA, warps 2-5 norms + epilogue
+constexpr int kGramPix = 64;               // pixels per stage (4 UMMA K-steps of 16)
+constexpr int kGroupBytes = kGramPix * 128;  // one 64-channel x 64-pixel SW128 tile
+constexpr int kGramMaxStages = 6;
+
+struct GramArgs {
+  int HW, C, heads;
+  int splits, chunk;           // pixels per split (multiple of 64)
+  int nblocks_n;               // column blocks (256 channels each)
+  int stages;
+  float* ws_gram;              // [B][splits][C][C]
+  float* ws_norm;              // [B][splits][2][C]
+};
+
+template <class T>
+__global__ void __launch_bounds__(kGramThreads)
+mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[kGramMaxStages];
+  __shared__ __align__(8) uint64_t bar_empty[kGramMaxStages];
+  __shared__ __align__(8) uint64_t bar_accum;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float red[4][6][64];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mb = blockIdx.x / g.nblocks_n;
+  const int nb = blockIdx.x % g.nblocks_n;
+  const int split = blockIdx.y;
+  const int b = blockIdx.z;
+  const int m0 = mb * 128;
+  const int n0 = nb * 256;
+  const int cdim = g.C / g.heads;
+  // skip blocks that do not touch any head's diagonal c x c block (block-uniform -> safe early exit)
+  {
+    const int m1 = min(m0 + 127, g.C - 1), n1 = min(n0 + 255, g.C - 1);
+    const int hlo = max(m0 / cdim, n0 / cdim), hhi = min(m1 / cdim, n1 / cdim);
+    if (hlo > hhi) return;
+  }
+  const int agroups = min(2, (g.C - m0 + 63) / 64);
+  const int bgroups = min(4, (g.C - n0 + 63) / 64);
+  const int block_n = bgroups * 64;
+  const uint32_t stage_bytes = (uint32_t)(agroups + bgroups) * kGroupBytes;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int p_begin = split * g.chunk;
+  const int p_end = min(p_begin + g.chunk, g.HW);
+  const int nst = p_end > p_begin ? (p_end - p_begin + kGramPix - 1) / kGramPix : 0;
+  const uint32_t tmem_cols = block_n <= 64 ? 64 : (block_n <= 128 ? 128 : 256);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 5);
+    }
+    mbar_init(smem_u32(&bar_accum), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_base_smem), tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < nst; ++it) {
+      mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+      if (lane == 0) {
+        const uint32_t full = smem_u32(&bar_full[stage]);
+        const uint32_t dst = smem_base + (uint32_t)stage * stage_bytes;
+        mbar_expect_tx(full, stage_bytes);
+        const int p = p_begin + it * kGramPix;
+        for (int gi = 0; gi < agroups; ++gi) tma_load_3d(dst + gi * kGroupBytes, &tmQKV, full, m0 + gi * 64, p, b);
+        for (int gi = 0; gi < bgroups; ++gi)
+          tma_load_3d(dst + (agroups + gi) * kGroupBytes, &tmQKV, full, g.C + n0 + gi * 64, p, b);
+      }
+      __syncwarp();
+      if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_f16(T::kFmt, 128, block_n, 1, 1);      // both operands MN-major
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < nst; ++it) {
+      mbar_wait(smem_u32(&bar_full[stage]), phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_src = smem_base + (uint32_t)stage * stage_bytes;
+        const uint32_t b_src = a_src + (uint32_t)agroups * kGroupBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {       // 16 pixels (two 8-row swizzle atoms = 2048 B) per MMA
+          const uint64_t ad = make_sdesc_sw128(a_src + k * 2048, kGroupBytes, 1024);
+          const uint64_t bd = make_sdesc_sw128(b_src + k * 2048, kGroupBytes, 1024);
+          umma_f16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bar_empty[stage]));
+        if (it == nst - 1) umma_commit(smem_u32(&bar_accum));
+      }
+      __syncwarp();
+      if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ---- squared norms: warp w takes pixel rows [16w', 16w'+16) of every group; lane owns 2 channels ----
+    const int wq = warp - 2;
+    float ss[6][2];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ss[i][0] = ss[i][1] = 0.f;
+    {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint8_t* base = smem_raw + (smem_base - smem_u32(smem_raw));
+      for (int it = 0; it < nst; ++it) {
+        mbar_wait(smem_u32(&bar_full[stage]), phase);
+        const uint8_t* st = base + (size_t)stage * stage_bytes;
+#pragma unroll
+        for (int gi = 0; gi < 6; ++gi) {
+          if (gi < agroups + bgroups) {
+#pragma unroll 4
+            for (int r = 0; r < 16; ++r) {
+              const int row = wq * 16 + r;
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(st + gi * kGroupBytes + row * 128 +
+                                                                    ((((lane >> 2) ^ (row & 7)) << 4) | ((lane & 3) << 2)));
+              const float x = unpack_lo<T>(v), y = unpack_hi<T>(v);
+              ss[gi][0] = fmaf(x, x, ss[gi][0]);
+              ss[gi][1] = fmaf(y, y, ss[gi][1]);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_empty[stage]));
+        if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+#pragma unroll
+    for (int gi = 0; gi < 6; ++gi) { red[wq][gi][lane * 2] = ss[gi][0]; red[wq][gi][lane * 2 + 1] = ss[gi][1]; }
+    asm volatile("bar.sync 1, 128;" ::: "memory");        // the four statistics warps only
+    {
+      float* nrm = g.ws_norm + ((size_t)(b * g.splits + split) * 2) * g.C;
+      const int t = threadIdx.x - 64;                     // 0..127
+      for (int e = t; e < (agroups + bgroups) * 64; e += 128) {
+        const int gi = e >> 6, ch = e & 63;
+        const float s = red[0][gi][ch] + red[1][gi][ch] + red[2][gi][ch] + red[3][gi][ch];
+        if (gi < agroups) {
+          const int cq = m0 + gi * 64 + ch;
+          if (nb == m0 / 256 && cq < g.C) nrm[cq] = s;          // the column block holding this row block's diagonal
+        } else {
+          const int ck = n0 + (gi - agroups) * 64 + ch;
+          if (mb == n0 / 128 && ck < g.C) nrm[g.C + ck] = s;    // the row block holding this column block's diagonal
+        }
+      }
+    }
+    // ---- epilogue: TMEM -> fp32 partial Gram ----
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int i = m0 + row;
+    float* gout = g.ws_gram + (size_t)(b * g.splits + split) * g.C * g.C + (size_t)i * g.C;
+    if (nst > 0) {
+      mbar_wait(smem_u32(&bar_accum), 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int c0 = 0; c0 < block_n; c0 += 16) {
+      uint32_t acc[16];
+      if (nst > 0) {
+        tmem_ld16(taddr_row + (uint32_t)c0, acc);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[q] = 0u;
+      }
+      if (i < g.C) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int j = n0 + c0 + q;
+          if (j < g.C) gout[j] = __uint_as_float(acc[q]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// finalize 1: softmax rows.  grid (heads, B), 256 threads; one warp per attention row.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mdta_softmax_kernel(const float* __restrict__ ws_gram, const float* __restrict__ ws_norm, const float* __restrict__ temperature,
+                    float* __restrict__ attn, int C, int heads, int splits) {
+  extern __shared__ float sm[];          // qn[c], kn[c]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int c = C / heads;
+  float* qn = sm;
+  float* kn = sm + c;
+  for (int e = threadIdx.x; e < 2 * c; e += blockDim.x) {
+    const int which = e / c, ch = e % c;
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += ws_norm[((size_t)(b * splits + sp) * 2 + which) * C + h * c + ch];
+    sm[e] = fmaxf(sqrtf(s), 1e-12f);     // F.normalize: x / max(||x||, eps)
+  }
+  __syncthreads();
+  const float temp = temperature[h];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < c; i += 8) {
+    // c <= 256 supported: up to 8 columns per lane
+    float v[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int j = lane + t * 32;
+      v[t] = -INFINITY;
+      if (j < c) {
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp)
+          s += ws_gram[(size_t)(b * splits + sp) * C * C + (size_t)(h * c + i) * C + h * c + j];
+        v[t] = s / (qn[i] * kn[j]) * temp;
+        mx = fmaxf(mx, v[t]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int j = lane + t * 32;
+      if (j < c) { v[t] = expf(v[t] - mx); sum += v[t]; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    float* arow = attn + ((size_t)(b * heads + h) * c + i) * c;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int j = lane + t * 32;
+      if (j < c) arow[j] = v[t] * inv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// finalize 2: Wf[b][o][h*c + j] = sum_i Wo[o][h*c + i] * A[b,h][i][j].  32x32 output tiles, K chunks of 32.
+// grid (ceil(C/32) o-tiles, heads * ceil(c/32) j-tiles, B), block (32, 8).
+// ------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+mdta_fold_kernel(const float* __restrict__ wo, const float* __restrict__ attn, unsigned short* __restrict__ wfold, int C,
+                 int heads, int kpad) {
+  __shared__ float sW[32][33];
+  __shared__ float sA[32][33];
+  const int c = C / heads;
+  const int jt_per_head = (c + 31) / 32;
+  const int h = blockIdx.y / jt_per_head;
+  const int j0 = (blockIdx.y % jt_per_head) * 32;
+  const int o0 = blockIdx.x * 32;
+  const int b = blockIdx.z;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const float* A = attn + (size_t)(b * heads + h) * c * c;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i0 = 0; i0 < c; i0 += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int rr = ty + r * 8;
+      const int o = o0 + rr, i = i0 + tx;
+      sW[rr][tx] = (o < C && i < c) ? wo[(size_t)o * C + h * c + i] : 0.f;
+      const int ii = i0 + rr, j = j0 + tx;
+      sA[rr][tx] = (ii < c && j < c) ? A[(size_t)ii * c + j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float a = sA[k][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(sW[ty + r * 8][k], a, acc[r]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int o = o0 + ty + r * 8, j = j0 + tx;
+    if (o < C && j < c) wfold[((size_t)b * C + o) * kpad + h * c + j] = to16<T>(acc[r]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+static int gram_nblocks_n(int C) { return (C + 255) / 256; }
+static int gram_nblocks_m(int C) { return (C + 127) / 128; }
+
+template <class T>
+static int launch_gram(const PirMdta* d, cudaStream_t stream) {
+  GramArgs g{};
+  g.HW = d->HW; g.C = d->C; g.heads = d->heads; g.splits = d->splits;
+  g.chunk = ((d->HW + d->splits - 1) / d->splits + kGramPix - 1) / kGramPix * kGramPix;
+  g.nblocks_n = gram_nblocks_n(d->C);
+  g.ws_gram = d->ws;
+  g.ws_norm = d->ws + (size_t)d->B * d->splits * d->C * d->C;
+  const int groups = (d->C >= 128 ? 2 : (d->C + 63) / 64) + (d->C >= 256 ? 4 : (d->C + 63) / 64);
+  const size_t stage_bytes = (size_t)groups * kGroupBytes;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > kGramMaxStages) stages = kGramMaxStages;
+  const int max_it = g.chunk / kGramPix;
+  if (stages > max_it) stages = max_it < 1 ? 1 : max_it;
+  g.stages = stages;
+  const size_t smem = stages * stage_bytes + 1024;
+
+  const CUtensorMapDataType dt = T::kFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const uint64_t dims[3] = {(uint64_t)3 * d->C, (uint64_t)d->HW, (uint64_t)d->B};
+  const uint64_t strides[2] = {(uint64_t)d->qkv_pitch * 2, (uint64_t)d->qkv_bstride * 2};
+  const uint32_t box[3] = {64, (uint32_t)kGramPix, 1};
+  CUtensorMap tm;
+  if (int e = pir_make_tmap(&tm, dt, 3, d->qkv, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  static bool set[2] = {false, false};
+  if (!set[T::kFmt]) {
+    if (cudaFuncSetAttribute(mdta_gram_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+      return pir_fail(PIR_ERR_CUDA, "pir_mdta_gram: cannot raise dynamic shared memory limit");
+    set[T::kFmt] = true;
+  }
+  dim3 grid((unsigned)(gram_nblocks_m(d->C) * g.nblocks_n), (unsigned)d->splits, (unsigned)d->B);
+  mdta_gram_kernel<T><<<grid, kGramThreads, smem, stream>>>(tm, g);
+  return pir_check_launch("pir_mdta_gram");
+}
+
+static int check_mdta(const PirMdta* d, const char* who) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "%s: null descriptor", who);
+  if (d->B <= 0 || d->HW <= 0 || d->C <= 0 || d->heads <= 0 || d->splits <= 0) return pir_fail(PIR_ERR_ARG, "%s: empty problem", who);
+  if (d->C % d->heads) return pir_fail(PIR_ERR_ARG, "%s: C must be divisible by heads", who);
+  if (d->C / d->heads > 256) return pir_fail(PIR_ERR_UNSUPPORTED, "%s: head dim > 256", who);
+  if ((d->C % 8) || (d->qkv_pitch % 8) || (d->qkv_bstride % 8) || ((uintptr_t)d->qkv & 15)) return pir_fail(PIR_ERR_ARG, "%s: qkv not 16-byte aligned", who);
+  if (!d->ws) return pir_fail(PIR_ERR_ARG, "%s: workspace missing", who);
+  return PIR_OK;
+}
+
+}  // namespace pir
+
+extern "C" int pir_mdta_splits(int32_t B, int32_t HW, int32_t C) {
+  const int blocks = B * ((C + 127) / 128) * ((C + 255) / 256);
+  int s = (2 * 148 + blocks - 1) / blocks;
+  const int cap = HW / 512 > 1 ? HW / 512 : 1;
+  if (s > cap) s = cap;
+  if (s > 64) s = 64;
+  return s < 1 ? 1 : s;
+}
+
+extern "C" int64_t pir_mdta_ws_floats(int32_t B, int32_t C, int32_t splits) {
+  // partial Grams + partial norms + attention matrices (upper bound: heads = 1)
+  return (int64_t)B * splits * ((int64_t)C * C + 2 * C) + (int64_t)B * C * C;
+}
+
+extern "C" int pir_mdta_gram(const PirMdta* d, void* stream) {
+  if (int e = pir::check_mdta(d, "pir_mdta_gram")) return e;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return d->dtype == PIR_DTYPE_BF16 ? pir::launch_gram<pir::BF16>(d, s) : pir::launch_gram<pir::FP16>(d, s);
+}
+
+extern "C" int pir_mdta_finalize(const PirMdta* d, void* stream) {
+  if (int e = pir::check_mdta(d, "pir_mdta_finalize")) return e;
+  if (!d->temperature || !d->wo || !d->wfold) return pir_fail(PIR_ERR_ARG, "pir_mdta_finalize: missing pointers");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int c = d->C / d->heads;
+  const float* ws_gram = d->ws;
+  const float* ws_norm = d->ws + (size_t)d->B * d->splits * d->C * d->C;
+  float* attn = d->ws + (size_t)d->B * d->splits * ((size_t)d->C * d->C + 2 * d->C);
+  pir::mdta_softmax_kernel<<<dim3(d->heads, d->B), 256, 2 * c * sizeof(float), s>>>(ws_gram, ws_norm, d->temperature, attn, d->C,
+                                                                                  d->heads, d->splits);
+  if (int e = pir_check_launch("pir_mdta_finalize(softmax)")) return e;
+  const int kpad = (d->C + 63) / 64 * 64;
+  dim3 grid((d->C + 31) / 32, d->heads * ((c + 31) / 32), d->B);
+  if (d->dtype == PIR_DTYPE_BF16)
+    pir::mdta_fold_kernel<pir::BF16><<<grid, dim3(32, 8), 0, s>>>(d->wo, attn, reinterpret_cast<unsigned short*>(d->wfold), d->C, d->heads, kpad);
+  else
+    pir::mdta_fold_kernel<pir::FP16><<<grid, dim3(32, 8), 0, s>>>(d->wo, attn, reinterpret_cast<unsigned short*>(d->wfold), d->C, d->heads, kpad);
+  return pir_check_launch("pir_mdta_finalize(fold)");
+}

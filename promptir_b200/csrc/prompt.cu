@@ -1,0 +1,264 @@
+// PromptGenBlock front half (net/model.py:226-232) and OverlapPatchEmbed (net/model.py:206) for sm_100a,
+// plus the fused tile blend of tiled inference (demo.py:43-47).  All three are small HBM/L2-bound SIMT kernels.
+#include "common.cuh"
+#include "host.h"
+
+namespace pir {
+
+// ------------------------------------------------------------------------------------------------------
+// (1) global average pool, stage 1: per-(image, pixel chunk) channel sums.  block = (C/8) x PL threads.
+// ------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+pool_partial_kernel(const unsigned short* __restrict__ x, long long pitch, long long bstride, int HW, int C, int chunk,
+                    float* __restrict__ partial) {
+  extern __shared__ float sred[];            // [PL][C]
+  const int groups = C >> 3;
+  const int PL = blockDim.x / groups;
+  const int cg = threadIdx.x % groups;
+  const int pl = threadIdx.x / groups;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * chunk;
+  const int p1 = min(p0 + chunk, HW);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (pl < PL) {
+    const unsigned short* xb = x + (size_t)b * bstride + cg * 8;
+    for (int p = p0 + pl; p < p1; p += PL) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)p * pitch));
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { acc[2 * q] += unpack_lo<T>(w4[q]); acc[2 * q + 1] += unpack_hi<T>(w4[q]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sred[pl * C + cg * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < PL; ++r) s += sred[r * C + c];
+    partial[((size_t)b * gridDim.x + blockIdx.x) * C + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// (2) linear + softmax over the L prompt components, weighted component sum, bilinear resize
+//     (align_corners = False), 16-bit NHWC store.  Each thread: one pixel x 8 channels.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kMaxL = 8;
+
+template <class T>
+__global__ void __launch_bounds__(256)
+prompt_mix_kernel(const float* __restrict__ partial, int nchunks, int HW, int C, const float* __restrict__ lin_w,
+                  const float* __restrict__ lin_b, int L, const float* __restrict__ prompt, int D, int S, int H, int W,
+                  unsigned short* __restrict__ out, long long pitch, long long bstride, float* __restrict__ weights_out) {
+  extern __shared__ float semb[];            // [C]
+  __shared__ float slog[kMaxL];
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < nchunks; ++k) s += partial[((size_t)b * nchunks + k) * C + c];
+    semb[c] = s / (float)HW;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < L) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(semb[c], lin_w[(size_t)warp * C + c], s);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) slog[warp] = s + lin_b[warp];
+  }
+  __syncthreads();
+  float wgt[kMaxL];
+  {
+    float mx = -INFINITY;
+    for (int l = 0; l < L; ++l) mx = fmaxf(mx, slog[l]);
+    float sum = 0.f;
+    for (int l = 0; l < L; ++l) { wgt[l] = expf(slog[l] - mx); sum += wgt[l]; }
+    const float inv = 1.0f / sum;
+    for (int l = 0; l < L; ++l) wgt[l] *= inv;
+  }
+  if (weights_out && blockIdx.x == 0 && threadIdx.x < L) weights_out[b * L + threadIdx.x] = wgt[threadIdx.x];
+
+  const int groups = D >> 3;
+  const long long total = (long long)H * W * groups;
+  const float sh = (float)S / (float)H, sw = (float)S / (float)W;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int dg = (int)(e % groups);
+    const int p = (int)(e / groups);
+    const int y = p / W, x = p % W;
+    float fy = fmaxf(sh * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * ((float)x + 0.5f) - 0.5f, 0.f);
+    const int y0 = min((int)fy, S - 1), x0 = min((int)fx, S - 1);
+    const int y1 = y0 + (y0 < S - 1 ? 1 : 0), x1 = x0 + (x0 < S - 1 ? 1 : 0);
+    const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const float* P = prompt + ((size_t)l * S * S) * D + dg * 8;
+      const float4* p00 = reinterpret_cast<const float4*>(P + ((size_t)y0 * S + x0) * D);
+      const float4* p01 = reinterpret_cast<const float4*>(P + ((size_t)y0 * S + x1) * D);
+      const float4* p10 = reinterpret_cast<const float4*>(P + ((size_t)y1 * S + x0) * D);
+      const float4* p11 = reinterpret_cast<const float4*>(P + ((size_t)y1 * S + x1) * D);
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const float4 a = __ldg(p00 + hlf), bq = __ldg(p01 + hlf), cq = __ldg(p10 + hlf), dq = __ldg(p11 + hlf);
+        const float wl = wgt[l];
+        acc[hlf * 4 + 0] = fmaf(wl, w00 * a.x + w01 * bq.x + w10 * cq.x + w11 * dq.x, acc[hlf * 4 + 0]);
+        acc[hlf * 4 + 1] = fmaf(wl, w00 * a.y + w01 * bq.y + w10 * cq.y + w11 * dq.y, acc[hlf * 4 + 1]);
+        acc[hlf * 4 + 2] = fmaf(wl, w00 * a.z + w01 * bq.z + w10 * cq.z + w11 * dq.z, acc[hlf * 4 + 2]);
+        acc[hlf * 4 + 3] = fmaf(wl, w00 * a.w + w01 * bq.w + w10 * cq.w + w11 * dq.w, acc[hlf * 4 + 3]);
+      }
+    }
+    uint4 ov;
+    ov.x = pack2<T>(acc[0], acc[1]); ov.y = pack2<T>(acc[2], acc[3]);
+    ov.z = pack2<T>(acc[4], acc[5]); ov.w = pack2<T>(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + (size_t)b * bstride + (size_t)p * pitch + dg * 8) = ov;
+  }
+}
+
+static int pool_chunks(int HW) {
+  int n = (HW + 255) / 256;
+  return n > 64 ? 64 : (n < 1 ? 1 : n);
+}
+
+template <class T>
+static int launch_prompt(const PirPrompt* d, cudaStream_t s) {
+  const int HW = d->H * d->W;
+  const int nchunks = pool_chunks(HW);
+  const int chunk = (HW + nchunks - 1) / nchunks;
+  const int groups = d->C / 8;
+  if (groups > 256) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_prompt_gen: C > 2048");
+  const int PL = 256 / groups;
+  const int threads = PL * groups;
+  pool_partial_kernel<T><<<dim3(nchunks, d->B), threads, (size_t)PL * d->C * sizeof(float), s>>>(
+      reinterpret_cast<const unsigned short*>(d->x), d->x_pitch, d->x_bstride, HW, d->C, chunk, d->ws);
+  if (int e = pir_check_launch("pir_prompt_gen(pool)")) return e;
+  const long long total = (long long)HW * (d->D / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  prompt_mix_kernel<T><<<dim3(blocks, d->B), 256, d->C * sizeof(float), s>>>(
+      d->ws, nchunks, HW, d->C, d->lin_w, d->lin_b, d->L, d->prompt, d->D, d->S, d->H, d->W,
+      reinterpret_cast<unsigned short*>(d->out), d->out_pitch, d->out_bstride, d->weights_out);
+  return pir_check_launch("pir_prompt_gen(mix)");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// OverlapPatchEmbed: dense 3x3 (pad 1) from the fp32 NCHW image to 16-bit NHWC.  K = 9*Cin = 27: SIMT.
+// block = (Cout/8) x 32 pixels.
+// ------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias, int H, int W,
+                   int Cin, int Cout, unsigned short* __restrict__ out, long long pitch, long long bstride) {
+  extern __shared__ float sw[];              // [Cin*9][Cout]
+  const int groups = Cout >> 3;
+  for (int e = threadIdx.x; e < Cin * 9 * Cout; e += blockDim.x) {
+    const int co = e % Cout, k = e / Cout;   // k = ci*9 + tap
+    sw[e] = w[(size_t)co * Cin * 9 + k];
+  }
+  __syncthreads();
+  const int g = threadIdx.x % groups;
+  const int pl = threadIdx.x / groups;
+  const int ppb = blockDim.x / groups;
+  const int b = blockIdx.y;
+  const long long p = (long long)blockIdx.x * ppb + pl;
+  if (p >= (long long)H * W) return;
+  const int y = (int)(p / W), x = (int)(p % W);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = bias ? bias[g * 8 + i] : 0.f;
+  const float* ib = img + (size_t)b * Cin * H * W;
+  for (int ci = 0; ci < Cin; ++ci) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(ib + ((size_t)ci * H + yy) * W + xx) : 0.f;
+      const float* ws = sw + (size_t)(ci * 9 + t) * Cout + g * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, ws[i], acc[i]);
+    }
+  }
+  uint4 ov;
+  ov.x = pack2<T>(acc[0], acc[1]); ov.y = pack2<T>(acc[2], acc[3]);
+  ov.z = pack2<T>(acc[4], acc[5]); ov.w = pack2<T>(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(out + (size_t)b * bstride + (size_t)p * pitch + g * 8) = ov;
+}
+
+template <class T>
+static int launch_patch_embed(const PirPatchEmbed* d, cudaStream_t s) {
+  const int groups = d->Cout / 8;
+  const int ppb = 256 / groups;
+  const int threads = ppb * groups;
+  const long long HW = (long long)d->H * d->W;
+  const size_t smem = (size_t)d->Cin * 9 * d->Cout * sizeof(float);
+  if (smem > 48 * 1024) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_patch_embed: weight does not fit 48 KB of shared memory");
+  patch_embed_kernel<T><<<dim3((unsigned)((HW + ppb - 1) / ppb), d->B), threads, smem, s>>>(
+      d->img, d->w, d->bias, d->H, d->W, d->Cin, d->Cout, reinterpret_cast<unsigned short*>(d->out), d->out_pitch, d->out_bstride);
+  return pir_check_launch("pir_patch_embed");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// tile blend (demo.py:36-47): out = clamp(sum of covering tiles / hit count, 0, 1), tiles summed in the
+// reference's loop order (rows outer, columns inner) -> deterministic, no atomics.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tile_blend_kernel(const float* __restrict__ tiles, int ny, int nx, const int* __restrict__ ys, const int* __restrict__ xs,
+                  int C, int th, int tw, float* __restrict__ out, int H, int W) {
+  const long long n = (long long)C * H * W;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(e % W);
+    const int y = (int)((e / W) % H);
+    const int c = (int)(e / ((long long)W * H));
+    float acc = 0.f, cnt = 0.f;
+    for (int iy = 0; iy < ny; ++iy) {
+      const int ly = y - ys[iy];
+      if (ly < 0 || ly >= th) continue;
+      for (int ix = 0; ix < nx; ++ix) {
+        const int lx = x - xs[ix];
+        if (lx < 0 || lx >= tw) continue;
+        acc += tiles[(((size_t)(iy * nx + ix) * C + c) * th + ly) * tw + lx];
+        cnt += 1.f;
+      }
+    }
+    out[e] = fminf(fmaxf(acc / cnt, 0.f), 1.f);
+  }
+}
+
+}  // namespace pir
+
+extern "C" int64_t pir_prompt_ws_floats(int32_t B, int32_t HW, int32_t C) {
+  return (int64_t)B * pir::pool_chunks(HW) * C;
+}
+
+extern "C" int pir_prompt_gen(const PirPrompt* d, void* stream) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_prompt_gen: null descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0) return pir_fail(PIR_ERR_ARG, "pir_prompt_gen: empty problem");
+  if ((d->C % 8) || (d->D % 8) || (d->x_pitch % 8) || (d->out_pitch % 8) || ((uintptr_t)d->x & 15) || ((uintptr_t)d->out & 15) ||
+      ((uintptr_t)d->prompt & 15))
+    return pir_fail(PIR_ERR_ARG, "pir_prompt_gen: channels / pitches / pointers are not vector aligned");
+  if (d->L < 1 || d->L > pir::kMaxL) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_prompt_gen: 1 <= L <= 8");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return d->dtype == PIR_DTYPE_BF16 ? pir::launch_prompt<pir::BF16>(d, s) : pir::launch_prompt<pir::FP16>(d, s);
+}
+
+extern "C" int pir_patch_embed(const PirPatchEmbed* d, void* stream) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_patch_embed: null descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Cin <= 0) return pir_fail(PIR_ERR_ARG, "pir_patch_embed: empty problem");
+  if ((d->Cout % 8) || d->Cout > 2048 || (d->out_pitch % 8) || ((uintptr_t)d->out & 15)) return pir_fail(PIR_ERR_ARG, "pir_patch_embed: Cout / pitch not vector aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return d->dtype == PIR_DTYPE_BF16 ? pir::launch_patch_embed<pir::BF16>(d, s) : pir::launch_patch_embed<pir::FP16>(d, s);
+}
+
+extern "C" int pir_tile_blend(const float* tiles, int32_t ny, int32_t nx, const int32_t* ys, const int32_t* xs, int32_t C,
+                              int32_t th, int32_t tw, float* out, int32_t H, int32_t W, void* stream) {
+  if (!tiles || !ys || !xs || !out || ny <= 0 || nx <= 0 || C <= 0) return pir_fail(PIR_ERR_ARG, "pir_tile_blend: bad arguments");
+  const long long n = (long long)C * H * W;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pir::tile_blend_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(tiles, ny, nx, ys, xs, C, th, tw, out, H, W);
+  return pir_check_launch("pir_tile_blend");
+}
