@@ -357,7 +357,7 @@ static int launch_gemm(const PirGemm* d, cudaStream_t stream) {
   const size_t smem = (size_t)g.stages * (kATileBytes + (size_t)g.block_n * kBlockK * 2) + 1024;
   static bool attr_set[2] = {false, false};
   if (!attr_set[T::kFmt]) {
-    if (cudaFuncSetAttribute(gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
       return pir_fail(PIR_ERR_CUDA, "pir_gemm: cannot raise dynamic shared memory limit");
     attr_set[T::kFmt] = true;
   }
