@@ -311,3 +311,44 @@ class Engine:
     def kernels_per_forward(self) -> int:
         per = {"mdta_finalize": 2, "prompt": 2}
         return sum(per.get(r["kind"], 1) for r in self.ops)
+
+
+# ----------------------------------------------------------------------------------------------------
+# algorithmic cost of an op record (for roofline accounting; DESIGN.md states the per-unit figures)
+# ----------------------------------------------------------------------------------------------------
+def _numel(t) -> int:
+    return 0 if t is None else int(t.numel())
+
+
+def op_cost(rec: dict):
+    """-> (algorithmic HBM bytes, FLOPs) of one launch: every operand read once, every result written once."""
+    kind = rec["kind"]
+    if kind == "gemm":
+        a, out = rec["a"], rec["out"]
+        B, H, W, K = a.shape
+        n, taps = rec["n"], rec["taps"]
+        wbytes = (B if rec["w_batched"] else 1) * n * taps * K * 2
+        by = a.numel() * a.element_size() + _numel(out) * out.element_size() + wbytes
+        if rec["res"] is not None:
+            by += _numel(rec["res"]) * rec["res"].element_size()
+        if rec["img"] is not None:
+            by += _numel(rec["img"]) * 4
+        return by, 2.0 * B * H * W * K * taps * n
+    if kind == "dwconv":
+        x, out = rec["x"], rec["out"]
+        return x.numel() * 2 + out.numel() * 2 + rec["w"].numel() * 2, 18.0 * x.numel()
+    if kind == "mdta_gram":
+        q = rec["qkv"]
+        B, H, W, c3 = q.shape
+        c = c3 // 3
+        return B * H * W * 2 * c * 2, 2.0 * B * H * W * c * (c // rec["heads"])
+    if kind == "mdta_finalize":
+        q = rec["qkv"]
+        B, c = q.shape[0], q.shape[3] // 3
+        return B * c * c * (4 * rec["splits"] + 2) + c * c * 4, 2.0 * B * c * c * (c // rec["heads"])
+    if kind == "prompt":
+        x, out = rec["x"], rec["out"]
+        return x.numel() * 2 + out.numel() * 2 + rec["prompt"].numel() * 4, 10.0 * out.numel() * 5
+    if kind == "patch_embed":
+        return rec["img"].numel() * 4 + rec["out"].numel() * 2, 2.0 * rec["out"].numel() * 27
+    raise KeyError(kind)

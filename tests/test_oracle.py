@@ -1,0 +1,74 @@
+"""CPU: the oracle against the golden vectors produced by the REAL reference (oracle/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import promptir_oracle as O
+from promptir_b200 import PromptIR
+
+
+@pytest.fixture(scope="module")
+def seeded():
+    torch.manual_seed(0)
+    m = PromptIR(decoder=True).eval()
+    return m, {k: v.detach() for k, v in m.state_dict().items()}
+
+
+def test_seed_identical_parameters(seeded, golden_dir):
+    """Same constructor order as net/model.py:260-320 -> same RNG stream -> identical tensors (digests from the reference)."""
+    meta = json.load(open(os.path.join(golden_dir, "params_seed0.json")))
+    _, sd = seeded
+    assert list(sd.keys()) == meta["keys"] and len(sd) == 548
+    assert sum(v.numel() for v in sd.values()) == meta["n_params"] == 35592263
+    for k, v in sd.items():
+        d = meta["params"][k]
+        assert list(v.shape) == d["shape"], k
+        f = v.double().flatten()
+        assert abs(f.sum().item() - d["sum"]) <= 1e-9 * max(1, abs(d["sum"])), k
+        assert f[0].item() == d["first"] and f[-1].item() == d["last"], k
+
+
+@pytest.mark.parametrize("case", ["a32", "a40x24", "a64", "cfg1_128"])
+def test_oracle_matches_reference_outputs(seeded, golden_dir, case):
+    g = np.load(os.path.join(golden_dir, "forward_seed0.npz"))
+    taps = {}
+    with torch.no_grad():
+        y = O.promptir_forward(seeded[1], torch.from_numpy(g[case + "_in"]), taps=taps)
+    assert (y - torch.from_numpy(g[case + "_out"])).abs().max().item() < 5e-6
+    meta = json.load(open(os.path.join(golden_dir, "taps_seed0.json")))[case]
+    for name, d in meta.items():
+        t = taps[name].double()
+        assert list(t.shape) == d["shape"], name
+        flat = t.flatten()
+        idx = torch.linspace(0, flat.numel() - 1, 64).long()
+        assert (flat[idx] - torch.tensor(d["sample"], dtype=torch.float64)).abs().max().item() < 2e-5, name
+
+
+def test_oracle_biasfree_with_bias(golden_dir):
+    g = np.load(os.path.join(golden_dir, "forward_seed3_biasfree.npz"))
+    torch.manual_seed(3)
+    m = PromptIR(decoder=True, bias=True, LayerNorm_type="BiasFree").eval()
+    arch = O.ArchSpec(layernorm_type="BiasFree")
+    with torch.no_grad():
+        y = O.promptir_forward({k: v.detach() for k, v in m.state_dict().items()}, torch.from_numpy(g["x"]), arch)
+    assert (y - torch.from_numpy(g["y"])).abs().max().item() < 5e-6
+
+
+def test_pad_and_tile_helpers_match_demo(seeded, golden_dir):
+    g = np.load(os.path.join(golden_dir, "forward_seed0.npz"))
+    x = torch.from_numpy(g["tile_in"])
+    xp, h, w = O.pad_to_multiple(x, 8)
+    assert (h, w) == (70, 52) and torch.equal(xp, torch.from_numpy(g["tile_padded"]))
+    with torch.no_grad():
+        out = O.tiled_restore(lambda t: O.promptir_forward(seeded[1], t), xp, tile=32, overlap=8)
+    assert (out - torch.from_numpy(g["tile_out"])).abs().max().item() < 5e-6
+    assert O.tile_origins(2160, 256, 32) == list(range(0, 1904, 224)) + [1904] and len(O.tile_origins(3840, 256, 32)) == 17
+
+
+def test_synthetic_batch_is_deterministic():
+    a, ca = O.synthetic_batch(5, 32, 32, seed=4)
+    b, cb = O.synthetic_batch(5, 32, 32, seed=4)
+    assert torch.equal(a, b) and torch.equal(ca, cb) and 0 <= a.min() and a.max() <= 1
