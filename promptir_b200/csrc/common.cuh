@@ -143,6 +143,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr) : "memory");
 }
+// 32 lanes x 64 consecutive fp32 columns -> 64 registers per thread
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+        "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+        "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]),
+        "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]),
+        "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Instruction descriptor, kind::f16, fp32 accumulate.  fmt: 0=f16 1=bf16.  major: 0=K-major 1=MN-major.
@@ -181,21 +196,21 @@ __device__ __forceinline__ bool elect_one() {
 // ---------------------------------------------------------------------------------------------------
 // misc math
 // ---------------------------------------------------------------------------------------------------
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7 + intrinsic error); 2 MUFU + ~10 FMA-class ops
-__device__ __forceinline__ float erf_fast(float x) {
+// exact-erf GELU via Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7):  with u = |x|/sqrt2, t = 1/(1 + p u),
+//   erf(u) = 1 - P(t) exp(-u^2)   =>   gelu(x) = 0.5 x (1 + erf(x/sqrt2)) = relu(x) - |x| * (0.5 P(t) exp(-x^2/2)).
+// 13 instructions, two of them MUFU (rcp.approx, ex2.approx); the 0.5 is folded into the coefficients.
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
   p *= t;
-  const float e = __expf(-ax * ax);
-  const float r = fmaf(-p, e, 1.0f);
-  return copysignf(r, x);
-}
-__device__ __forceinline__ float gelu_erf(float x) {          // 0.5 x (1 + erf(x / sqrt 2))
-  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f));
+  const float e = ex2_approx(x * x * (-0.5f * 1.4426950408889634f));
+  return fmaf(-ax, p * e, fmaxf(x, 0.0f));
 }
 
 }  // namespace pir

@@ -17,6 +17,8 @@
 //
 // Replaces, for the reference, nn.Conv2d(k=1) at net/model.py:88,92,111,113,294,296,303,305,313, the LayerNorm
 // at :60-63/:39-41 feeding them, nn.Conv2d(k=3) at :164,174,223,320 and PixelUnshuffle/PixelShuffle :165,175.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -371,5 +373,12 @@ static int launch_gemm(const PirGemm* d, cudaStream_t stream) {
 extern "C" int pir_gemm(const PirGemm* d, void* stream) {
   if (!d) return pir_fail(PIR_ERR_ARG, "pir_gemm: null descriptor");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // pointwise convs with 16-bit NHWC output (K1/K4/K5/K7/reduce) take the persistent kernel; PIR_GEMM_SIMPLE=1
+  // forces the one-tile-per-CTA kernel below for A/B measurements
+  static const bool simple = getenv("PIR_GEMM_SIMPLE") != nullptr;
+  if (!simple && d->taps == 1 && d->out_mode == PIR_OUT_NHWC16 && d->K > 0 && d->N > 0 && d->B > 0 && d->H > 0 && d->W > 0 &&
+      (d->K % 8) == 0 && (d->a_pitch % 8) == 0 && (d->a_bstride % 8) == 0 && ((uintptr_t)d->a & 15) == 0 && ((uintptr_t)d->w & 15) == 0 &&
+      (!d->ln_mode || d->ln_s))
+    return pir::pir_gemm_pw(d, s);
   return d->dtype == PIR_DTYPE_BF16 ? pir::launch_gemm<pir::BF16>(d, s) : pir::launch_gemm<pir::FP16>(d, s);
 }

@@ -14,3 +14,6 @@ int pir_check_launch(const char* what);
 // dims/box have `rank` entries, strides_bytes has rank-1 entries (dimension 0 is contiguous).
 int pir_make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
+// persistent pointwise GEMM (gemm_pw.cu): taps == 1, NHWC16 output
+namespace pir { int pir_gemm_pw(const PirGemm* d, cudaStream_t stream); }

@@ -359,12 +359,20 @@ static int check_mdta(const PirMdta* d, const char* who) {
 }  // namespace pir
 
 extern "C" int pir_mdta_splits(int32_t B, int32_t HW, int32_t C) {
-  const int blocks = B * ((C + 127) / 128) * ((C + 255) / 256);
-  int s = (2 * 148 + blocks - 1) / blocks;
-  const int cap = HW / 512 > 1 ? HW / 512 : 1;
-  if (s > cap) s = cap;
-  if (s > 64) s = 64;
-  return s < 1 ? 1 : s;
+  // The Gram kernel runs one CTA per SM (its TMA ring fills shared memory), so pick the split-K factor that
+  // fills whole waves of 148 CTAs best; each split keeps at least 256 pixels.
+  const int units = B * ((C + 127) / 128) * ((C + 255) / 256);          // CTAs per split (upper bound)
+  const int cap = HW / 256 > 1 ? (HW / 256 > 64 ? 64 : HW / 256) : 1;
+  int best = 1;
+  double best_u = 0.0;
+  for (int s = 1; s <= cap; ++s) {
+    const int total = units * s;
+    if (total > 2 * 148 && s > 1) break;
+    const int waves = (total + 147) / 148;
+    const double u = (double)total / (148.0 * waves);
+    if (u > best_u + 1e-9) { best_u = u; best = s; }
+  }
+  return best;
 }
 
 extern "C" int64_t pir_mdta_ws_floats(int32_t B, int32_t C, int32_t splits) {

@@ -78,7 +78,8 @@ def main():
     print(f"eager {te:.3f} ms ({mp / te * 1e3:.1f} MP/s)   graph {tg:.3f} ms ({mp / tg * 1e3:.1f} MP/s)")
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/time_forward.json", "w") as f:
-        json.dump({"B": B, "H": H, "W": W, "eager_ms": te, "graph_ms": tg, "by_tag_ms": dict(agg)}, f)
+        json.dump({"B": B, "H": H, "W": W, "eager_ms": te, "graph_ms": tg, "by_tag_ms": dict(agg),
+                   "ops": [{"i": i, "ms": r[0], "tag": r[1], "shape": list(r[2]), "bytes": r[3]} for i, r in enumerate(rows)]}, f)
 
 
 if __name__ == "__main__":
