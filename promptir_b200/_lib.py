@@ -36,6 +36,13 @@ class PirDwConv(C.Structure):
                 ("out", vp), ("out_pitch", i64), ("out_bstride", i64)]
 
 
+class PirPwDw(C.Structure):
+    _fields_ = [("dtype", i32), ("gate", i32), ("ln_mode", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32), ("N", i32),
+                ("a", vp), ("a_pitch", i64), ("a_bstride", i64),
+                ("w", vp), ("ln_s", vp), ("vec_t", vp), ("dw_w", vp), ("dw_bias", vp),
+                ("out", vp), ("out_pitch", i64), ("out_bstride", i64)]
+
+
 class PirMdta(C.Structure):
     _fields_ = [("dtype", i32), ("B", i32), ("HW", i32), ("C", i32), ("heads", i32), ("splits", i32),
                 ("qkv", vp), ("qkv_pitch", i64), ("qkv_bstride", i64),
@@ -63,6 +70,8 @@ SYMBOLS = {
     "pir_check_device": (i32, []),
     "pir_gemm": (i32, [C.POINTER(PirGemm), vp]),
     "pir_dwconv3x3": (i32, [C.POINTER(PirDwConv), vp]),
+    "pir_pwdw_supported": (i32, [i32, i32, i32]),
+    "pir_pwdw": (i32, [C.POINTER(PirPwDw), vp]),
     "pir_mdta_splits": (i32, [i32, i32, i32]),
     "pir_mdta_ws_floats": (i64, [i32, i32, i32]),
     "pir_mdta_gram": (i32, [C.POINTER(PirMdta), vp]),

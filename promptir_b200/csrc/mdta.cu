@@ -26,7 +26,7 @@ struct GramArgs {
   int splits, chunk;           // pixels per split (multiple of 64)
   int nblocks_n;               // column blocks (256 channels each)
   int stages;
-  float* ws_gram;              // [B][splits][C][C]
+  float* ws_gram;              // [B][splits][C][c]  (c = C / heads: only the heads' diagonal blocks)
   float* ws_norm;              // [B][splits][2][C]
 };
 
@@ -123,11 +123,16 @@ mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
       if (++stage == g.stages) { stage = 0; phase ^= 1u; }
     }
   } else {
-    // ---- squared norms: warp w takes pixel rows [16w', 16w'+16) of every group; lane owns 2 channels ----
+    // ---- squared norms: warp w takes pixel rows [16w', 16w'+16) of every group.  A lane owns one 16-byte chunk
+    //      (8 channels) of rows 4i + lane/8: all LDS.128 of a stage are issued before the FMAs that consume them ----
     const int wq = warp - 2;
-    float ss[6][2];
+    const int rsub = lane >> 3, ch8 = lane & 7;
+    const int ngroups = agroups + bgroups;
+    float ss[6][8];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) ss[i][0] = ss[i][1] = 0.f;
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss[i][e] = 0.f;
     {
       int stage = 0;
       uint32_t phase = 0;
@@ -135,17 +140,29 @@ mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
       for (int it = 0; it < nst; ++it) {
         mbar_wait(smem_u32(&bar_full[stage]), phase);
         const uint8_t* st = base + (size_t)stage * stage_bytes;
+        uint4 v[6][4];
 #pragma unroll
         for (int gi = 0; gi < 6; ++gi) {
-          if (gi < agroups + bgroups) {
-#pragma unroll 4
-            for (int r = 0; r < 16; ++r) {
-              const int row = wq * 16 + r;
-              const uint32_t v = *reinterpret_cast<const uint32_t*>(st + gi * kGroupBytes + row * 128 +
-                                                                    ((((lane >> 2) ^ (row & 7)) << 4) | ((lane & 3) << 2)));
-              const float x = unpack_lo<T>(v), y = unpack_hi<T>(v);
-              ss[gi][0] = fmaf(x, x, ss[gi][0]);
-              ss[gi][1] = fmaf(y, y, ss[gi][1]);
+          if (gi < ngroups) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = wq * 16 + i * 4 + rsub;
+              v[gi][i] = *reinterpret_cast<const uint4*>(st + gi * kGroupBytes + row * 128 + ((ch8 ^ (row & 7)) << 4));
+            }
+          }
+        }
+#pragma unroll
+        for (int gi = 0; gi < 6; ++gi) {
+          if (gi < ngroups) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t w4[4] = {v[gi][i].x, v[gi][i].y, v[gi][i].z, v[gi][i].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x = unpack_lo<T>(w4[e]), y = unpack_hi<T>(w4[e]);
+                ss[gi][2 * e] = fmaf(x, x, ss[gi][2 * e]);
+                ss[gi][2 * e + 1] = fmaf(y, y, ss[gi][2 * e + 1]);
+              }
             }
           }
         }
@@ -155,12 +172,20 @@ mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
       }
     }
 #pragma unroll
-    for (int gi = 0; gi < 6; ++gi) { red[wq][gi][lane * 2] = ss[gi][0]; red[wq][gi][lane * 2 + 1] = ss[gi][1]; }
+    for (int gi = 0; gi < 6; ++gi) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = ss[gi][e];
+        t += __shfl_xor_sync(0xffffffffu, t, 8);
+        t += __shfl_xor_sync(0xffffffffu, t, 16);
+        if (rsub == 0) red[wq][gi][ch8 * 8 + e] = t;
+      }
+    }
     asm volatile("bar.sync 1, 128;" ::: "memory");        // the four statistics warps only
     {
       float* nrm = g.ws_norm + ((size_t)(b * g.splits + split) * 2) * g.C;
       const int t = threadIdx.x - 64;                     // 0..127
-      for (int e = t; e < (agroups + bgroups) * 64; e += 128) {
+      for (int e = t; e < ngroups * 64; e += 128) {
         const int gi = e >> 6, ch = e & 63;
         const float s = red[0][gi][ch] + red[1][gi][ch] + red[2][gi][ch] + red[3][gi][ch];
         if (gi < agroups) {
@@ -172,17 +197,26 @@ mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
         }
       }
     }
-    // ---- epilogue: TMEM -> fp32 partial Gram ----
+    // ---- epilogue: TMEM -> fp32 partial Gram, only the c x c diagonal block of the row's head is kept:
+    //      ws_gram[b][split][i][j - head(i)*c]  ----
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int i = m0 + row;
-    float* gout = g.ws_gram + (size_t)(b * g.splits + split) * g.C * g.C + (size_t)i * g.C;
+    const int hi = i / cdim;
+    const int jlo = hi * cdim, jhi = jlo + cdim;                       // this row's valid column range
+    float* gout = g.ws_gram + ((size_t)(b * g.splits + split) * g.C + (size_t)i) * cdim;
+    // columns any row of this warp needs (warp-uniform, so the aligned TMEM loads stay converged)
+    const int wlo = ((m0 + quarter * 32) / cdim) * cdim;
+    const int whi = (min(m0 + quarter * 32 + 31, g.C - 1) / cdim + 1) * cdim;
     if (nst > 0) {
       mbar_wait(smem_u32(&bar_accum), 0);
       tc_fence_after();
     }
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool vec4 = (cdim & 3) == 0;
     for (int c0 = 0; c0 < block_n; c0 += 16) {
+      const int j0 = n0 + c0;
+      if (j0 + 16 <= wlo || j0 >= whi || m0 + quarter * 32 >= g.C) continue;      // warp-uniform
       uint32_t acc[16];
       if (nst > 0) {
         tmem_ld16(taddr_row + (uint32_t)c0, acc);
@@ -192,10 +226,20 @@ mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
         for (int q = 0; q < 16; ++q) acc[q] = 0u;
       }
       if (i < g.C) {
+        if (vec4) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int j = n0 + c0 + q;
-          if (j < g.C) gout[j] = __uint_as_float(acc[q]);
+          for (int q = 0; q < 16; q += 4) {
+            const int j = j0 + q;
+            if (j >= jlo && j + 3 < jhi)
+              *reinterpret_cast<float4*>(gout + (j - jlo)) = make_float4(__uint_as_float(acc[q]), __uint_as_float(acc[q + 1]),
+                                                                         __uint_as_float(acc[q + 2]), __uint_as_float(acc[q + 3]));
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int j = j0 + q;
+            if (j >= jlo && j < jhi) gout[j - jlo] = __uint_as_float(acc[q]);
+          }
         }
       }
     }
@@ -209,58 +253,65 @@ mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// finalize 1: softmax rows.  grid (heads, B), 256 threads; one warp per attention row.
+// finalize 1: softmax rows.  grid (ceil(C/8), B), 256 threads: one warp per attention row (i = channel of q).
+// The split-K partials are summed with four independent accumulators so the loads overlap.
 // ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sum_splits(const float* p, size_t stride, int splits) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int sp = 0;
+  for (; sp + 4 <= splits; sp += 4) {
+    s0 += p[(size_t)sp * stride];
+    s1 += p[(size_t)(sp + 1) * stride];
+    s2 += p[(size_t)(sp + 2) * stride];
+    s3 += p[(size_t)(sp + 3) * stride];
+  }
+  for (; sp < splits; ++sp) s0 += p[(size_t)sp * stride];
+  return (s0 + s1) + (s2 + s3);
+}
+
 __global__ void __launch_bounds__(256)
 mdta_softmax_kernel(const float* __restrict__ ws_gram, const float* __restrict__ ws_norm, const float* __restrict__ temperature,
                     float* __restrict__ attn, int C, int heads, int splits) {
-  extern __shared__ float sm[];          // qn[c], kn[c]
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int c = C / heads;
-  float* qn = sm;
-  float* kn = sm + c;
-  for (int e = threadIdx.x; e < 2 * c; e += blockDim.x) {
-    const int which = e / c, ch = e % c;
-    float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += ws_norm[((size_t)(b * splits + sp) * 2 + which) * C + h * c + ch];
-    sm[e] = fmaxf(sqrtf(s), 1e-12f);     // F.normalize: x / max(||x||, eps)
-  }
-  __syncthreads();
-  const float temp = temperature[h];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = warp; i < c; i += 8) {
-    // c <= 256 supported: up to 8 columns per lane
-    float v[8];
-    float mx = -INFINITY;
+  const int r = blockIdx.x * 8 + warp;         // global q channel
+  const int b = blockIdx.y;
+  if (r >= C) return;
+  const int c = C / heads;
+  const int h = r / c, i = r - h * c;
+  const float* gbase = ws_gram + ((size_t)b * splits * C + r) * c;             // + sp * C * c
+  const float* nbase = ws_norm + (size_t)b * splits * 2 * C;                   // + sp * 2 * C
+  const float qn = fmaxf(sqrtf(sum_splits(nbase + r, (size_t)2 * C, splits)), 1e-12f);   // F.normalize: x / max(||x||, eps)
+  const float temp = temperature[h];
+  // c <= 256 supported: up to 8 columns per lane
+  float v[8];
+  float mx = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int j = lane + t * 32;
-      v[t] = -INFINITY;
-      if (j < c) {
-        float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp)
-          s += ws_gram[(size_t)(b * splits + sp) * C * C + (size_t)(h * c + i) * C + h * c + j];
-        v[t] = s / (qn[i] * kn[j]) * temp;
-        mx = fmaxf(mx, v[t]);
-      }
+  for (int t = 0; t < 8; ++t) {
+    const int j = lane + t * 32;
+    v[t] = -INFINITY;
+    if (j < c) {
+      const float kn = fmaxf(sqrtf(sum_splits(nbase + C + h * c + j, (size_t)2 * C, splits)), 1e-12f);
+      const float s = sum_splits(gbase + j, (size_t)C * c, splits);
+      v[t] = s / (qn * kn) * temp;
+      mx = fmaxf(mx, v[t]);
     }
+  }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int j = lane + t * 32;
-      if (j < c) { v[t] = expf(v[t] - mx); sum += v[t]; }
-    }
+  for (int t = 0; t < 8; ++t) {
+    const int j = lane + t * 32;
+    if (j < c) { v[t] = expf(v[t] - mx); sum += v[t]; }
+  }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.0f / sum;
-    float* arow = attn + ((size_t)(b * heads + h) * c + i) * c;
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  float* arow = attn + ((size_t)(b * heads + h) * c + i) * c;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int j = lane + t * 32;
-      if (j < c) arow[j] = v[t] * inv;
-    }
+  for (int t = 0; t < 8; ++t) {
+    const int j = lane + t * 32;
+    if (j < c) arow[j] = v[t] * inv;
   }
 }
 
@@ -319,7 +370,7 @@ static int launch_gram(const PirMdta* d, cudaStream_t stream) {
   g.chunk = ((d->HW + d->splits - 1) / d->splits + kGramPix - 1) / kGramPix * kGramPix;
   g.nblocks_n = gram_nblocks_n(d->C);
   g.ws_gram = d->ws;
-  g.ws_norm = d->ws + (size_t)d->B * d->splits * d->C * d->C;
+  g.ws_norm = d->ws + (size_t)d->B * d->splits * d->C * (d->C / d->heads);
   const int groups = (d->C >= 128 ? 2 : (d->C + 63) / 64) + (d->C >= 256 ? 4 : (d->C + 63) / 64);
   const size_t stage_bytes = (size_t)groups * kGroupBytes;
   int stages = (int)((200 * 1024) / stage_bytes);
@@ -392,10 +443,9 @@ extern "C" int pir_mdta_finalize(const PirMdta* d, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int c = d->C / d->heads;
   const float* ws_gram = d->ws;
-  const float* ws_norm = d->ws + (size_t)d->B * d->splits * d->C * d->C;
-  float* attn = d->ws + (size_t)d->B * d->splits * ((size_t)d->C * d->C + 2 * d->C);
-  pir::mdta_softmax_kernel<<<dim3(d->heads, d->B), 256, 2 * c * sizeof(float), s>>>(ws_gram, ws_norm, d->temperature, attn, d->C,
-                                                                                  d->heads, d->splits);
+  const float* ws_norm = d->ws + (size_t)d->B * d->splits * d->C * c;
+  float* attn = d->ws + (size_t)d->B * d->splits * ((size_t)d->C * c + 2 * d->C);
+  pir::mdta_softmax_kernel<<<dim3((d->C + 7) / 8, d->B), 256, 0, s>>>(ws_gram, ws_norm, d->temperature, attn, d->C, d->heads, d->splits);
   if (int e = pir_check_launch("pir_mdta_finalize(softmax)")) return e;
   const int kpad = (d->C + 63) / 64 * 64;
   dim3 grid((d->C + 31) / 32, d->heads * ((c + 31) / 32), d->B);

@@ -7,9 +7,10 @@ One Engine is specialised to (batch, height, width, dtype).  It owns
   * derived weight caches (packing.py) -- rebuilt in place whenever a parameter's version counter changes,
   * the program: an ordered list of prepared C-ABI launches (ops.py), replayed eagerly or as a CUDA graph.
 
-Per TransformerBlock (net/model.py:192-196) the program is seven kernels (+ two tiny ones):
-  K1 gemm   LN1 folded, C -> 3C                     K5 gemm   LN2 folded, C -> 2*hp
-  K2 dwconv 3x3 on 3C                               K6 dwconv 3x3 + GELU gate, 2*hp -> hp
+Per TransformerBlock (net/model.py:192-196) the program is five kernels (+ two tiny ones) where the x tile fits
+shared memory (C <= 192), seven otherwise:
+  K12 pwdw  LN1 + 1x1 (C -> 3C) + dw3x3             K56 pwdw  LN2 + 1x1 (C -> 2*hp) + dw3x3 + GELU gate
+      (else K1 gemm, K2 dwconv)                         (else K5 gemm, K6 dwconv)
   K3 mdta_gram (+ finalize: softmax, fold into Wo)  K7 gemm   hp -> C, + residual (in place)
   K4 gemm   v . Wfold[b] -> C, + residual (in place)
 
@@ -19,6 +20,7 @@ and the packing without a GPU.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -38,6 +40,9 @@ class Engine:
         self.device = torch.device(device)
         self.dtype = dtype
         self.cuda = self.device.type == "cuda"
+        # depthwise taps of the fused kernels are IEEE half whatever the storage type (fp32 only for the CPU wiring tests)
+        self.dw16 = torch.float32 if dtype == torch.float32 else torch.float16
+        self.fuse = os.environ.get("PROMPTIR_B200_FUSE", "1") != "0"     # 0: never use the fused pir_pwdw kernels (A/B timing)
         if self.cuda:
             from . import _lib
             _lib.check(_lib.load().pir_check_device(), "pir_check_device")
@@ -219,18 +224,35 @@ class Engine:
         gated = self._scratch(self.S2, h, w, hp)
         wfold = self.wfold[c]
         splits = ops.mdta_splits(B, h * w, c)
+        # fused LN -> 1x1 -> depthwise 3x3 kernels where the x tile fits shared memory (levels 1-3); else two kernels
+        fuse_qkv = self.fuse and ops.pwdw_supported(c, 3 * c, False)
+        fuse_ffn = self.fuse and ops.pwdw_supported(c, hp, True)
 
-        self._gemm(x, qkv_w, qkv_pre, n=3 * c, ln_mode=self.ln_mode, ln_s=qkv_s, vec_t=qkv_t, tag="K1")
-        self._emit("dwconv", lambda: ops.dwconv3x3(qkv_pre, dwq_w, qkv, gate=False, bias=dwq_b), x=qkv_pre, w=dwq_w, out=qkv,
-                   gate=False, bias=dwq_b, tag="K2")
+        if fuse_qkv:
+            (dwq_h,) = self._cached(lambda: [packing.pack_depthwise(at.qkv_dwconv.weight, self.dw16)])
+            self._emit("pwdw", lambda: ops.pwdw(x, qkv_w, dwq_h, qkv, gate=False, ln_mode=self.ln_mode, ln_s=qkv_s, vec_t=qkv_t,
+                                                dw_bias=dwq_b),
+                       a=x, w=qkv_w, dw_w=dwq_h, out=qkv, gate=False, ln_mode=self.ln_mode, ln_s=qkv_s, vec_t=qkv_t, dw_bias=dwq_b,
+                       tag="K12")
+        else:
+            self._gemm(x, qkv_w, qkv_pre, n=3 * c, ln_mode=self.ln_mode, ln_s=qkv_s, vec_t=qkv_t, tag="K1")
+            self._emit("dwconv", lambda: ops.dwconv3x3(qkv_pre, dwq_w, qkv, gate=False, bias=dwq_b), x=qkv_pre, w=dwq_w, out=qkv,
+                       gate=False, bias=dwq_b, tag="K2")
         gram_fin = ops.mdta(qkv, heads, self.ws, temp, wo, wfold, splits) if self.cuda else (None, None)
         self._emit("mdta_gram", (lambda: gram_fin[0]), qkv=qkv, heads=heads, ws=self.ws, splits=splits, tag="K3a")
         self._emit("mdta_finalize", (lambda: gram_fin[1]), qkv=qkv, heads=heads, ws=self.ws, splits=splits, temperature=temp,
                    wo=wo, wfold=wfold, tag="K3b")
         self._gemm(qkv[..., 2 * c:], wfold, x, n=c, res=x, vec_t=wo_b, w_batched=True, tag="K4")
-        self._gemm(x, pin_w, hid_pre, n=2 * hp, ln_mode=self.ln_mode, ln_s=pin_s, vec_t=pin_t, tag="K5")
-        self._emit("dwconv", lambda: ops.dwconv3x3(hid_pre, dwf_w, gated, gate=True, bias=dwf_b), x=hid_pre, w=dwf_w, out=gated,
-                   gate=True, bias=dwf_b, tag="K6")
+        if fuse_ffn:
+            (dwf_h,) = self._cached(lambda: [packing.pack_depthwise(ff.dwconv.weight, self.dw16, chan_map=gmap, c_total=2 * hp)])
+            self._emit("pwdw", lambda: ops.pwdw(x, pin_w, dwf_h, gated, gate=True, ln_mode=self.ln_mode, ln_s=pin_s, vec_t=pin_t,
+                                                dw_bias=dwf_b),
+                       a=x, w=pin_w, dw_w=dwf_h, out=gated, gate=True, ln_mode=self.ln_mode, ln_s=pin_s, vec_t=pin_t, dw_bias=dwf_b,
+                       tag="K56")
+        else:
+            self._gemm(x, pin_w, hid_pre, n=2 * hp, ln_mode=self.ln_mode, ln_s=pin_s, vec_t=pin_t, tag="K5")
+            self._emit("dwconv", lambda: ops.dwconv3x3(hid_pre, dwf_w, gated, gate=True, bias=dwf_b), x=hid_pre, w=dwf_w, out=gated,
+                       gate=True, bias=dwf_b, tag="K6")
         self._gemm(gated, pout_w, x, n=c, res=x, vec_t=pout_t, tag="K7")
 
     def _down(self, mod, x: Tensor, out: Tensor) -> None:
@@ -334,6 +356,12 @@ def op_cost(rec: dict):
         if rec["img"] is not None:
             by += _numel(rec["img"]) * 4
         return by, 2.0 * B * H * W * K * taps * n
+    if kind == "pwdw":
+        a, out = rec["a"], rec["out"]
+        npre = rec["w"].shape[0]
+        pix = a.shape[0] * a.shape[1] * a.shape[2]
+        return (a.numel() * 2 + out.numel() * 2 + rec["w"].numel() * 2 + rec["dw_w"].numel() * 2,
+                2.0 * pix * a.shape[3] * npre + 18.0 * pix * npre)
     if kind == "dwconv":
         x, out = rec["x"], rec["out"]
         return x.numel() * 2 + out.numel() * 2 + rec["w"].numel() * 2, 18.0 * x.numel()

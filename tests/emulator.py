@@ -68,6 +68,19 @@ def emu_dwconv(r):
     out.copy_(_nhwc(y).to(out.dtype))
 
 
+def emu_pwdw(r):
+    """pir_pwdw = pir_gemm (LN fold) -> fp16 intermediate -> depthwise 3x3 (fp16 taps) -> optional GELU gate."""
+    a, w, out = r["a"], r["w"], r["out"]
+    B, H, W, K = a.shape
+    npre = w.shape[0]
+    pre = torch.empty(B, H, W, npre, dtype=torch.float32, device=a.device)
+    emu_gemm(dict(a=a, w=w, out=pre, n=npre, taps=1, w_batched=False, ln_mode=r["ln_mode"], ln_s=r["ln_s"], vec_t=r["vec_t"],
+                  res=None, out_mode=OUT_NHWC32, img=None))
+    if a.dtype != torch.float32:                       # fp32 programs are the exact-wiring check
+        pre = pre.clamp(-65504, 65504).to(torch.float16)
+    emu_dwconv(dict(x=pre, w=r["dw_w"], out=out, bias=r["dw_bias"], gate=r["gate"]))
+
+
 def emu_mdta_finalize(r):
     qkv, heads, wo, wfold, temp = r["qkv"], r["heads"], r["wo"], r["wfold"], r["temperature"]
     B, H, W, c3 = qkv.shape
@@ -97,7 +110,7 @@ def emu_patch_embed(r):
     r["out"].copy_(_nhwc(F.conv2d(r["img"], r["w"], r["bias"], padding=1)).to(r["out"].dtype))
 
 
-DISPATCH = {"gemm": emu_gemm, "dwconv": emu_dwconv, "mdta_gram": lambda r: None, "mdta_finalize": emu_mdta_finalize,
+DISPATCH = {"gemm": emu_gemm, "dwconv": emu_dwconv, "pwdw": emu_pwdw, "mdta_gram": lambda r: None, "mdta_finalize": emu_mdta_finalize,
             "prompt": emu_prompt, "patch_embed": emu_patch_embed}
 
 

@@ -31,8 +31,10 @@ def test_program_emulation_matches_reference(model, golden_dir, dt, lim):
 def test_program_shape(model):
     eng = Engine(model, 2, 64, 64, "cpu", torch.bfloat16)
     kinds = [r["kind"] for r in eng.ops]
-    assert kinds.count("dwconv") == 94 and kinds.count("mdta_gram") == 47 and kinds.count("prompt") == 3
-    assert kinds.count("gemm") == 47 * 4 + 3 + 3 + 5 + 3 + 1 and kinds[0] == "patch_embed"
+    fused = kinds.count("pwdw")                          # blocks with C <= 192 use the fused LN+1x1+dw3x3 kernels
+    assert fused == 2 * (47 - 8 - 2) and kinds.count("dwconv") == 94 - fused
+    assert kinds.count("mdta_gram") == 47 and kinds.count("prompt") == 3
+    assert kinds.count("gemm") == 47 * 4 - fused + 3 + 3 + 5 + 3 + 1 and kinds[0] == "patch_embed"
     assert eng.kernels_per_forward() == len(eng.ops) + 47 + 3
     by, fl = map(sum, zip(*(op_cost(r) for r in eng.ops)))
     # 350 GFLOP and 7.29 GB per 256x256 image; 64x64 is 1/16 of that per image (+ weights)

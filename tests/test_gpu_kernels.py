@@ -228,6 +228,52 @@ def test_dwconv_gate(case, dt):
 
 
 # --------------------------------------------------------------------------------------------------
+# fused LN -> 1x1 -> depthwise 3x3 (-> gate)
+# --------------------------------------------------------------------------------------------------
+PWDW_CASES = [
+    # B, H, W, C, N, gate, ln, a_pitch, a_off, conv bias, dw bias
+    (2, 40, 72, 48, 144, False, LN_WITHBIAS, None, 0, False, False),     # 8x32 tiles, ragged right/bottom edges, partial chunk
+    (1, 16, 16, 96, 288, False, LN_WITHBIAS, None, 0, False, False),     # 16x16 tiles
+    (2, 24, 40, 96, 256, True, LN_WITHBIAS, 160, 64, False, False),      # gate, x is a channel slice
+    (1, 32, 32, 192, 512, True, LN_WITHBIAS, None, 0, False, False),     # 12x16 tiles (two M groups), three k-blocks
+    (1, 20, 12, 192, 576, False, LN_BIASFREE, None, 0, True, True),      # BiasFree LN, both biases
+    (1, 24, 24, 160, 432, True, LN_WITHBIAS, None, 0, True, True),       # hidden not a multiple of 32, K not a multiple of 64
+    (1, 16, 24, 160, 480, False, LN_NONE, None, 0, False, False),        # no LayerNorm
+    (3, 8, 8, 48, 128, True, LN_WITHBIAS, None, 0, False, False),        # tiny images, several per CTA
+    (1, 64, 64, 96, 256, True, LN_WITHBIAS, None, 0, False, False),      # many tiles per CTA: ring/phase wrap
+]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", PWDW_CASES, ids=lambda c: "B%dH%dW%dC%dN%d%s" % (c[0], c[1], c[2], c[3], c[4], "g" if c[5] else "p"))
+def test_pwdw(case, dt):
+    B, H, W, Cc, N, gate, ln, pitch, off, cbias, dbias = case
+    torch.manual_seed(Cc + N)
+    npre = 2 * N if gate else N
+    assert ops.pwdw_supported(Cc, N, gate)
+    x, _ = rand_act(B, H, W, Cc, dt, pitch, off, scale=2.0)
+    x += 0.5                                                   # non-zero mean so the LayerNorm fold matters
+    wt = torch.randn(npre, Cc, device=DEV) / Cc ** 0.5
+    gamma = torch.rand(Cc, device=DEV) + 0.5 if ln else None
+    beta = torch.randn(Cc, device=DEV) * 0.2 if ln == LN_WITHBIAS else None
+    w16, ln_s, vec_t = packing.pack_pointwise(wt, dt, gamma=gamma, beta=beta, bias=torch.randn(npre, device=DEV) * 0.1 if cbias else None)
+    dw = packing.pack_depthwise(torch.randn(npre, 1, 3, 3, device=DEV) / 3, torch.float16)
+    db = torch.randn(npre, device=DEV) * 0.1 if dbias else None
+    out_buf = torch.zeros(B, H, W, N + 8, device=DEV, dtype=dt)
+    out = out_buf[..., :N]
+    ref = out.clone()
+    rec = dict(a=x, w=w16, dw_w=dw, out=ref, gate=gate, ln_mode=ln, ln_s=ln_s, vec_t=vec_t, dw_bias=db)
+    emulator.emu_pwdw(rec)
+    ops.pwdw(x, w16, dw, out, gate=gate, ln_mode=ln, ln_s=ln_s, vec_t=vec_t, dw_bias=db)(stream())
+    torch.cuda.synchronize()
+    # the nine taps are accumulated in fp16: up to ~3 roundings of 2^-11 relative to the largest partial sum (stated
+    # tolerance of the fused kernel), on top of one unit in the last place of the 16-bit output
+    atol, rtol = tol(dt, 2.0)
+    report_mismatch("pwdw", out, ref, atol + 1.5e-3 * ref.abs().max().item(), rtol)
+    assert float(out_buf[..., N:].abs().max()) == 0
+
+
+# --------------------------------------------------------------------------------------------------
 # MDTA gram + finalize
 # --------------------------------------------------------------------------------------------------
 MDTA_CASES = [(2, 16, 16, 48, 1), (1, 32, 32, 96, 2), (2, 24, 24, 96, 1), (1, 16, 16, 192, 4), (2, 8, 8, 384, 8), (1, 8, 8, 704, 4),
@@ -252,16 +298,17 @@ def test_mdta(case, dt):
     torch.cuda.synchronize()
     ref = torch.zeros_like(wfold)
     emulator.emu_mdta_finalize(dict(qkv=qkv, heads=heads, wo=wo, wfold=ref, temperature=temp))
-    # check the raw Gram partial sums too (first image, summed over splits) for a sharper diagnosis
-    g = ws[: B * splits * Cc * Cc].view(B, splits, Cc, Cc).sum(1)
+    # check the raw Gram partial sums too (summed over splits) for a sharper diagnosis.  Workspace layout:
+    # [B][splits][C][c] diagonal head blocks, then [B][splits][2][C] squared norms (csrc/mdta.cu)
+    c = Cc // heads
+    g = ws[: B * splits * Cc * c].view(B, splits, Cc, c).sum(1)
     q = qkv[..., :Cc].float().reshape(B, -1, Cc)
     k = qkv[..., Cc:2 * Cc].float().reshape(B, -1, Cc)
-    gref = torch.einsum("bpi,bpj->bij", q, k)
-    c = Cc // heads
-    mask = torch.block_diag(*[torch.ones(c, c, device=DEV)] * heads).bool()
-    gerr = ((g - gref).abs() * mask).max().item()
+    gfull = torch.einsum("bpi,bpj->bij", q, k)
+    gref = torch.stack([gfull[:, h * c:(h + 1) * c, h * c:(h + 1) * c] for h in range(heads)], 1).reshape(B, Cc, c)
+    gerr = (g - gref).abs().max().item()
     assert gerr <= 1e-3 * max(1.0, gref.abs().max().item()), f"gram mismatch {gerr} (ref max {gref.abs().max().item()})"
-    nrm = ws[B * splits * Cc * Cc: B * splits * (Cc * Cc + 2 * Cc)].view(B, splits, 2, Cc).sum(1)
+    nrm = ws[B * splits * Cc * c: B * splits * (Cc * c + 2 * Cc)].view(B, splits, 2, Cc).sum(1)
     nref = torch.stack([q.pow(2).sum(1), k.pow(2).sum(1)], dim=1)
     assert torch.allclose(nrm, nref, rtol=1e-4, atol=1e-3), f"norm mismatch {(nrm - nref).abs().max().item()}"
     report_mismatch("mdta_wfold", wfold.view(B, 1, Cc, kp), ref.view(B, 1, Cc, kp), *tol(dt))

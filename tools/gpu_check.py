@@ -18,6 +18,7 @@ GROUPS = {
     "conv3x3": "tests/test_gpu_kernels.py::test_gemm_conv3x3",
     "dw_plain": "tests/test_gpu_kernels.py::test_dwconv_plain",
     "dw_gate": "tests/test_gpu_kernels.py::test_dwconv_gate",
+    "pwdw": "tests/test_gpu_kernels.py::test_pwdw",
     "mdta": "tests/test_gpu_kernels.py::test_mdta",
     "prompt": "tests/test_gpu_kernels.py::test_prompt_gen",
     "patch": "tests/test_gpu_kernels.py::test_patch_embed",

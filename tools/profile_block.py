@@ -24,7 +24,7 @@ def main():
     s = torch.cuda.current_stream().cuda_stream
     eng.launch_all(s)
     torch.cuda.synchronize()
-    k1 = [i for i, r in enumerate(eng.ops) if r.get("tag") == "K1"]
+    k1 = [i for i, r in enumerate(eng.ops) if r.get("tag") in ("K1", "K12")]
     lo = k1[which]
     hi = k1[which + 1] if which + 1 < len(k1) else lo + 9
     block = [r for r in eng.ops[lo:hi] if r.get("tag", "").startswith("K")]
