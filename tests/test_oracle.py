@@ -72,3 +72,17 @@ def test_synthetic_batch_is_deterministic():
     a, ca = O.synthetic_batch(5, 32, 32, seed=4)
     b, cb = O.synthetic_batch(5, 32, 32, seed=4)
     assert torch.equal(a, b) and torch.equal(ca, cb) and 0 <= a.min() and a.max() <= 1
+
+
+def test_gelu_sigmoid_polynomial_bound():
+    """The CUDA kernels evaluate erf-GELU as x*sigmoid(2x(a + b u + c u^2)), u = min(x^2, 25) (csrc/common.cuh gelu_erf).
+    Restated here in fp32 with the same constants: it must stay within 2.6e-5 of torch's exact erf GELU everywhere."""
+    import re
+    src = open(os.path.join(os.path.dirname(__file__), "..", "promptir_b200", "csrc", "common.cuh")).read()
+    a, b, c = (float(v) for v in re.search(r"kGeluA = ([-0-9.e]+)f, kGeluB = ([-0-9.e]+)f, kGeluC = ([-0-9.e]+)f", src).groups())
+    x = torch.cat([torch.linspace(-30, 30, 2_000_001), torch.tensor([-1e4, -100.0, 100.0, 1e4, 0.0])])
+    u = (x * x).clamp_max(25.0)
+    t = u * (u * c + b) + a
+    y = x / (1.0 + torch.exp2(x * t))
+    ref = torch.nn.functional.gelu(x.double()).float()
+    assert (y - ref).abs().max().item() <= 2.6e-5
