@@ -83,9 +83,11 @@ int pir_dwconv3x3(const PirDwConv* d, void* stream);
 /* ---- fused LayerNorm -> 1x1 conv -> depthwise 3x3 (-> GELU gate) -----------------------------------
  * gate == 0: out[b,p,n] = dw3x3( W . LN(x) )[n],                                   n < N      (model.py:60-63,111-112,120)
  * gate == 1: out[b,p,n] = gelu_erf(dw3x3(W . LN(x))[n]) * dw3x3(W . LN(x))[N + n], n < N      (model.py:60-63,88-90,96-97)
- * Same result as pir_gemm (ln fold) followed by pir_dwconv3x3, but the pre-conv tensor (N resp. 2N channels per
- * pixel) stays in shared memory as fp16 (values saturate at +-65504).  w: packed [N or 2N][Kpad] 16-bit like
- * pir_gemm; dw_w: [3][3][N or 2N] fp16 (always IEEE half, also when dtype is bf16); dw_bias fp32 or NULL.
+ * Same function as pir_gemm (ln fold) followed by pir_dwconv3x3, but the pre-conv tensor (N resp. 2N channels per
+ * pixel) stays in shared memory as fp16 (values saturate at +-65504) and the LayerNorm is applied to the x tile
+ * before the GEMM (normalised rows rounded to the 16-bit type; gamma lives in w, beta in vec_t).  w: packed
+ * [N or 2N][Kpad] 16-bit like pir_gemm; vec_t: fp32 [N or 2N] additive vector (W.beta + conv bias) or NULL;
+ * dw_w: [3][3][N or 2N] fp16 (always IEEE half, also when dtype is bf16); dw_bias fp32 or NULL.
  * pir_pwdw_supported() tells whether (C, N, gate) fits the shared-memory plan; otherwise use the two calls.     */
 typedef struct PirPwDw {
   int32_t dtype, gate, ln_mode;
@@ -93,7 +95,7 @@ typedef struct PirPwDw {
   int32_t N;                /* output channels (the 1x1 conv produces N, or 2N when gate == 1)             */
   const void* a; int64_t a_pitch, a_bstride;
   const void* w;
-  const float* ln_s; const float* vec_t;
+  const float* vec_t;
   const void* dw_w; const float* dw_bias;
   void* out; int64_t out_pitch, out_bstride;
 } PirPwDw;

@@ -39,7 +39,7 @@ class PirDwConv(C.Structure):
 class PirPwDw(C.Structure):
     _fields_ = [("dtype", i32), ("gate", i32), ("ln_mode", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32), ("N", i32),
                 ("a", vp), ("a_pitch", i64), ("a_bstride", i64),
-                ("w", vp), ("ln_s", vp), ("vec_t", vp), ("dw_w", vp), ("dw_bias", vp),
+                ("w", vp), ("vec_t", vp), ("dw_w", vp), ("dw_bias", vp),
                 ("out", vp), ("out_pitch", i64), ("out_bstride", i64)]
 
 

@@ -103,7 +103,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ========================================= TMA producer ==========================================
-    if (g.resident && lane == 0) {
+    if (g.resident && elect_one()) {
       const uint32_t bf = smem_u32(&bar_bfull);
       mbar_expect_tx(bf, (uint32_t)g.nkb * (uint32_t)g.n_alloc * 128u);
       for (int kb = 0; kb < g.nkb; ++kb)
@@ -119,7 +119,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int bboxes = g.resident ? 0 : (ncols + 63) / 64;
         for (int kb = 0; kb < g.nkb; ++kb) {
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t full = smem_u32(&bar_full[stage]);
             const uint32_t dst = ring + (uint32_t)stage * stage_bytes;
             mbar_expect_tx(full, kPwATile + (uint32_t)bboxes * 8192u);
@@ -148,7 +148,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < g.nkb; ++kb) {
           mbar_wait(smem_u32(&bar_full[st]), ph);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t a_src = ring + (uint32_t)st * stage_bytes;
             const uint32_t b_src = g.resident ? base + ((uint32_t)kb * g.n_alloc + (uint32_t)c * g.NC) * 128u : a_src + kPwATile;
             const int rem = g.K - kb * kPwBlockK;
@@ -213,7 +213,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int grp = (warp - 6) >> 2;                 // slabs with (u & 1) == grp belong to this group
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const bool leader = (((warp - 6) & 3) == 0 && lane == 0);
+    const bool lead_warp = ((warp - 6) & 3) == 0;     // its elected lane issues the TMA stores (always the same lane)
     const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int n16 = (g.N + 15) / 16 * 16;
     uint32_t q = 0, u = 0, ti = 0;
@@ -290,7 +290,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           fence_proxy_async();                                 // generic-proxy smem writes -> visible to the TMA store
           named_bar(2 + grp, 128);
-          if (leader) {
+          if (lead_warp && elect_one()) {
             tma_store_3d(&tmO, slots + slot * kPwSlab, ncol0, m0, b);
             bulk_commit();
             bulk_wait_read<1>();                               // this group's previous store has finished reading smem
@@ -300,10 +300,10 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // release the accumulator buffer: every thread of the group has finished its TMEM loads (tcgen05.wait::ld above)
         tc_fence_before();
         named_bar(4 + grp, 128);
-        if (leader) mbar_arrive(smem_u32(&bar_tempty[buf]));
+        if (lead_warp && elect_one()) mbar_arrive(smem_u32(&bar_tempty[buf]));
       }
     }
-    if (leader) bulk_wait_all();                               // smem must outlive the last store
+    if (lead_warp && elect_one()) bulk_wait_all();                               // smem must outlive the last store
   } else {
     // ========================================= residual prefetch ======================================
     if (g.has_res) {
@@ -317,7 +317,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t grp = u & 1u, j = u >> 1;
             const uint32_t slot = grp * 2u + (j & 1u), sph = (j >> 1) & 1u;
             mbar_wait(smem_u32(&bar_slot_empty[slot]), sph ^ 1u);
-            if (lane == 0) {
+            if (elect_one()) {
               const uint32_t full = smem_u32(&bar_slot_full[slot]);
               mbar_expect_tx(full, kPwSlab);
               tma_load_3d(slots + slot * kPwSlab, &tmR, full, c * g.NC + s0, m0, b);

@@ -105,7 +105,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t phase = 0;
     for (int kb = 0; kb < total_kb; ++kb) {
       mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t full = smem_u32(&bar_full[stage]);
         const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
         const uint32_t b_dst = a_dst + kATileBytes;
@@ -132,7 +132,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int kb = 0; kb < total_kb; ++kb) {
       mbar_wait(smem_u32(&bar_full[stage]), phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_src = smem_base + (uint32_t)stage * stage_bytes;
         const uint32_t b_src = a_src + kATileBytes;
         const int kc = (kb % g.nkb) * kBlockK;

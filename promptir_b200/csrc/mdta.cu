@@ -88,7 +88,7 @@ mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
     uint32_t phase = 0;
     for (int it = 0; it < nst; ++it) {
       mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t full = smem_u32(&bar_full[stage]);
         const uint32_t dst = smem_base + (uint32_t)stage * stage_bytes;
         mbar_expect_tx(full, stage_bytes);
@@ -107,7 +107,7 @@ mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
     for (int it = 0; it < nst; ++it) {
       mbar_wait(smem_u32(&bar_full[stage]), phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_src = smem_base + (uint32_t)stage * stage_bytes;
         const uint32_t b_src = a_src + (uint32_t)agroups * kGroupBytes;
 #pragma unroll

@@ -230,10 +230,8 @@ class Engine:
 
         if fuse_qkv:
             (dwq_h,) = self._cached(lambda: [packing.pack_depthwise(at.qkv_dwconv.weight, self.dw16)])
-            self._emit("pwdw", lambda: ops.pwdw(x, qkv_w, dwq_h, qkv, gate=False, ln_mode=self.ln_mode, ln_s=qkv_s, vec_t=qkv_t,
-                                                dw_bias=dwq_b),
-                       a=x, w=qkv_w, dw_w=dwq_h, out=qkv, gate=False, ln_mode=self.ln_mode, ln_s=qkv_s, vec_t=qkv_t, dw_bias=dwq_b,
-                       tag="K12")
+            self._emit("pwdw", lambda: ops.pwdw(x, qkv_w, dwq_h, qkv, gate=False, ln_mode=self.ln_mode, vec_t=qkv_t, dw_bias=dwq_b),
+                       a=x, w=qkv_w, dw_w=dwq_h, out=qkv, gate=False, ln_mode=self.ln_mode, vec_t=qkv_t, dw_bias=dwq_b, tag="K12")
         else:
             self._gemm(x, qkv_w, qkv_pre, n=3 * c, ln_mode=self.ln_mode, ln_s=qkv_s, vec_t=qkv_t, tag="K1")
             self._emit("dwconv", lambda: ops.dwconv3x3(qkv_pre, dwq_w, qkv, gate=False, bias=dwq_b), x=qkv_pre, w=dwq_w, out=qkv,
@@ -245,10 +243,8 @@ class Engine:
         self._gemm(qkv[..., 2 * c:], wfold, x, n=c, res=x, vec_t=wo_b, w_batched=True, tag="K4")
         if fuse_ffn:
             (dwf_h,) = self._cached(lambda: [packing.pack_depthwise(ff.dwconv.weight, self.dw16, chan_map=gmap, c_total=2 * hp)])
-            self._emit("pwdw", lambda: ops.pwdw(x, pin_w, dwf_h, gated, gate=True, ln_mode=self.ln_mode, ln_s=pin_s, vec_t=pin_t,
-                                                dw_bias=dwf_b),
-                       a=x, w=pin_w, dw_w=dwf_h, out=gated, gate=True, ln_mode=self.ln_mode, ln_s=pin_s, vec_t=pin_t, dw_bias=dwf_b,
-                       tag="K56")
+            self._emit("pwdw", lambda: ops.pwdw(x, pin_w, dwf_h, gated, gate=True, ln_mode=self.ln_mode, vec_t=pin_t, dw_bias=dwf_b),
+                       a=x, w=pin_w, dw_w=dwf_h, out=gated, gate=True, ln_mode=self.ln_mode, vec_t=pin_t, dw_bias=dwf_b, tag="K56")
         else:
             self._gemm(x, pin_w, hid_pre, n=2 * hp, ln_mode=self.ln_mode, ln_s=pin_s, vec_t=pin_t, tag="K5")
             self._emit("dwconv", lambda: ops.dwconv3x3(hid_pre, dwf_w, gated, gate=True, bias=dwf_b), x=hid_pre, w=dwf_w, out=gated,

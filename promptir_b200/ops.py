@@ -107,7 +107,7 @@ def pwdw_supported(c: int, n: int, gate: bool) -> bool:
 
 
 def pwdw(x: torch.Tensor, w: torch.Tensor, dw_w: torch.Tensor, out: torch.Tensor, *, gate: bool, ln_mode: int = LN_NONE,
-         ln_s: Optional[torch.Tensor] = None, vec_t: Optional[torch.Tensor] = None, dw_bias: Optional[torch.Tensor] = None) -> Launch:
+         vec_t: Optional[torch.Tensor] = None, dw_bias: Optional[torch.Tensor] = None) -> Launch:
     """Fused LN -> 1x1 conv -> depthwise 3x3 (-> GELU gate) (pir_pwdw).  w: packed [Npre, Kpad]; dw_w: fp16 [9, Npre]."""
     pa, B, H, W, K, apitch, abs_ = _nhwc(x, "pwdw.a")
     po, oB, oH, oW, N, opitch, obs = _nhwc(out, "pwdw.out")
@@ -119,10 +119,10 @@ def pwdw(x: torch.Tensor, w: torch.Tensor, dw_w: torch.Tensor, out: torch.Tensor
     d.dtype, d.gate, d.ln_mode = dtype_code(x.dtype), int(gate), ln_mode
     d.B, d.H, d.W, d.C, d.N = B, H, W, K, N
     d.a, d.a_pitch, d.a_bstride = pa, apitch, abs_
-    d.w, d.ln_s, d.vec_t = w.data_ptr(), _ptr(ln_s), _ptr(vec_t)
+    d.w, d.vec_t = w.data_ptr(), _ptr(vec_t)
     d.dw_w, d.dw_bias = dw_w.data_ptr(), _ptr(dw_bias)
     d.out, d.out_pitch, d.out_bstride = po, opitch, obs
-    return _prepared("pir_pwdw", d, (x, w, dw_w, out, ln_s, vec_t, dw_bias))
+    return _prepared("pir_pwdw", d, (x, w, dw_w, out, vec_t, dw_bias))
 
 
 def mdta_splits(B: int, HW: int, Cdim: int) -> int:

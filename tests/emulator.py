@@ -69,13 +69,21 @@ def emu_dwconv(r):
 
 
 def emu_pwdw(r):
-    """pir_pwdw = pir_gemm (LN fold) -> fp16 intermediate -> depthwise 3x3 (fp16 taps) -> optional GELU gate."""
+    """pir_pwdw: LayerNorm of x (no affine; rounded to the 16-bit type) -> 1x1 conv with the gamma-folded weights + t
+    -> fp16 intermediate -> depthwise 3x3 (fp16 taps) -> optional GELU gate."""
     a, w, out = r["a"], r["w"], r["out"]
     B, H, W, K = a.shape
     npre = w.shape[0]
-    pre = torch.empty(B, H, W, npre, dtype=torch.float32, device=a.device)
-    emu_gemm(dict(a=a, w=w, out=pre, n=npre, taps=1, w_batched=False, ln_mode=r["ln_mode"], ln_s=r["ln_s"], vec_t=r["vec_t"],
-                  res=None, out_mode=OUT_NHWC32, img=None))
+    A = a.float()
+    if r["ln_mode"]:
+        mu = A.mean(-1, keepdim=True)
+        var = ((A * A).mean(-1, keepdim=True) - mu * mu).clamp_min(0)
+        rstd = torch.rsqrt(var + 1e-5)
+        A = A * rstd if r["ln_mode"] == LN_BIASFREE else (A - mu) * rstd
+        A = A.to(a.dtype).float()
+    pre = torch.einsum("bhwk,nk->bhwn", A, w.float()[:, :K])
+    if r["vec_t"] is not None:
+        pre = pre + r["vec_t"].view(1, 1, 1, -1)
     if a.dtype != torch.float32:                       # fp32 programs are the exact-wiring check
         pre = pre.clamp(-65504, 65504).to(torch.float16)
     emu_dwconv(dict(x=pre, w=r["dw_w"], out=out, bias=r["dw_bias"], gate=r["gate"]))

@@ -262,9 +262,9 @@ def test_pwdw(case, dt):
     out_buf = torch.zeros(B, H, W, N + 8, device=DEV, dtype=dt)
     out = out_buf[..., :N]
     ref = out.clone()
-    rec = dict(a=x, w=w16, dw_w=dw, out=ref, gate=gate, ln_mode=ln, ln_s=ln_s, vec_t=vec_t, dw_bias=db)
+    rec = dict(a=x, w=w16, dw_w=dw, out=ref, gate=gate, ln_mode=ln, vec_t=vec_t, dw_bias=db)
     emulator.emu_pwdw(rec)
-    ops.pwdw(x, w16, dw, out, gate=gate, ln_mode=ln, ln_s=ln_s, vec_t=vec_t, dw_bias=db)(stream())
+    ops.pwdw(x, w16, dw, out, gate=gate, ln_mode=ln, vec_t=vec_t, dw_bias=db)(stream())
     torch.cuda.synchronize()
     # the nine taps are accumulated in fp16: up to ~3 roundings of 2^-11 relative to the largest partial sum (stated
     # tolerance of the fused kernel), on top of one unit in the last place of the 16-bit output
