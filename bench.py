@@ -187,12 +187,14 @@ def run_ours(args):
     evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in eng.ops] for _ in range(nrep)]
     eng.launch_all(s)
     torch.cuda.synchronize()
+    torch.cuda.profiler.start()          # `ncu --profile-from-start off` captures exactly these launches (profiles/*launches*)
     for rep in range(nrep):
         for (a, b), r in zip(evs[rep], eng.ops):
             a.record()
             r["launch"](s)
             b.record()
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     tags = {}
     for i, r in enumerate(eng.ops):
         tag = r.get("tag") or r["kind"]
@@ -221,6 +223,8 @@ def run_ours(args):
                 "peak": pk["hbm"] if hbm_bound else pk["tc"], "unit": "GB/s" if hbm_bound else "TFLOP/s",
                 "frac": round(ach / (pk["hbm"] if hbm_bound else pk["tc"]), 4), "traffic": None,
                 "launches_per_step": td["n"], "avg_launch_ms": round(td["ms"] / td["n"], 4), "peak_source": pk["src"],
+                "note": ("K56/K12 are the fused LN+1x1+dw3x3(+gate) kernels: their binding resource is CUDA-core issue (fp16x2 FMA, "
+                         "MUFU), not HBM or the tensor pipe -- see DESIGN.md 3.2 and profiles/ for issue-slot utilisation") if top in ("K56", "K12") else "",
                 "how": "CUDA events around each launch, eager pass, mean of %d steps; achieved = algorithmic bytes / time" % nrep}
     whole_t_min = sum(max(d["bytes"] / pk["hbm"] / 1e6, d["flops"] / pk["tc"] / 1e9) for d in tags.values())
 
