@@ -251,15 +251,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int i = 0; i < 16; ++i)
           if (n + i < g.N) o[(size_t)(n + i) * 4] = to16<T>(v[i]);
       } else if (g.out_mode == PIR_OUT_SHUFFLE16) {
-        // PixelShuffle(2): out[b, 2y+i, 2x+j, c] = conv[b, y, x, 4c + 2i + j]
+        // PixelShuffle(2): out[b, 2y+i, 2x+j, c] = conv[b, y, x, 4c + 2i + j].  The 16 columns n..n+15 of this thread are four
+        // consecutive output channels (n/4 .. n/4+3) for each of the four sub-pixels: one 8-byte store per sub-pixel.
         unsigned short* o = reinterpret_cast<unsigned short*>(g.out) + (size_t)img_b * g.out_bstride;
         const size_t W2 = (size_t)g.W * 2;
+        if (n + 16 <= g.N && (g.out_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(g.out) & 7) == 0 && (g.out_bstride & 3) == 0) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int nn = n + i;
-          if (nn < g.N) {
-            const size_t dp = ((size_t)(2 * py + ((nn >> 1) & 1))) * W2 + (size_t)(2 * px + (nn & 1));
-            o[dp * g.out_pitch + (nn >> 2)] = to16<T>(v[i]);
+          for (int sub = 0; sub < 4; ++sub) {
+            const size_t dp = ((size_t)(2 * py + (sub >> 1))) * W2 + (size_t)(2 * px + (sub & 1));
+            uint2 ov;
+            ov.x = pack2<T>(v[sub], v[4 + sub]);
+            ov.y = pack2<T>(v[8 + sub], v[12 + sub]);
+            *reinterpret_cast<uint2*>(o + dp * g.out_pitch + (n >> 2)) = ov;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int nn = n + i;
+            if (nn < g.N) {
+              const size_t dp = ((size_t)(2 * py + ((nn >> 1) & 1))) * W2 + (size_t)(2 * px + (nn & 1));
+              o[dp * g.out_pitch + (nn >> 2)] = to16<T>(v[i]);
+            }
           }
         }
       } else if (g.out_mode == PIR_OUT_FINAL_NCHW32) {

@@ -20,6 +20,8 @@
 //     tensor it replaces; values saturate at +-65504), applies the erf-GELU gate in fp32 and stores 16-bit NHWC.
 //
 // Warp roles (576 threads): 0 TMA producer | 1 TMEM alloc + MMA issue | 2-9 compute group 0 | 10-17 compute group 1.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -28,7 +30,7 @@ namespace pir {
 constexpr int kFwThreads = 576;
 constexpr int kFwCompute = 512;
 constexpr int kFwGroup = 256;                // threads per compute group
-constexpr int kFwBStages = 4;               // weight-chunk TMA ring
+constexpr int kFwBStages = 2;               // weight TMA ring (one super-chunk per stage)
 constexpr int kFwChunk = 32;                 // pre-conv channels per chunk = UMMA N (gate: 16 of x1 + the matching 16 of x2)
 
 struct FwArgs {
@@ -42,6 +44,7 @@ struct FwArgs {
   int tiles_x, tiles_y, n_items;
   int has_bias;            // depthwise bias present
   int has_t;               // additive per-channel vector present
+  int dbg;                 // diagnostics (PIR_PWDW_DBG): 1 skip the stencil, 2 skip the drain arithmetic, 4 skip the stores
   uint32_t off_b, off_conv, off_dw, off_vec, off_bias;   // byte offsets from the 1024-aligned base
   const void* dw_w;        // [9][n_pre] fp16
   const float* dw_bias;    // [n_pre] or null
@@ -64,17 +67,21 @@ __device__ __forceinline__ float2 h2_to_f2(uint32_t v) {
 // the 64 columns are BANDS = 64 / TW row bands of R rows over a TW-wide tile.
 //   GATE : 4 gated channels per thread (16 gated channels per chunk), fp16 tile = two planes of 32-byte rows
 //   plain: 8 channels per thread       (32 channels per chunk),      fp16 tile = one plane of 64-byte rows
-template <int MT_, int TW_, int R_, bool GATE_>
+template <int MT_, int TW_, int R_, bool GATE_, int NA_, int SC_>
 struct FwCfg {
   static constexpr int MT = MT_, TW = TW_, R = R_;
   static constexpr bool GATE = GATE_;
+  static constexpr int NA = NA_;
+  static constexpr int SC = SC_;                             // chunks per super-chunk: one tcgen05.mma covers SC * 32 channels
+  static constexpr int SCN = SC * kFwChunk;                  // UMMA N of a full super-chunk                             // x-tile buffers: 2 = the next item's tile is loaded and normalised ahead
   static constexpr int BANDS = 64 / TW;
   static constexpr int TH = R * BANDS;
   static constexpr int SW = TW + 2;
   static constexpr int NPIX = (TH + 2) * SW;
-  static constexpr int TMEM_COLS = 4 * MT * kFwChunk <= 256 ? 256 : 512;   // 2 groups x 2 buffers x MT x 32 columns
+  static constexpr int TMEM_COLS = 2 * MT * SCN <= 256 ? 256 : 512;          // 2 super-chunk buffers x MT x SC x 32 columns
+  static_assert(2 * MT * SCN <= 512, "accumulators do not fit TMEM");
   static constexpr uint32_t A_KB_BYTES = MT * 128 * 128;     // one k-block of the halo'd tile
-  static constexpr uint32_t B_KB_BYTES = kFwChunk * 128;
+  static constexpr uint32_t B_KB_BYTES = SCN * 128;          // one k-block of a super-chunk's weights
   static constexpr uint32_t CONV_BYTES = MT * 128 * 64;      // fp16 tile of one group (32 channels per pixel)
   static_assert(NPIX <= MT * 128, "halo'd tile does not fit the M tiles");
 };
@@ -84,12 +91,13 @@ __global__ void __launch_bounds__(kFwThreads, 1)
 pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwArgs g) {
   constexpr int MT = Cfg::MT, TW = Cfg::TW, R = Cfg::R, TH = Cfg::TH, SW = Cfg::SW, NPIX = Cfg::NPIX;
   constexpr bool GATE = Cfg::GATE;
+  constexpr int NA = Cfg::NA, SC = Cfg::SC, SCN = Cfg::SCN;
   constexpr uint32_t A_KB_BYTES = Cfg::A_KB_BYTES, B_KB_BYTES = Cfg::B_KB_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_afull, bar_aready, bar_aempty;
+  __shared__ __align__(8) uint64_t bar_afull[2], bar_aready[2], bar_aempty[2];
   __shared__ __align__(8) uint64_t bar_bfull[kFwBStages], bar_bempty[kFwBStages];
-  __shared__ __align__(8) uint64_t bar_tfull[4], bar_tempty[4];          // accumulator buffers: group * 2 + (chunk of the group & 1)
+  __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];          // super-chunk accumulator buffers
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -99,28 +107,52 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t b_stage_bytes = (uint32_t)g.nkb * B_KB_BYTES;
   const unsigned short* sdw = reinterpret_cast<const unsigned short*>(base_ptr + g.off_dw);
   float* svec = reinterpret_cast<float*>(base_ptr + g.off_vec);              // [n_vec] additive vector t
-  float* sbias = reinterpret_cast<float*>(base_ptr + g.off_bias);            // [n_vec] depthwise bias
+  const uint32_t* sseed = reinterpret_cast<const uint32_t*>(base_ptr + g.off_bias);   // [2][n_chunks * 32] fp16 accumulator seeds
   const int n_vec = g.n_vec;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
-    mbar_init(smem_u32(&bar_afull), 1); mbar_init(smem_u32(&bar_aready), kFwCompute / 32); mbar_init(smem_u32(&bar_aempty), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_afull[i]), 1); mbar_init(smem_u32(&bar_aready[i]), kFwCompute / 32); mbar_init(smem_u32(&bar_aempty[i]), 1);
+    }
     for (int i = 0; i < kFwBStages; ++i) { mbar_init(smem_u32(&bar_bfull[i]), 1); mbar_init(smem_u32(&bar_bempty[i]), 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&bar_tfull[i]), 1); mbar_init(smem_u32(&bar_tempty[i]), kFwGroup / 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tfull[i]), 1); mbar_init(smem_u32(&bar_tempty[i]), kFwCompute / 32); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), Cfg::TMEM_COLS); tmem_relinquish(); }
-  // per-CTA constants: depthwise taps (fp16), additive vector, depthwise bias
+  // per-CTA constants.  Depthwise taps are regrouped chunk-major so a thread reaches all its taps from ONE base address:
+  //   GATE : [chunk][x1 | x2][tap][16 ch]   plain: [chunk][tap][32 ch]     (fp16, 576 bytes per chunk)
+  // svec: additive vector t.  Two fp16 accumulator seeds per pre-conv channel (same regrouping, 32 channels per chunk):
+  //   sseed[0] = depthwise bias                              (tiles touching the image border: t is added in the drain)
+  //   sseed[1] = depthwise bias + t[n] * sum of the 9 taps   (interior tiles: the conv of the constant t is a constant)
   {
     const unsigned short* src = reinterpret_cast<const unsigned short*>(g.dw_w);
     unsigned short* dst = const_cast<unsigned short*>(sdw);
-    for (int i = threadIdx.x; i < 9 * n_vec; i += kFwThreads) {
-      const int t = i / n_vec, c = i - t * n_vec;
-      dst[i] = c < g.n_pre ? src[(size_t)t * g.n_pre + c] : (unsigned short)0;
+    for (int i = threadIdx.x; i < g.n_chunks * 288; i += kFwThreads) {
+      const int c = i / 288, r = i - c * 288;
+      int tap, n;
+      if (GATE) { const int half = r / 144, rr = r - half * 144; tap = rr >> 4; n = (half ? g.hp : 0) + c * 16 + (rr & 15); if (c * 16 + (rr & 15) >= g.hp) n = g.n_pre; }
+      else { tap = r >> 5; n = c * 32 + (r & 31); }
+      dst[i] = n < g.n_pre ? src[(size_t)tap * g.n_pre + n] : (unsigned short)0;
     }
-    for (int i = threadIdx.x; i < n_vec; i += kFwThreads) {
-      svec[i] = (g.vec_t && i < g.n_pre) ? g.vec_t[i] : 0.f;
-      sbias[i] = (g.dw_bias && i < g.n_pre) ? g.dw_bias[i] : 0.f;
+    for (int i = threadIdx.x; i < n_vec; i += kFwThreads) svec[i] = (g.vec_t && i < g.n_pre) ? g.vec_t[i] : 0.f;
+    unsigned short* seed = reinterpret_cast<unsigned short*>(base_ptr + g.off_bias);
+    for (int i = threadIdx.x; i < g.n_chunks * 32; i += kFwThreads) {
+      const int c = i >> 5, r = i & 31;
+      int n;
+      if (GATE) { n = (r >= 16 ? g.hp : 0) + c * 16 + (r & 15); if (c * 16 + (r & 15) >= g.hp) n = g.n_pre; }
+      else n = i;
+      float bias = 0.f, tsum = 0.f;
+      if (n < g.n_pre) {
+        if (g.dw_bias) bias = g.dw_bias[n];
+        if (g.vec_t) {
+          float wsum = 0.f;
+          for (int tap = 0; tap < 9; ++tap) wsum += __half2float(__ushort_as_half(src[(size_t)tap * g.n_pre + n]));
+          tsum = g.vec_t[n] * wsum;
+        }
+      }
+      seed[i] = __half_as_ushort(__float2half_rn(bias));
+      seed[g.n_chunks * 32 + i] = __half_as_ushort(__float2half_rn(bias + tsum));
     }
   }
   tc_fence_before();
@@ -128,31 +160,47 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const int per_img = g.tiles_x * g.tiles_y;
+  const int n_super = (g.n_chunks + SC - 1) / SC;
+  const uint32_t a_buf_bytes = (uint32_t)g.nkb * A_KB_BYTES;               // one x-tile buffer
 
   if (warp == 0) {
     // ========================================= TMA producer ==========================================
-    uint32_t q = 0, it = 0;
-    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+    // order: A(0) | A(1) B(0,*) | A(2) B(1,*) | ...   (NA == 2: the next item's tile is requested before this item's weights)
+    auto load_a = [&](int item, uint32_t it) {
       const int b = item / per_img, r = item % per_img;
       const int x0 = (r % g.tiles_x) * TW - 1, y0 = (r / g.tiles_x) * TH - 1;
-      mbar_wait_sleep(smem_u32(&bar_aempty), (it & 1u) ^ 1u);
+      const uint32_t ab = it % NA;
+      mbar_wait_sleep(smem_u32(&bar_aempty[ab]), ((it / NA) & 1u) ^ 1u);
       if (elect_one()) {
-        const uint32_t full = smem_u32(&bar_afull);
+        const uint32_t full = smem_u32(&bar_afull[ab]);
         mbar_expect_tx(full, (uint32_t)g.nkb * (uint32_t)(NPIX * 128));
-        for (int kb = 0; kb < g.nkb; ++kb) tma_load_4d(base + (uint32_t)kb * A_KB_BYTES, &tmA, full, kb * 64, x0, y0, b);
+        for (int kb = 0; kb < g.nkb; ++kb) tma_load_4d(base + ab * a_buf_bytes + (uint32_t)kb * A_KB_BYTES, &tmA, full, kb * 64, x0, y0, b);
       }
       __syncwarp();
-      for (int c = 0; c < g.n_chunks; ++c, ++q) {
+    };
+    uint32_t q = 0, it = 0;
+    if (NA == 2 && (int)blockIdx.x < g.n_items) load_a(blockIdx.x, 0);
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+      if (NA == 2) {
+        if (item + (int)gridDim.x < g.n_items) load_a(item + gridDim.x, it + 1);
+      } else {
+        load_a(item, it);
+      }
+      for (int sc = 0; sc < n_super; ++sc, ++q) {
         const uint32_t st = q % kFwBStages;
+        const int nvalid = min(SC, g.n_chunks - sc * SC);
         mbar_wait_sleep(smem_u32(&bar_bempty[st]), ((q / kFwBStages) & 1u) ^ 1u);
         if (elect_one()) {
           const uint32_t full = smem_u32(&bar_bfull[st]);
           const uint32_t dst = base + g.off_b + st * b_stage_bytes;
-          const int r0 = GATE ? c * 16 : c * 32, r1 = GATE ? g.hp + c * 16 : c * 32 + 16;
-          mbar_expect_tx(full, b_stage_bytes);
+          mbar_expect_tx(full, (uint32_t)g.nkb * (uint32_t)nvalid * 4096u);
           for (int kb = 0; kb < g.nkb; ++kb) {
-            tma_load_2d(dst + (uint32_t)kb * B_KB_BYTES, &tmB, full, kb * 64, r0);
-            tma_load_2d(dst + (uint32_t)kb * B_KB_BYTES + 2048u, &tmB, full, kb * 64, r1);
+            for (int j = 0; j < nvalid; ++j) {               // chunk c occupies rows [32 j, 32 j + 32) of the stage
+              const int c = sc * SC + j;
+              const int r0 = GATE ? c * 16 : c * 32, r1 = GATE ? g.hp + c * 16 : c * 32 + 16;
+              tma_load_2d(dst + (uint32_t)kb * B_KB_BYTES + (uint32_t)j * 4096u, &tmB, full, kb * 64, r0);
+              tma_load_2d(dst + (uint32_t)kb * B_KB_BYTES + (uint32_t)j * 4096u + 2048u, &tmB, full, kb * 64, r1);
+            }
           }
         }
         __syncwarp();
@@ -160,45 +208,40 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ========================================= MMA issuer ============================================
-    // chunk c of an item goes to compute group c & 1; each group owns two accumulator buffers, so the tensor core runs
-    // up to two chunks per group ahead of the CUDA cores
-    const uint32_t idesc = make_idesc_f16(T::kFmt, 128, kFwChunk, 0, 0);
+    // one tcgen05.mma covers a whole super-chunk (SC chunks = SC * 32 accumulator columns per 128-pixel row group): small-N
+    // MMAs are latency bound (~110 cycles each whatever N), so N is made as large as TMEM double buffering allows
     const uint64_t desc_hi = make_sdesc_sw128(0, 16, 1024);           // everything but the start address
     uint32_t q = 0, it = 0;
-    uint32_t cnt0 = 0u, cnt1 = 0u;                    // chunks issued so far per group
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
-      mbar_wait(smem_u32(&bar_aready), it & 1u);
+      const uint32_t ab = it % NA;
+      mbar_wait(smem_u32(&bar_aready[ab]), (it / NA) & 1u);
       tc_fence_after();
-      for (int c = 0; c < g.n_chunks; ++c, ++q) {
+      for (int sc = 0; sc < n_super; ++sc, ++q) {
         const uint32_t st = q % kFwBStages, ph = (q / kFwBStages) & 1u;
-        const uint32_t grp = (uint32_t)c & 1u;
-        const uint32_t cnt = grp ? cnt1 : cnt0;
-        const uint32_t buf = grp * 2u + (cnt & 1u);
+        const uint32_t sb = q & 1u;
+        const int nvalid = min(SC, g.n_chunks - sc * SC);
+        const uint32_t idesc = make_idesc_f16(T::kFmt, 128, nvalid * kFwChunk, 0, 0);
         mbar_wait(smem_u32(&bar_bfull[st]), ph);
-        mbar_wait(smem_u32(&bar_tempty[buf]), ((cnt >> 1) & 1u) ^ 1u);
-        if (grp) ++cnt1; else ++cnt0;
+        mbar_wait(smem_u32(&bar_tempty[sb]), ((q >> 1) & 1u) ^ 1u);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t b_lo = (base + g.off_b + st * b_stage_bytes) >> 4;
+          for (int kb = 0; kb < g.nkb; ++kb) {
+            const int rem = g.C - kb * 64;
+            const int ksteps = rem >= 64 ? 4 : (rem + 15) >> 4;
+            const uint64_t bd = desc_hi | (uint64_t)((b_lo + (uint32_t)kb * (B_KB_BYTES >> 4)) & 0x3fffu);
+            for (int k = 0; k < ksteps; ++k) {         // 32 bytes (16 elements) along K per step: +2 in the address field
 #pragma unroll
-          for (int t = 0; t < MT; ++t) {
-            const uint32_t d = tmem_base + buf * (uint32_t)(MT * kFwChunk) + (uint32_t)(t * kFwChunk);
-            const uint32_t a_lo = (base + (uint32_t)t * 16384u) >> 4;
-            uint32_t accum = 0u;
-            for (int kb = 0; kb < g.nkb; ++kb) {
-              const int rem = g.C - kb * 64;
-              const int ksteps = rem >= 64 ? 4 : (rem + 15) >> 4;
-              const uint64_t ad = desc_hi | (uint64_t)((a_lo + (uint32_t)kb * (A_KB_BYTES >> 4)) & 0x3fffu);
-              const uint64_t bd = desc_hi | (uint64_t)((b_lo + (uint32_t)kb * (B_KB_BYTES >> 4)) & 0x3fffu);
-              for (int k = 0; k < ksteps; ++k) {       // 32 bytes (16 elements) along K per step: +2 in the address field
-                umma_f16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, accum);
-                accum = 1u;
+              for (int t = 0; t < MT; ++t) {           // row groups innermost: consecutive MMAs hit different accumulators
+                const uint32_t d = tmem_base + sb * (uint32_t)(MT * SCN) + (uint32_t)(t * SCN);
+                const uint32_t a_lo = (base + ab * a_buf_bytes + (uint32_t)kb * A_KB_BYTES + (uint32_t)t * 16384u) >> 4;
+                umma_f16(d, (desc_hi | (uint64_t)(a_lo & 0x3fffu)) + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
               }
             }
           }
           umma_commit(smem_u32(&bar_bempty[st]));
-          umma_commit(smem_u32(&bar_tfull[buf]));
-          if (c == g.n_chunks - 1) umma_commit(smem_u32(&bar_aempty));        // x tile no longer needed by the tensor core
+          umma_commit(smem_u32(&bar_tfull[sb]));
+          if (sc == n_super - 1) umma_commit(smem_u32(&bar_aempty[ab]));      // x tile no longer needed by the tensor core
         }
         __syncwarp();
       }
@@ -227,12 +270,13 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     const int nbar = 1 + grp * 2;                    // named barriers of this group: nbar, nbar + 1
     auto grp_bar = [](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kFwGroup) : "memory"); };
-    uint32_t it = 0, uses = 0;
-    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
-      const int b = item / per_img, rr = item % per_img;
+    // ---- LayerNorm of an item's halo'd tile in place; pixels outside the image stay zero ----
+    auto layernorm_tile = [&](int item, uint32_t itn) {
+      const int rr = item % per_img;
       const int x0 = (rr % g.tiles_x) * TW, y0 = (rr / g.tiles_x) * TH;
-      // ---- LayerNorm of the halo'd tile in place (one pixel per thread); pixels outside the image stay zero ----
-      mbar_wait(smem_u32(&bar_afull), it & 1u);
+      const uint32_t ab = itn % NA;
+      uint8_t* a_tile = base_ptr + (size_t)ab * a_buf_bytes;
+      mbar_wait(smem_u32(&bar_afull[ab]), (itn / NA) & 1u);
       if (g.ln_mode) {
         // four threads per pixel; thread `part` owns the physical 16-byte chunks 2*part + (e ^ (m & 1)), e = 0, 1, of every
         // k-block (the row parity term keeps the quarter-warp's LDS.128 conflict free); statistics meet through shuffles
@@ -244,7 +288,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           float s1 = 0.f, s2 = 0.f;
           for (int kb = 0; kb < g.nkb; ++kb) {
             if (act) {
-              const uint8_t* a_row = base_ptr + (size_t)kb * A_KB_BYTES + (size_t)m * 128;
+              const uint8_t* a_row = a_tile + (size_t)kb * A_KB_BYTES + (size_t)m * 128;
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const uint4 v = *reinterpret_cast<const uint4*>(a_row + ((2 * part + (e ^ (m & 1))) << 4));
@@ -267,7 +311,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const float shift = g.ln_mode == 2 ? 0.f : -rstd * mu;            // BiasFree: numerator not centred
           for (int kb = 0; kb < g.nkb; ++kb) {
             if (act) {
-              uint8_t* a_row = base_ptr + (size_t)kb * A_KB_BYTES + (size_t)m * 128;
+              uint8_t* a_row = a_tile + (size_t)kb * A_KB_BYTES + (size_t)m * 128;
               const int valid = min(64, g.C - kb * 64);                       // channels of this k-block that exist
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
@@ -288,9 +332,22 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       fence_proxy_async();                           // generic-proxy writes of the tile -> visible to tcgen05.mma
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_aready));
+      if (lane == 0) mbar_arrive(smem_u32(&bar_aready[ab]));
+    };
+    uint32_t it = 0, uses = 0;
+    if (NA == 2 && (int)blockIdx.x < g.n_items) layernorm_tile(blockIdx.x, 0);
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+      const int b = item / per_img, rr = item % per_img;
+      const int x0 = (rr % g.tiles_x) * TW, y0 = (rr / g.tiles_x) * TH;
+      if (NA == 2) {
+        if (item + (int)gridDim.x < g.n_items) layernorm_tile(item + gridDim.x, it + 1);   // next item's tile, one item ahead
+      } else {
+        layernorm_tile(item, it);
+      }
 
-      // inside-the-image flags of the pixels this thread drains (t[n] is added inside only)
+      // interior tile: the halo is inside the image too, so t[n] can ride on the accumulator seed instead of the drain
+      const bool interior = x0 >= 1 && y0 >= 1 && x0 + TW + 1 <= g.W && y0 + TH + 1 <= g.H;
+      // inside-the-image flags of the pixels this thread drains (border tiles: t[n] is added inside only)
       bool inside[MT];
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
@@ -299,21 +356,25 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         inside[t] = m < NPIX && py >= 0 && py < g.H && px >= 0 && px < g.W;
       }
 
-      for (int c = grp; c < g.n_chunks; c += 2, ++uses) {
+      for (int sc = 0; sc < n_super; ++sc, ++uses) {
+      // the group's chunks of this super-chunk: j = j0, j0 + 2, ... (j0 alternates per item so odd chunk counts balance out)
+      const uint32_t sb = uses & 1u;
+      mbar_wait(smem_u32(&bar_tfull[sb]), (uses >> 1) & 1u);
+      tc_fence_after();
+      for (int j = (grp + (int)it) & 1; j < SC; j += 2) {
+        const int c = sc * SC + j;
+        if (c >= g.n_chunks) break;
         // ---- drain: TMEM -> (+ t[n]) -> fp16 shared-memory tile of this group ----
-        const uint32_t buf = (uint32_t)grp * 2u + (uses & 1u);
-        mbar_wait(smem_u32(&bar_tfull[buf]), (uses >> 1) & 1u);
-        tc_fence_after();
         const int nb = GATE ? (slice ? g.hp + c * 16 : c * 16) : c * 32 + slice * 16;    // first pre-conv channel of this warp's slice
 #pragma unroll
         for (int t = 0; t < MT; ++t) {
           const int m = t * 128 + quarter * 32 + lane;
           uint32_t acc[16];
-          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)(MT * kFwChunk) + (uint32_t)(t * kFwChunk + slice * 16), acc);
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + sb * (uint32_t)(MT * SCN) + (uint32_t)(t * SCN + j * kFwChunk + slice * 16), acc);
           tmem_ld_wait();
-          if (m < NPIX) {
+          if (m < NPIX && !(g.dbg & 2)) {
             uint32_t pk[8];
-            if (g.has_t && inside[t]) {
+            if (g.has_t && !interior && inside[t]) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float4 t4 = reinterpret_cast<const float4*>(svec + nb)[e];
@@ -338,29 +399,22 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[buf]));      // accumulator buffer may be overwritten
         grp_bar(nbar);                                                 // fp16 tile complete
 
         // ---- stencil from shared memory ----
-        if (GATE) {
+        if (g.dbg & 1) {
+        } else if (GATE) {
           const int ch = c * 16 + cg * 4;                              // gated channel of this thread
+          const uint8_t* wbase = reinterpret_cast<const uint8_t*>(sdw) + (size_t)c * 576 + cg * 8;
           uint2 w1[9], w2[9];
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            w1[t] = *reinterpret_cast<const uint2*>(sdw + (size_t)t * n_vec + ch);
-            w2[t] = *reinterpret_cast<const uint2*>(sdw + (size_t)t * n_vec + g.hp + ch);
+            w1[t] = *reinterpret_cast<const uint2*>(wbase + t * 32);
+            w2[t] = *reinterpret_cast<const uint2*>(wbase + 288 + t * 32);
           }
-          // the depthwise bias seeds the fp16 accumulators (zero when the conv has no bias)
-          uint32_t b1[2] = {0u, 0u}, b2[2] = {0u, 0u};
-          if (g.has_bias) {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              b1[i] = pack_f16_sat(sbias[ch + 2 * i], sbias[ch + 2 * i + 1]);
-              b2[i] = pack_f16_sat(sbias[g.hp + ch + 2 * i], sbias[g.hp + ch + 2 * i + 1]);
-            }
-          }
+          // accumulator seeds: depthwise bias (+ the conv of the constant t on interior tiles)
+          const uint32_t* sd = sseed + (interior ? g.n_chunks * 16 : 0) + c * 16 + cg * 2;
+          const uint32_t b1[2] = {sd[0], sd[1]}, b2[2] = {sd[8], sd[9]};
           const int x = x0 + tx;
           const bool ok = ch < g.hp && x < g.W;
           unsigned short* outp = reinterpret_cast<unsigned short*>(g.out) + (size_t)b * g.out_bstride + ch +
@@ -397,19 +451,17 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               uint2 ov;
               ov.x = pack2<T>(gelu_erf(pa.x) * qa.x, gelu_erf(pa.y) * qa.y);
               ov.y = pack2<T>(gelu_erf(pb.x) * qb.x, gelu_erf(pb.y) * qb.y);
-              if (ok && y0 + band * R + o < g.H) *reinterpret_cast<uint2*>(outp + o * out_row) = ov;
+              if (ok && y0 + band * R + o < g.H && !(g.dbg & 4)) *reinterpret_cast<uint2*>(outp + o * out_row) = ov;
             }
           }
         } else {
           const int ch = c * 32 + cg * 8;
+          const uint8_t* wbase = reinterpret_cast<const uint8_t*>(sdw) + (size_t)c * 576 + cg * 16;
           uint4 wt[9];
 #pragma unroll
-          for (int t = 0; t < 9; ++t) wt[t] = *reinterpret_cast<const uint4*>(sdw + (size_t)t * n_vec + ch);
-          uint32_t bb[4] = {0u, 0u, 0u, 0u};             // the depthwise bias seeds the fp16 accumulators
-          if (g.has_bias) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) bb[i] = pack_f16_sat(sbias[ch + 2 * i], sbias[ch + 2 * i + 1]);
-          }
+          for (int t = 0; t < 9; ++t) wt[t] = *reinterpret_cast<const uint4*>(wbase + t * 64);
+          const uint32_t* sd = sseed + (interior ? g.n_chunks * 16 : 0) + c * 16 + cg * 4;
+          const uint32_t bb[4] = {sd[0], sd[1], sd[2], sd[3]};
           const int x = x0 + tx;
           const bool ok = ch < g.n_pre && x < g.W;
           unsigned short* outp = reinterpret_cast<unsigned short*>(g.out) + (size_t)b * g.out_bstride + ch +
@@ -446,11 +498,15 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const float2 f = h2_to_f2(p[o % 3][e]);
                 op[e] = pack2<T>(f.x, f.y);
               }
-              if (ok && y0 + band * R + o < g.H) *reinterpret_cast<uint4*>(outp + o * out_row) = ov;
+              if (ok && y0 + band * R + o < g.H && !(g.dbg & 4)) *reinterpret_cast<uint4*>(outp + o * out_row) = ov;
             }
           }
         }
         grp_bar(nbar + 1);                                             // fp16 tile may be overwritten
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[sb]));          // this warp is done with the super-chunk's accumulators
       }
     }
   }
@@ -462,12 +518,32 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // ---------------------------------------------------------------------------------------------------
 struct FwPlan {
-  int mt, tw;              // template configuration
+  int mt, tw, na, sc;      // template configuration
   uint32_t smem;
   FwArgs g;
 };
 
 static int tile_h(int mt, int tw) { return mt == 3 ? (tw == 32 ? 8 : 16) : 12; }
+
+static bool plan_fits(const PirPwDw* d, FwPlan* p, int mt, int na, int sc) {
+  FwArgs& g = p->g;
+  if (2 * mt * sc * kFwChunk > 512) return false;                      // TMEM
+  // shared-memory plan: [A: na x nkb x MT x 16 KB] [B ring: 2 x nkb x SC x 4 KB] [fp16 tiles: 2 x MT x 8 KB] [dw taps] [t] [accumulator seeds]
+  uint32_t off = (uint32_t)na * g.nkb * mt * 16384u;
+  g.off_b = off; off += (uint32_t)kFwBStages * g.nkb * (uint32_t)sc * 4096u;
+  g.off_conv = off; off += 2u * (uint32_t)mt * 128u * 64u;
+  g.off_dw = off; off += (uint32_t)g.n_chunks * 576u;
+  g.off_vec = off; off += (uint32_t)g.n_vec * 4u;
+  g.off_bias = off; off += (uint32_t)g.n_chunks * 128u;
+  if (off + 1024u > 227u * 1024u - 1024u) return false;
+  p->mt = mt; p->na = na; p->sc = sc; p->smem = off + 1024u;
+  p->tw = (mt == 3 && d->W > 16) ? 32 : 16;
+  const int th = tile_h(mt, p->tw);
+  g.tiles_x = (d->W + p->tw - 1) / p->tw;
+  g.tiles_y = (d->H + th - 1) / th;
+  g.n_items = g.tiles_x * g.tiles_y * d->B;
+  return true;
+}
 
 static int plan_pwdw(const PirPwDw* d, FwPlan* p) {
   FwArgs& g = p->g;
@@ -482,24 +558,14 @@ static int plan_pwdw(const PirPwDw* d, FwPlan* p) {
   g.n_vec = gate ? g.hp + g.n_chunks * 16 : g.n_chunks * 32;
   g.has_bias = d->dw_bias ? 1 : 0;
   g.has_t = d->vec_t ? 1 : 0;
-  // shared-memory plan: [A: nkb x MT x 16 KB] [B ring: 4 x nkb x 4 KB] [fp16 tiles: 2 x MT x 8 KB] [dw taps] [t] [dw bias]
-  for (int mt = 3; mt >= 2; --mt) {
-    uint32_t off = (uint32_t)g.nkb * mt * 16384u;
-    g.off_b = off; off += (uint32_t)kFwBStages * g.nkb * (uint32_t)kFwChunk * 128u;
-    g.off_conv = off; off += 2u * (uint32_t)mt * 128u * 64u;
-    g.off_dw = off; off += (uint32_t)((9 * g.n_vec * 2 + 15) / 16 * 16);
-    g.off_vec = off; off += (uint32_t)g.n_vec * 4u;
-    g.off_bias = off; off += (uint32_t)g.n_vec * 4u;
-    if (off + 1024u <= 227u * 1024u - 1024u) {
-      p->mt = mt; p->smem = off + 1024u;
-      p->tw = (mt == 3 && d->W > 16) ? 32 : 16;
-      const int th = tile_h(mt, p->tw);
-      g.tiles_x = (d->W + p->tw - 1) / p->tw;
-      g.tiles_y = (d->H + th - 1) / th;
-      g.n_items = g.tiles_x * g.tiles_y * d->B;
-      return PIR_OK;
-    }
-  }
+  { const char* e = getenv("PIR_PWDW_DBG"); g.dbg = e ? atoi(e) : 0; }
+  // configurations <MT row groups, NA x-tile buffers, SC chunks per MMA>, best first.  PIR_PWDW_CFG="<mt><na><sc>" forces one.
+  static const char* force = getenv("PIR_PWDW_CFG");
+  if (force && force[0] && force[1] && force[2])
+    return plan_fits(d, p, force[0] - '0', force[1] - '0', force[2] - '0') ? PIR_OK : PIR_ERR_UNSUPPORTED;
+  static const int pref[][3] = {{2, 2, 4}, {2, 1, 4}, {2, 2, 2}, {2, 1, 2}, {3, 1, 2}};
+  for (const auto& c : pref)
+    if (plan_fits(d, p, c[0], c[1], c[2])) return PIR_OK;
   return PIR_ERR_UNSUPPORTED;
 }
 
@@ -545,9 +611,13 @@ static int launch_pwdw(const PirPwDw* d, cudaStream_t stream) {
     const uint32_t box[2] = {64, 16};
     if (int e = pir_make_tmap(&tmB, dt, 2, d->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   }
-  if (p.mt == 3 && p.tw == 32) return launch_cfg<T, FwCfg<3, 32, 4, GATE>>(p, tmA, tmB, stream);
-  if (p.mt == 3) return launch_cfg<T, FwCfg<3, 16, 4, GATE>>(p, tmA, tmB, stream);
-  return launch_cfg<T, FwCfg<2, 16, 3, GATE>>(p, tmA, tmB, stream);
+  if (p.mt == 2 && p.na == 2 && p.sc == 4) return launch_cfg<T, FwCfg<2, 16, 3, GATE, 2, 4>>(p, tmA, tmB, stream);
+  if (p.mt == 2 && p.na == 1 && p.sc == 4) return launch_cfg<T, FwCfg<2, 16, 3, GATE, 1, 4>>(p, tmA, tmB, stream);
+  if (p.mt == 2 && p.na == 2 && p.sc == 2) return launch_cfg<T, FwCfg<2, 16, 3, GATE, 2, 2>>(p, tmA, tmB, stream);
+  if (p.mt == 2 && p.na == 1 && p.sc == 2) return launch_cfg<T, FwCfg<2, 16, 3, GATE, 1, 2>>(p, tmA, tmB, stream);
+  if (p.mt == 3 && p.na == 1 && p.sc == 2 && p.tw == 32) return launch_cfg<T, FwCfg<3, 32, 4, GATE, 1, 2>>(p, tmA, tmB, stream);
+  if (p.mt == 3 && p.na == 1 && p.sc == 2) return launch_cfg<T, FwCfg<3, 16, 4, GATE, 1, 2>>(p, tmA, tmB, stream);
+  return pir_fail(PIR_ERR_UNSUPPORTED, "pir_pwdw: configuration <%d,%d,%d> is not compiled", p.mt, p.na, p.sc);
 }
 
 }  // namespace pir
