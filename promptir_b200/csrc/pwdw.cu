@@ -59,6 +59,26 @@ __device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {
 __device__ __forceinline__ uint32_t hfma2_u(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
 }
+__device__ __forceinline__ uint32_t hmul2_u(uint32_t a, uint32_t b) {
+  uint32_t r; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t hmin2_u(uint32_t a, uint32_t b) {
+  uint32_t r; asm("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t htanh2_u(uint32_t a) {
+  uint32_t r; asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a)); return r;
+}
+// gelu(p) * q on packed fp16 pairs, for 16-bit outputs with 8 mantissa bits (bf16): the same three-coefficient erf-GELU fit as
+// gelu_erf() in its tanh form, 0.5 p (1 + tanh(p (a + b u + c u^2))), u = min(p^2, 25), evaluated in fp16 (MUFU.TANH.F16).
+// Its error (~5e-4 * |p q|) stays 4-8x below the bf16 rounding of the result; fp16 outputs take the fp32 path instead.
+__device__ __forceinline__ uint32_t gelu_gate_h2(uint32_t p, uint32_t q) {
+  constexpr uint32_t kA = 0x3a613a61u, kB = 0x28bd28bdu, kC = 0x8dc28dc2u, k25 = 0x4e404e40u, kHalf = 0x38003800u;   // 0.7975, 0.037006, -3.5152e-4, 25, 0.5
+  const uint32_t u = hmin2_u(hmul2_u(p, p), k25);
+  const uint32_t t = hfma2_u(u, hfma2_u(u, kC, kB), kA);
+  const uint32_t th = htanh2_u(hmul2_u(p, t));
+  const uint32_t hx = hmul2_u(p, kHalf);
+  return hmul2_u(hfma2_u(hx, th, hx), q);
+}
 __device__ __forceinline__ float2 h2_to_f2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
@@ -446,11 +466,17 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             const int o = r - 2;
             if (o >= 0) {
-              const float2 pa = h2_to_f2(p[o % 3][0]), pb = h2_to_f2(p[o % 3][1]);
-              const float2 qa = h2_to_f2(qq[o % 3][0]), qb = h2_to_f2(qq[o % 3][1]);
               uint2 ov;
-              ov.x = pack2<T>(gelu_erf(pa.x) * qa.x, gelu_erf(pa.y) * qa.y);
-              ov.y = pack2<T>(gelu_erf(pb.x) * qb.x, gelu_erf(pb.y) * qb.y);
+              if (T::kFmt == 1) {                                       // bf16 output: packed fp16 GELU gate, then convert
+                const float2 ga = h2_to_f2(gelu_gate_h2(p[o % 3][0], qq[o % 3][0])), gb = h2_to_f2(gelu_gate_h2(p[o % 3][1], qq[o % 3][1]));
+                ov.x = pack2<T>(ga.x, ga.y);
+                ov.y = pack2<T>(gb.x, gb.y);
+              } else {
+                const float2 pa = h2_to_f2(p[o % 3][0]), pb = h2_to_f2(p[o % 3][1]);
+                const float2 qa = h2_to_f2(qq[o % 3][0]), qb = h2_to_f2(qq[o % 3][1]);
+                ov.x = pack2<T>(gelu_erf(pa.x) * qa.x, gelu_erf(pa.y) * qa.y);
+                ov.y = pack2<T>(gelu_erf(pb.x) * qb.x, gelu_erf(pb.y) * qb.y);
+              }
               if (ok && y0 + band * R + o < g.H && !(g.dbg & 4)) *reinterpret_cast<uint2*>(outp + o * out_row) = ov;
             }
           }
