@@ -138,8 +138,10 @@ static int launch_prompt(const PirPrompt* d, cudaStream_t s) {
       reinterpret_cast<const unsigned short*>(d->x), d->x_pitch, d->x_bstride, HW, d->C, chunk, d->ws);
   if (int e = pir_check_launch("pir_prompt_gen(pool)")) return e;
   const long long total = (long long)HW * (d->D / 8);
+  // every block re-derives the component weights from the pooled partials, so keep the grid to a few blocks per SM in total
   int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int cap = (148 * 4 + d->B - 1) / d->B;
+  if (blocks > cap) blocks = cap;
   prompt_mix_kernel<T><<<dim3(blocks, d->B), 256, d->C * sizeof(float), s>>>(
       d->ws, nchunks, HW, d->C, d->lin_w, d->lin_b, d->L, d->prompt, d->D, d->S, d->H, d->W,
       reinterpret_cast<unsigned short*>(d->out), d->out_pitch, d->out_bstride, d->weights_out);
@@ -165,8 +167,8 @@ patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w, c
   const int pl = threadIdx.x / groups;
   const int ppb = blockDim.x / groups;
   const int b = blockIdx.y;
-  const long long p = (long long)blockIdx.x * ppb + pl;
-  if (p >= (long long)H * W) return;
+  // grid-stride over pixel groups: the 3x3xCinxCout weights are staged once per (persistent) block, not once per 42 pixels
+  for (long long p = (long long)blockIdx.x * ppb + pl; p < (long long)H * W; p += (long long)gridDim.x * ppb) {
   const int y = (int)(p / W), x = (int)(p % W);
   float acc[8];
 #pragma unroll
@@ -186,6 +188,7 @@ patch_embed_kernel(const float* __restrict__ img, const float* __restrict__ w, c
   ov.x = pack2<T>(acc[0], acc[1]); ov.y = pack2<T>(acc[2], acc[3]);
   ov.z = pack2<T>(acc[4], acc[5]); ov.w = pack2<T>(acc[6], acc[7]);
   *reinterpret_cast<uint4*>(out + (size_t)b * bstride + (size_t)p * pitch + g * 8) = ov;
+  }
 }
 
 template <class T>
@@ -196,7 +199,10 @@ static int launch_patch_embed(const PirPatchEmbed* d, cudaStream_t s) {
   const long long HW = (long long)d->H * d->W;
   const size_t smem = (size_t)d->Cin * 9 * d->Cout * sizeof(float);
   if (smem > 48 * 1024) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_patch_embed: weight does not fit 48 KB of shared memory");
-  patch_embed_kernel<T><<<dim3((unsigned)((HW + ppb - 1) / ppb), d->B), threads, smem, s>>>(
+  long long gx = (HW + ppb - 1) / ppb;
+  const long long cap = (148 * 8 + d->B - 1) / d->B;                 // ~8 resident blocks per SM over the whole batch
+  if (gx > cap) gx = cap;
+  patch_embed_kernel<T><<<dim3((unsigned)gx, d->B), threads, smem, s>>>(
       d->img, d->w, d->bias, d->H, d->W, d->Cin, d->Cout, reinterpret_cast<unsigned short*>(d->out), d->out_pitch, d->out_bstride);
   return pir_check_launch("pir_patch_embed");
 }

@@ -32,7 +32,8 @@ Tensor = torch.Tensor
 
 
 class Engine:
-    def __init__(self, module, batch: int, height: int, width: int, device, dtype: torch.dtype = torch.bfloat16):
+    def __init__(self, module, batch: int, height: int, width: int, device, dtype: torch.dtype = torch.bfloat16,
+                 img_in: Optional[Tensor] = None, out: Optional[Tensor] = None):
         if height % 8 or width % 8:
             raise ValueError("height and width must be multiples of 8")
         self.m = module
@@ -50,6 +51,7 @@ class Engine:
         self._packers: List[Callable[[], None]] = []
         self._graph = None
         self._param_version = -1
+        self._io = (img_in, out)
         self._build()
 
     # ------------------------------------------------------------------------------------------------
@@ -139,8 +141,11 @@ class Engine:
         self.r3 = self._zeros(B, h3, w3, m.reduce_noise_level3.out_channels)
         self.r2 = self._zeros(B, h2, w2, m.reduce_noise_level2.out_channels)
         self.r1 = self._zeros(B, h1, w1, m.reduce_noise_level1.out_channels)
-        self.img_in = torch.zeros(B, m.patch_embed.proj.in_channels, H, W, dtype=torch.float32, device=self.device)
-        self.out = torch.zeros(B, m.output.out_channels, H, W, dtype=torch.float32, device=self.device)
+        self.img_in = self._io[0] if self._io[0] is not None else torch.zeros(B, m.patch_embed.proj.in_channels, H, W, dtype=torch.float32,
+                                                                               device=self.device)
+        self.out = self._io[1] if self._io[1] is not None else torch.zeros(B, m.output.out_channels, H, W, dtype=torch.float32,
+                                                                            device=self.device)
+        assert self.img_in.is_contiguous() and self.out.is_contiguous() and self.img_in.shape[0] == B and self.out.shape[0] == B
 
         enc1 = self.cat1[..., up1:]
         enc2 = self.cat2[..., up2:]
@@ -329,6 +334,71 @@ class Engine:
     def kernels_per_forward(self) -> int:
         per = {"mdta_finalize": 2, "prompt": 2}
         return sum(per.get(r["kind"], 1) for r in self.ops)
+
+
+class SplitEngine:
+    """Two half-batch Engines replayed as two parallel branches of ONE CUDA graph.
+
+    Images are independent, so the two halves have no dependency on each other: while one branch sits in a latency-bound
+    step (the tiny MDTA finalize kernels, the 32x32-level blocks, kernel tails) the other branch's persistent kernels take
+    the idle SMs.  Same interface as Engine (img_in / out are the full-batch tensors; the halves work on views)."""
+
+    def __init__(self, module, batch: int, height: int, width: int, device, dtype: torch.dtype = torch.bfloat16):
+        assert batch >= 2
+        self.m, self.B, self.H, self.W = module, batch, height, width
+        self.device, self.dtype = torch.device(device), dtype
+        self.cuda = self.device.type == "cuda"
+        cin, cout = module.patch_embed.proj.in_channels, module.output.out_channels
+        self.img_in = torch.zeros(batch, cin, height, width, dtype=torch.float32, device=self.device)
+        self.out = torch.zeros(batch, cout, height, width, dtype=torch.float32, device=self.device)
+        h = batch // 2
+        self.parts = [Engine(module, h, height, width, device, dtype, self.img_in[:h], self.out[:h]),
+                      Engine(module, batch - h, height, width, device, dtype, self.img_in[h:], self.out[h:])]
+        self.ops = self.parts[0].ops + self.parts[1].ops
+        self.launches = self.parts[0].launches + self.parts[1].launches
+        self._graph = None
+        self._side = torch.cuda.Stream(self.device) if self.cuda else None
+
+    def refresh_weights(self) -> None:
+        for p in self.parts:
+            p.refresh_weights()
+
+    def launch_all(self, stream: int) -> None:
+        for p in self.parts:
+            p.launch_all(stream)
+
+    def kernels_per_forward(self) -> int:
+        return sum(p.kernels_per_forward() for p in self.parts)
+
+    def run(self, img: Tensor, use_graph: bool = True) -> Tensor:
+        if not self.cuda:
+            raise RuntimeError("promptir_b200.SplitEngine.run needs a CUDA (sm_100a) device; there is no CPU path")
+        if tuple(img.shape) != tuple(self.img_in.shape):
+            raise ValueError(f"engine built for {tuple(self.img_in.shape)}, got {tuple(img.shape)}")
+        for p in self.parts:
+            if p._current_version() != p._param_version:
+                p.refresh_weights()
+        self.img_in.copy_(img)
+        self.replay(use_graph)
+        return self.out.clone()
+
+    def replay(self, use_graph: bool = True) -> None:
+        if not use_graph:
+            self.launch_all(torch.cuda.current_stream(self.device).cuda_stream)
+            return
+        if self._graph is None:
+            self.launch_all(torch.cuda.current_stream(self.device).cuda_stream)     # warm: kernel attributes outside capture
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                main = torch.cuda.current_stream(self.device)
+                self._side.wait_stream(main)                                         # fork
+                self.parts[0].launch_all(main.cuda_stream)
+                with torch.cuda.stream(self._side):
+                    self.parts[1].launch_all(self._side.cuda_stream)
+                main.wait_stream(self._side)                                         # join
+            self._graph = g
+        self._graph.replay()
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -74,6 +74,11 @@ def main():
         return a.elapsed_time(b) / n
     te = timed(lambda: eng.replay(False))
     tg = timed(lambda: eng.replay(True))
+    from promptir_b200.engine import SplitEngine
+    sp = SplitEngine(m, B, H, W, "cuda", dt)
+    sp.img_in.copy_(eng.img_in)
+    ts = timed(lambda: sp.replay(True))
+    print(f"split graph {ts:.3f} ms ({B * H * W / 1e6 / ts * 1e3:.1f} MP/s)   max |split - whole| = {(sp.out - eng.out).abs().max().item():.3e}")
     mp = B * H * W / 1e6
     print(f"eager {te:.3f} ms ({mp / te * 1e3:.1f} MP/s)   graph {tg:.3f} ms ({mp / tg * 1e3:.1f} MP/s)")
     os.makedirs("gpurun_out", exist_ok=True)
