@@ -44,7 +44,7 @@ struct FwArgs {
   int tiles_x, tiles_y, n_items;
   int has_bias;            // depthwise bias present
   int has_t;               // additive per-channel vector present
-  int dbg;                 // diagnostics (PIR_PWDW_DBG): 1 skip the stencil, 2 skip the drain arithmetic, 4 skip the stores
+  int dbg;                 // diagnostics (PIR_PWDW_DBG): 1 skip the stencil, 2 skip the drain arithmetic, 4 skip the stores, 8 skip LayerNorm, 16 skip TMEM loads
   uint32_t off_b, off_conv, off_dw, off_vec, off_bias;   // byte offsets from the 1024-aligned base
   const void* dw_w;        // [9][n_pre] fp16
   const float* dw_bias;    // [n_pre] or null
@@ -297,7 +297,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t ab = itn % NA;
       uint8_t* a_tile = base_ptr + (size_t)ab * a_buf_bytes;
       mbar_wait(smem_u32(&bar_afull[ab]), (itn / NA) & 1u);
-      if (g.ln_mode) {
+      if (g.ln_mode && !(g.dbg & 8)) {
         // four threads per pixel; thread `part` owns the physical 16-byte chunks 2*part + (e ^ (m & 1)), e = 0, 1, of every
         // k-block (the row parity term keeps the quarter-warp's LDS.128 conflict free); statistics meet through shuffles
         for (int task0 = 0; task0 < NPIX * 4; task0 += kFwCompute) {
@@ -390,8 +390,10 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int t = 0; t < MT; ++t) {
           const int m = t * 128 + quarter * 32 + lane;
           uint32_t acc[16];
-          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + sb * (uint32_t)(MT * SCN) + (uint32_t)(t * SCN + j * kFwChunk + slice * 16), acc);
-          tmem_ld_wait();
+          if (!(g.dbg & 16)) {
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + sb * (uint32_t)(MT * SCN) + (uint32_t)(t * SCN + j * kFwChunk + slice * 16), acc);
+            tmem_ld_wait();
+          }
           if (m < NPIX && !(g.dbg & 2)) {
             uint32_t pk[8];
             if (g.has_t && !interior && inside[t]) {
