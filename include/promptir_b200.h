@@ -159,6 +159,152 @@ int pir_patch_embed(const PirPatchEmbed* d, void* stream);
 int pir_tile_blend(const float* tiles, int32_t ny, int32_t nx, const int32_t* ys, const int32_t* xs, int32_t C,
                    int32_t th, int32_t tw, float* out, int32_t H, int32_t W, void* stream);
 
+/* ==================================================================================================================
+ * Training: forward extras and the backward kernels (reference: autograd of net/model.py under train.py:37-46).
+ * Gradients of activations are NHWC 16-bit like the activations; parameter gradients are fp32 in the parameter's own
+ * layout.  `inv_scale` undoes a static loss scale the caller applied to dL/d(out).
+ * ================================================================================================================== */
+
+/* ---- LayerNorm over channels, split from the GEMM for training (model.py:39-41, 60-63) ---------------------------
+ * pir_ln_fwd: xhat = (x - mu) * rstd (WithBias) or x * rstd (BiasFree), rounded to 16 bits; rstd[b*H*W + p] fp32.
+ *             (gamma/beta live in the following 1x1 conv's packed weights.)
+ * pir_ln_bwd: g += rstd * (d - mean_c(d) - xhat * mean_c(d * xhat))                    (WithBias)
+ *             g += rstd * (d - (xhat - mean_c(xhat)) * mean_c(d * xhat))               (BiasFree)
+ *             where d = dL/d(xhat) is passed in `x`.                                                            */
+typedef struct PirLn {
+  int32_t dtype, ln_mode;
+  int32_t B, H, W, C;
+  const void* x; int64_t x_pitch, x_bstride;
+  void* xhat; int64_t xh_pitch, xh_bstride;
+  float* rstd;
+  void* g; int64_t g_pitch, g_bstride;
+} PirLn;
+int pir_ln_fwd(const PirLn* d, void* stream);
+int pir_ln_bwd(const PirLn* d, void* stream);
+
+/* ---- weight gradient of a 1x1 / 3x3 convolution: split-K tcgen05 Gram over the pixels ----------------------------
+ * ws[(img*splits + s)][tap][m][n] = sum over the pixels p of split s of  a[p, m] * b[p + off(tap), n]
+ * (tap = ky*3 + kx, off = (ky-1, kx-1), zero outside the image; taps = 1 or 9).  per_image = 0: the splits cover the
+ * whole batch (P = splits partials); per_image = 1: every image keeps its own P = B*splits partials (MDTA backward).
+ * colsum (optional) receives the matching partial column sums of a: colsum[part][m].  fp32, deterministic.          */
+typedef struct PirWgrad {
+  int32_t dtype;
+  int32_t B, H, W;
+  int32_t M, N, taps;
+  int32_t per_image, splits;
+  const void* a; int64_t a_pitch, a_bstride;
+  const void* b; int64_t b_pitch, b_bstride;
+  float* ws;
+  float* colsum;
+} PirWgrad;
+int pir_wgrad_splits(int32_t B, int32_t HW, int32_t M, int32_t N, int32_t taps, int32_t per_image);
+int pir_wgrad(const PirWgrad* d, void* stream);
+
+/* Reduce P partials into the parameter gradient dst_w[R][Cc][taps] (a conv weight [R, Cc, 3, 3] or [R, Cc, 1, 1]).
+ * Parameter row r reads partial row  r < half ? r : r - half + half_pad  (GDFN's padded [x1 | x2] row space).
+ * With gamma (taps == 1; the conv input was xhat, the packed weight W*gamma, the additive vector W.beta + bias):
+ *   G = sum_P ws,  s = sum_P colsum:   dW[r][k] = gamma[k] G[r][k] + beta[k] s[r],
+ *   dgamma[k] = sum_r W[r][k] G[r][k],  dbeta[k] = sum_r W[r][k] s[r],  dbias[r] = s[r].     (model.py:60-63 backward) */
+typedef struct PirWgradFin {
+  int32_t P, M, N, taps;
+  int32_t R, Cc, half, half_pad;
+  const float* ws; const float* colsum;
+  float inv_scale;
+  const float* gamma; const float* beta; const float* w;
+  float* dst_w; float* dst_gamma; float* dst_beta; float* dst_bias;
+} PirWgradFin;
+int pir_wgrad_finalize(const PirWgradFin* d, void* stream);
+
+/* ---- weight gradient of a depthwise 3x3: dw[c][tap] = sum_p dy[p, c] * x[p + off(tap), c]  (model.py:90,112) -------
+ * ws: fp32 [parts][10][C] scratch (9 taps + bias); dst_w [R][9], dst_bias [R] or NULL; row map as above.            */
+typedef struct PirDwWgrad {
+  int32_t dtype;
+  int32_t B, H, W, C;
+  int32_t parts, R, half, half_pad;
+  const void* x; int64_t x_pitch, x_bstride;
+  const void* dy; int64_t dy_pitch, dy_bstride;
+  float* ws; float inv_scale;
+  float* dst_w; float* dst_bias;
+} PirDwWgrad;
+int pir_dw_wgrad_parts(int32_t B, int32_t H, int32_t W, int32_t C);
+int pir_dw_wgrad(const PirDwWgrad* d, void* stream);
+
+/* ---- GDFN gate backward (model.py:96-97): y = [y1 | y2] (2C channels) is overwritten by its gradient --------------
+ * dy1 = dg * y2 * (Phi(y1) + y1 phi(y1)),  dy2 = dg * y1 * Phi(y1)      (exact erf GELU)                            */
+typedef struct PirGateBwd {
+  int32_t dtype;
+  int32_t B, H, W, C;
+  void* y; int64_t y_pitch, y_bstride;
+  const void* dg; int64_t dg_pitch, dg_bstride;
+} PirGateBwd;
+int pir_gate_bwd(const PirGateBwd* d, void* stream);
+
+/* ---- MDTA backward on the c x c matrices (model.py:123-137) --------------------------------------------------------
+ * Inputs: the forward workspace of pir_mdta_gram/finalize (Gram partials, norms, attention), and the per-image partial
+ * weight gradient dWfold[b] = sum_p g[p,:]^T v[p,:] produced by pir_wgrad(per_image = 1) in ws_b (+ colsum_b).
+ * Outputs: dst_wo (+=0, assigned) [C][C], dst_temp [heads], dst_bias [C] or NULL, and two per-image 16-bit weight sets
+ *   wft[b][j][o] = Wfold[b][o][j]                   -> dv     = pir_gemm(g, wft, batched)
+ *   wqk[b][2C][Kpad(2C)]                            -> d[q|k] = pir_gemm([q|k], wqk, batched)
+ * where wqk carries softmax, temperature, cosine and L2-normalisation backward.  scratch: pir_mdta_bwd_ws_floats().   */
+typedef struct PirMdtaBwd {
+  int32_t dtype;
+  int32_t B, C, heads;
+  int32_t splits_f, splits_b;
+  const float* ws_f; const float* ws_b; const float* colsum_b;
+  const float* temperature; const float* wo;
+  float inv_scale;
+  float* scratch;
+  void* wft; void* wqk;
+  float* dst_wo; float* dst_temp; float* dst_bias;
+} PirMdtaBwd;
+int64_t pir_mdta_bwd_ws_floats(int32_t B, int32_t C, int32_t heads);
+int pir_mdta_bwd(const PirMdtaBwd* d, void* stream);
+
+/* ---- PixelShuffle(2) / PixelUnshuffle(2) as a permutation (gradients of model.py:165,175) --------------------------
+ * up = 1: in [B,H,W,4c] -> out [B,2H,2W,c];  up = 0: in [B,2H,2W,c] -> out [B,H,W,4c].  H, W, C describe the 4c side. */
+typedef struct PirShuffle {
+  int32_t dtype, up;
+  int32_t B, H, W, C;
+  const void* in; int64_t in_pitch, in_bstride;
+  void* out; int64_t out_pitch, out_bstride;
+} PirShuffle;
+int pir_pixel_shuffle(const PirShuffle* d, void* stream);
+
+/* ---- PromptGenBlock backward (model.py:226-232): bilinear^T, component mix, softmax, linear, mean pool --------------
+ * dup: gradient of the resized prompt [B,H,W,D]; pool_ws / weights: what pir_prompt_gen left in ws / weights_out.
+ * demb[b][c] = dL/d(mean-pooled feature) / (H*W): add it to every pixel of the feature gradient with pir_bcast_add.     */
+typedef struct PirPromptBwd {
+  int32_t dtype;
+  int32_t B, H, W, C, L, D, S;
+  const void* dup; int64_t dup_pitch, dup_bstride;
+  const float* prompt; const float* weights; const float* pool_ws; const float* lin_w;
+  float inv_scale;
+  float* scratch;
+  float* demb;
+  float* dst_prompt; float* dst_lin_w; float* dst_lin_b;
+} PirPromptBwd;
+int64_t pir_prompt_bwd_ws_floats(int32_t B, int32_t L, int32_t D, int32_t S);
+int pir_prompt_bwd(const PirPromptBwd* d, void* stream);
+
+/* g[b,p,c] += v[b][c] */
+typedef struct PirBcastAdd {
+  int32_t dtype;
+  int32_t B, H, W, C;
+  void* g; int64_t g_pitch, g_bstride;
+  const float* v;
+} PirBcastAdd;
+int pir_bcast_add(const PirBcastAdd* d, void* stream);
+
+/* fp32 NCHW [B,C,H,W] -> 16-bit NHWC [B,H,W,Cpad] (* scale), channels C..Cpad-1 zero */
+typedef struct PirToNhwc16 {
+  int32_t dtype;
+  int32_t B, C, H, W, Cpad;
+  const float* src;
+  void* out; int64_t out_pitch, out_bstride;
+  float scale;
+} PirToNhwc16;
+int pir_nchw32_to_nhwc16(const PirToNhwc16* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

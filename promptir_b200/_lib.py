@@ -63,6 +63,77 @@ class PirPatchEmbed(C.Structure):
                 ("out", vp), ("out_pitch", i64), ("out_bstride", i64)]
 
 
+f32 = C.c_float
+
+
+class PirLn(C.Structure):
+    _fields_ = [("dtype", i32), ("ln_mode", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32),
+                ("x", vp), ("x_pitch", i64), ("x_bstride", i64),
+                ("xhat", vp), ("xh_pitch", i64), ("xh_bstride", i64),
+                ("rstd", vp),
+                ("g", vp), ("g_pitch", i64), ("g_bstride", i64)]
+
+
+class PirWgrad(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("M", i32), ("N", i32), ("taps", i32),
+                ("per_image", i32), ("splits", i32),
+                ("a", vp), ("a_pitch", i64), ("a_bstride", i64),
+                ("b", vp), ("b_pitch", i64), ("b_bstride", i64),
+                ("ws", vp), ("colsum", vp)]
+
+
+class PirWgradFin(C.Structure):
+    _fields_ = [("P", i32), ("M", i32), ("N", i32), ("taps", i32), ("R", i32), ("Cc", i32), ("half", i32), ("half_pad", i32),
+                ("ws", vp), ("colsum", vp), ("inv_scale", f32),
+                ("gamma", vp), ("beta", vp), ("w", vp),
+                ("dst_w", vp), ("dst_gamma", vp), ("dst_beta", vp), ("dst_bias", vp)]
+
+
+class PirDwWgrad(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32), ("parts", i32), ("R", i32), ("half", i32),
+                ("half_pad", i32),
+                ("x", vp), ("x_pitch", i64), ("x_bstride", i64),
+                ("dy", vp), ("dy_pitch", i64), ("dy_bstride", i64),
+                ("ws", vp), ("inv_scale", f32), ("dst_w", vp), ("dst_bias", vp)]
+
+
+class PirGateBwd(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32),
+                ("y", vp), ("y_pitch", i64), ("y_bstride", i64),
+                ("dg", vp), ("dg_pitch", i64), ("dg_bstride", i64)]
+
+
+class PirMdtaBwd(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("C", i32), ("heads", i32), ("splits_f", i32), ("splits_b", i32),
+                ("ws_f", vp), ("ws_b", vp), ("colsum_b", vp), ("temperature", vp), ("wo", vp),
+                ("inv_scale", f32), ("scratch", vp), ("wft", vp), ("wqk", vp),
+                ("dst_wo", vp), ("dst_temp", vp), ("dst_bias", vp)]
+
+
+class PirShuffle(C.Structure):
+    _fields_ = [("dtype", i32), ("up", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32),
+                ("in_", vp), ("in_pitch", i64), ("in_bstride", i64),
+                ("out", vp), ("out_pitch", i64), ("out_bstride", i64)]
+
+
+class PirPromptBwd(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32), ("L", i32), ("D", i32), ("S", i32),
+                ("dup", vp), ("dup_pitch", i64), ("dup_bstride", i64),
+                ("prompt", vp), ("weights", vp), ("pool_ws", vp), ("lin_w", vp),
+                ("inv_scale", f32), ("scratch", vp), ("demb", vp),
+                ("dst_prompt", vp), ("dst_lin_w", vp), ("dst_lin_b", vp)]
+
+
+class PirBcastAdd(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32),
+                ("g", vp), ("g_pitch", i64), ("g_bstride", i64), ("v", vp)]
+
+
+class PirToNhwc16(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("C", i32), ("H", i32), ("W", i32), ("Cpad", i32),
+                ("src", vp), ("out", vp), ("out_pitch", i64), ("out_bstride", i64), ("scale", f32)]
+
+
 # every symbol include/promptir_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "pir_abi_version": (i32, []),
@@ -80,6 +151,21 @@ SYMBOLS = {
     "pir_prompt_gen": (i32, [C.POINTER(PirPrompt), vp]),
     "pir_patch_embed": (i32, [C.POINTER(PirPatchEmbed), vp]),
     "pir_tile_blend": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, i32, vp]),
+    "pir_ln_fwd": (i32, [C.POINTER(PirLn), vp]),
+    "pir_ln_bwd": (i32, [C.POINTER(PirLn), vp]),
+    "pir_wgrad_splits": (i32, [i32, i32, i32, i32, i32, i32]),
+    "pir_wgrad": (i32, [C.POINTER(PirWgrad), vp]),
+    "pir_wgrad_finalize": (i32, [C.POINTER(PirWgradFin), vp]),
+    "pir_dw_wgrad_parts": (i32, [i32, i32, i32, i32]),
+    "pir_dw_wgrad": (i32, [C.POINTER(PirDwWgrad), vp]),
+    "pir_gate_bwd": (i32, [C.POINTER(PirGateBwd), vp]),
+    "pir_mdta_bwd_ws_floats": (i64, [i32, i32, i32]),
+    "pir_mdta_bwd": (i32, [C.POINTER(PirMdtaBwd), vp]),
+    "pir_pixel_shuffle": (i32, [C.POINTER(PirShuffle), vp]),
+    "pir_prompt_bwd_ws_floats": (i64, [i32, i32, i32, i32]),
+    "pir_prompt_bwd": (i32, [C.POINTER(PirPromptBwd), vp]),
+    "pir_bcast_add": (i32, [C.POINTER(PirBcastAdd), vp]),
+    "pir_nchw32_to_nhwc16": (i32, [C.POINTER(PirToNhwc16), vp]),
 }
 
 _lib = None

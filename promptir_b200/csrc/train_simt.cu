@@ -1,0 +1,894 @@
+// Training-side SIMT kernels for sm_100a: everything of the backward pass that is NOT a tensor-core contraction.
+// Reference: autograd of net/model.py (LayerNorm :39-41,60-63; GDFN gate :96-97; MDTA :123-137; PixelShuffle/Unshuffle
+// :165,175; PromptGenBlock :226-232) as driven by train.py:37-46.  All of them are HBM/L2-bound: 16-byte vector loads and
+// stores on NHWC 16-bit tensors, fp32 arithmetic, deterministic reductions (no atomics).
+#include "common.cuh"
+#include "host.h"
+
+namespace pir {
+
+constexpr int kMaxLTrain = 8;
+
+template <class T> __device__ __forceinline__ void unpack8t(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { f[2 * q] = unpack_lo<T>(w[q]); f[2 * q + 1] = unpack_hi<T>(w[q]); }
+}
+template <class T> __device__ __forceinline__ uint4 pack8t(const float (&f)[8]) {
+  uint4 v;
+  v.x = pack2<T>(f[0], f[1]); v.y = pack2<T>(f[2], f[3]); v.z = pack2<T>(f[4], f[5]); v.w = pack2<T>(f[6], f[7]);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// LayerNorm forward / backward.  LPP lanes cooperate on one pixel, each owning up to 3 chunks of 8 channels.
+// ------------------------------------------------------------------------------------------------------
+struct LnArgs {
+  int npix_img, B, C, nch, biasfree;       // nch = chunks per lane
+  const unsigned short* x; long long x_pitch, x_bstride;
+  unsigned short* xhat; long long xh_pitch, xh_bstride;
+  float* rstd;
+  unsigned short* g; long long g_pitch, g_bstride;
+};
+
+template <int LPP> __device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPP / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <class T, int LPP>
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const LnArgs a) {
+  const int sub = threadIdx.x % LPP;
+  const int ppb = blockDim.x / LPP;
+  const long long total = (long long)a.B * a.npix_img;
+  const long long gstride = (long long)gridDim.x * ppb;
+  const int chunks = a.C >> 3;
+  const float invC = 1.0f / (float)a.C;
+  const long long rounds = (total + gstride - 1) / gstride;
+  for (long long it = 0; it < rounds; ++it) {
+    // all lanes of a warp iterate together (shuffles); out-of-range pixels are masked
+    const long long p = it * gstride + (long long)blockIdx.x * ppb + threadIdx.x / LPP;
+    const bool live = p < total;
+    const int b = live ? (int)(p / a.npix_img) : 0;
+    const int pi = live ? (int)(p % a.npix_img) : 0;
+    const unsigned short* xp = a.x + (size_t)b * a.x_bstride + (size_t)pi * a.x_pitch;
+    float v[3][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int ch = sub + i * LPP;
+      const bool ok = live && i < a.nch && ch < chunks;
+      if (ok) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xp + ch * 8));
+        unpack8t<T>(u, v[i]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[i][e];
+    }
+    const float mu = group_sum<LPP>(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int ch = sub + i * LPP;
+      if (i < a.nch && ch < chunks) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mu; q = fmaf(d, d, q); }
+      }
+    }
+    const float rstd = rsqrtf(group_sum<LPP>(q) * invC + 1e-5f);
+    if (!live) continue;
+    const float sh = a.biasfree ? 0.f : mu;
+    unsigned short* op = a.xhat + (size_t)b * a.xh_bstride + (size_t)pi * a.xh_pitch;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int ch = sub + i * LPP;
+      if (i < a.nch && ch < chunks) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - sh) * rstd;
+        *reinterpret_cast<uint4*>(op + ch * 8) = pack8t<T>(o);
+      }
+    }
+    if (sub == 0) a.rstd[p] = rstd;
+  }
+}
+
+template <class T, int LPP>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const LnArgs a) {
+  const int sub = threadIdx.x % LPP;
+  const int ppb = blockDim.x / LPP;
+  const long long total = (long long)a.B * a.npix_img;
+  const long long gstride = (long long)gridDim.x * ppb;
+  const int chunks = a.C >> 3;
+  const float invC = 1.0f / (float)a.C;
+  const long long rounds = (total + gstride - 1) / gstride;
+  for (long long it = 0; it < rounds; ++it) {
+    const long long p = it * gstride + (long long)blockIdx.x * ppb + threadIdx.x / LPP;
+    const bool live = p < total;
+    const int b = live ? (int)(p / a.npix_img) : 0;
+    const int pi = live ? (int)(p % a.npix_img) : 0;
+    const unsigned short* dp = a.x + (size_t)b * a.x_bstride + (size_t)pi * a.x_pitch;
+    const unsigned short* hp = a.xhat + (size_t)b * a.xh_bstride + (size_t)pi * a.xh_pitch;
+    float d[3][8], h[3][8];
+    float sd = 0.f, sdh = 0.f, sh = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int ch = sub + i * LPP;
+      if (live && i < a.nch && ch < chunks) {
+        unpack8t<T>(__ldg(reinterpret_cast<const uint4*>(dp + ch * 8)), d[i]);
+        unpack8t<T>(__ldg(reinterpret_cast<const uint4*>(hp + ch * 8)), h[i]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { d[i][e] = 0.f; h[i][e] = 0.f; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { sd += d[i][e]; sdh = fmaf(d[i][e], h[i][e], sdh); sh += h[i][e]; }
+    }
+    const float md = group_sum<LPP>(sd) * invC, mdh = group_sum<LPP>(sdh) * invC, mh = group_sum<LPP>(sh) * invC;
+    if (!live) continue;
+    const float rstd = a.rstd[p];
+    unsigned short* gp = a.g + (size_t)b * a.g_bstride + (size_t)pi * a.g_pitch;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int ch = sub + i * LPP;
+      if (i < a.nch && ch < chunks) {
+        float gv[8];
+        unpack8t<T>(*reinterpret_cast<const uint4*>(gp + ch * 8), gv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dx = a.biasfree ? (d[i][e] - (h[i][e] - mh) * mdh) : (d[i][e] - md - h[i][e] * mdh);
+          gv[e] = fmaf(rstd, dx, gv[e]);
+        }
+        *reinterpret_cast<uint4*>(gp + ch * 8) = pack8t<T>(gv);
+      }
+    }
+  }
+}
+
+static void ln_plan(int C, int* lpp, int* nch) {
+  // lanes per pixel in {8, 16, 32}, chunks per lane <= 3: least wasted lane-chunks
+  const int chunks = C / 8;
+  int best = 1 << 30;
+  *lpp = 32; *nch = 3;
+  for (int l = 8; l <= 32; l <<= 1) {
+    const int n = (chunks + l - 1) / l;
+    if (n > 3) continue;
+    if (l * n - chunks < best) { best = l * n - chunks; *lpp = l; *nch = n; }
+  }
+}
+
+template <class T>
+static int launch_ln(const PirLn* d, bool bwd, cudaStream_t s) {
+  LnArgs a{};
+  a.npix_img = d->H * d->W; a.B = d->B; a.C = d->C; a.biasfree = d->ln_mode == PIR_LN_BIASFREE;
+  a.x = reinterpret_cast<const unsigned short*>(d->x); a.x_pitch = d->x_pitch; a.x_bstride = d->x_bstride;
+  a.xhat = reinterpret_cast<unsigned short*>(d->xhat); a.xh_pitch = d->xh_pitch; a.xh_bstride = d->xh_bstride;
+  a.rstd = d->rstd;
+  a.g = reinterpret_cast<unsigned short*>(d->g); a.g_pitch = d->g_pitch; a.g_bstride = d->g_bstride;
+  int lpp;
+  ln_plan(d->C, &lpp, &a.nch);
+  const long long total = (long long)d->B * a.npix_img;
+  const int ppb = 256 / lpp;
+  long long blocks = (total + ppb - 1) / ppb;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+#define PIR_LN_LAUNCH(L)                                                          \
+  if (bwd) ln_bwd_kernel<T, L><<<(unsigned)blocks, 256, 0, s>>>(a);               \
+  else ln_fwd_kernel<T, L><<<(unsigned)blocks, 256, 0, s>>>(a)
+  if (lpp == 8) { PIR_LN_LAUNCH(8); } else if (lpp == 16) { PIR_LN_LAUNCH(16); } else { PIR_LN_LAUNCH(32); }
+#undef PIR_LN_LAUNCH
+  return pir_check_launch(bwd ? "pir_ln_bwd" : "pir_ln_fwd");
+}
+
+static int check_ln(const PirLn* d, bool bwd, const char* who) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "%s: null descriptor", who);
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0) return pir_fail(PIR_ERR_ARG, "%s: empty problem", who);
+  if (d->ln_mode != PIR_LN_WITHBIAS && d->ln_mode != PIR_LN_BIASFREE) return pir_fail(PIR_ERR_ARG, "%s: ln_mode", who);
+  if ((d->C % 8) || d->C > 768) return pir_fail(PIR_ERR_UNSUPPORTED, "%s: C must be a multiple of 8 and <= 768", who);
+  if ((d->x_pitch % 8) || (d->xh_pitch % 8) || (d->x_bstride % 8) || (d->xh_bstride % 8) || ((uintptr_t)d->x & 15) || ((uintptr_t)d->xhat & 15) ||
+      !d->x || !d->xhat || !d->rstd)
+    return pir_fail(PIR_ERR_ARG, "%s: tensors missing or not 16-byte aligned", who);
+  if (bwd && (!d->g || (d->g_pitch % 8) || (d->g_bstride % 8) || ((uintptr_t)d->g & 15))) return pir_fail(PIR_ERR_ARG, "%s: g missing or misaligned", who);
+  return PIR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// GDFN gate backward (exact erf GELU), in place on y = [y1 | y2]
+// ------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+gate_bwd_kernel(unsigned short* __restrict__ y, long long ypitch, long long ybs, const unsigned short* __restrict__ dg, long long gpitch,
+                long long gbs, int HW, int C, long long total) {
+  const int chunks = C >> 3;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % chunks);
+    const long long p = e / chunks;
+    const int b = (int)(p / HW), pi = (int)(p % HW);
+    unsigned short* yp = y + (size_t)b * ybs + (size_t)pi * ypitch + ch * 8;
+    float y1[8], y2[8], d[8];
+    unpack8t<T>(*reinterpret_cast<const uint4*>(yp), y1);
+    unpack8t<T>(*reinterpret_cast<const uint4*>(yp + C), y2);
+    unpack8t<T>(__ldg(reinterpret_cast<const uint4*>(dg + (size_t)b * gbs + (size_t)pi * gpitch + ch * 8)), d);
+    float o1[8], o2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float cdf = 0.5f * (1.0f + erff(y1[i] * 0.7071067811865476f));
+      const float pdf = expf(-0.5f * y1[i] * y1[i]) * 0.3989422804014327f;
+      o1[i] = d[i] * y2[i] * fmaf(y1[i], pdf, cdf);
+      o2[i] = d[i] * y1[i] * cdf;
+    }
+    *reinterpret_cast<uint4*>(yp) = pack8t<T>(o1);
+    *reinterpret_cast<uint4*>(yp + C) = pack8t<T>(o2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// PixelShuffle(2) / PixelUnshuffle(2): channel index of the 4c side = ch*4 + i*2 + j  <->  pixel (2y+i, 2x+j), channel ch
+// one thread: one low-resolution pixel x 8 channels of the c side = 32 contiguous channels of the 4c side
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+shuffle_kernel(const unsigned short* __restrict__ in, long long ipitch, long long ibs, unsigned short* __restrict__ out, long long opitch,
+               long long obs, int H, int W, int c, int up, long long total) {
+  const int chunks = c >> 3;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % chunks);
+    long long p = e / chunks;
+    const int x = (int)(p % W); p /= W;
+    const int y = (int)(p % H);
+    const int b = (int)(p / H);
+    unsigned short v[4][8];                       // [i*2+j][channel of the c side]
+    if (up) {                                     // read 32 channels of the 4c side
+      const unsigned short* ip = in + (size_t)b * ibs + ((size_t)y * W + x) * ipitch + ch * 32;
+      unsigned short w[32];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(w + q * 8) = __ldg(reinterpret_cast<const uint4*>(ip + q * 8));
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int ij = 0; ij < 4; ++ij) v[ij][k] = w[k * 4 + ij];
+#pragma unroll
+      for (int ij = 0; ij < 4; ++ij) {
+        unsigned short* op = out + (size_t)b * obs + ((size_t)(2 * y + (ij >> 1)) * (2 * W) + 2 * x + (ij & 1)) * opitch + ch * 8;
+        *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(v[ij]);
+      }
+    } else {
+#pragma unroll
+      for (int ij = 0; ij < 4; ++ij) {
+        const unsigned short* ip = in + (size_t)b * ibs + ((size_t)(2 * y + (ij >> 1)) * (2 * W) + 2 * x + (ij & 1)) * ipitch + ch * 8;
+        *reinterpret_cast<uint4*>(v[ij]) = __ldg(reinterpret_cast<const uint4*>(ip));
+      }
+      unsigned short w[32];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int ij = 0; ij < 4; ++ij) w[k * 4 + ij] = v[ij][k];
+      unsigned short* op = out + (size_t)b * obs + ((size_t)y * W + x) * opitch + ch * 32;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(op + q * 8) = *reinterpret_cast<const uint4*>(w + q * 8);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// g[b,p,c] += v[b][c]
+// ------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+bcast_add_kernel(unsigned short* __restrict__ g, long long pitch, long long bs, const float* __restrict__ v, int HW, int C, long long total) {
+  const int chunks = C >> 3;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % chunks);
+    const long long p = e / chunks;
+    const int b = (int)(p / HW), pi = (int)(p % HW);
+    unsigned short* gp = g + (size_t)b * bs + (size_t)pi * pitch + ch * 8;
+    float f[8];
+    unpack8t<T>(*reinterpret_cast<const uint4*>(gp), f);
+    const float* vp = v + (size_t)b * C + ch * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] += __ldg(vp + i);
+    *reinterpret_cast<uint4*>(gp) = pack8t<T>(f);
+  }
+}
+
+// fp32 NCHW -> 16-bit NHWC, 8 channels per pixel (C <= 8, the rest zero)
+template <class T>
+__global__ void __launch_bounds__(256)
+to_nhwc16_kernel(const float* __restrict__ src, unsigned short* __restrict__ out, long long pitch, long long bs, int C, int HW, float scale,
+                 long long total) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(p / HW), pi = (int)(p % HW);
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) f[c] = c < C ? __ldg(src + ((size_t)b * C + c) * HW + pi) * scale : 0.f;
+    *reinterpret_cast<uint4*>(out + (size_t)b * bs + (size_t)pi * pitch) = pack8t<T>(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// depthwise 3x3 weight gradient.  grid (parts, channel groups of 64); block 256 = 32 pixel lanes x 8 channel lanes.
+// A CTA takes a contiguous range of image rows; each thread walks x = lane, lane + 32, ... and keeps 9 + 1 fp32 accumulators
+// for each of its 8 channels (FHFMA: 16-bit x 16-bit -> fp32).  Neighbour loads overlap in L1.
+// ------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256)
+dw_wgrad_kernel(const unsigned short* __restrict__ x, long long xpitch, long long xbs, const unsigned short* __restrict__ dy, long long dpitch,
+                long long dbs, int B, int H, int W, int C, float* __restrict__ ws) {
+  __shared__ float red[8][10][64];
+  const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int warp = threadIdx.x >> 5;
+  const int c = blockIdx.y * 64 + cl * 8;
+  const bool c_ok = c < C;
+  const int rows = B * H;
+  const int per = (rows + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * per, r_end = min(r_begin + per, rows);
+  float acc[10][8];
+#pragma unroll
+  for (int t = 0; t < 10; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  if (c_ok) {
+    for (int r = r_begin; r < r_end; ++r) {
+      const int b = r / H, yy = r % H;
+      const unsigned short* xb = x + (size_t)b * xbs + c;
+      const unsigned short* db = dy + (size_t)b * dbs + c;
+      for (int xx = pl; xx < W; xx += 32) {
+        const uint4 dv = __ldg(reinterpret_cast<const uint4*>(db + ((size_t)yy * W + xx) * dpitch));
+        const uint32_t dw4[4] = {dv.x, dv.y, dv.z, dv.w};
+        float df[8];
+        unpack8t<T>(dv, df);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[9][i] += df[i];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int sy = yy + ky - 1;
+          if (sy < 0 || sy >= H) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int sx = xx + kx - 1;
+            if (sx < 0 || sx >= W) continue;
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)sy * W + sx) * xpitch));
+            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+            float* a = acc[ky * 3 + kx];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              a[2 * q] = fma16<T>(lo16(xw[q]), lo16(dw4[q]), a[2 * q]);
+              a[2 * q + 1] = fma16<T>(hi16(xw[q]), hi16(dw4[q]), a[2 * q + 1]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // reduce over the 4 pixel lanes of a warp, then over the 8 warps
+#pragma unroll
+  for (int t = 0; t < 10; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = acc[t][i];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((threadIdx.x & 31) < 8) red[warp][t][cl * 8 + i] = v;
+    }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 10 * 64; e += 256) {
+    const int t = e >> 6, ch = e & 63;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][t][ch];
+    const int cc = blockIdx.y * 64 + ch;
+    if (cc < C) ws[((size_t)blockIdx.x * 10 + t) * C + cc] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dw_wgrad_fin_kernel(const float* __restrict__ ws, int parts, int C, int R, int half, int half_pad, float inv_scale, float* __restrict__ dst_w,
+                    float* __restrict__ dst_bias) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= R * 10) return;
+  const int r = e / 10, t = e % 10;
+  const int pr = r < half ? r : r - half + half_pad;
+  float s = 0.f;
+  for (int p = 0; p < parts; ++p) s += ws[((size_t)p * 10 + t) * C + pr];
+  s *= inv_scale;
+  if (t < 9) dst_w[(size_t)r * 9 + t] = s;
+  else if (dst_bias) dst_bias[r] = s;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// MDTA backward on the channel x channel matrices.  Scratch layout (floats), per pir_mdta_bwd_ws_floats():
+//   nrm [B][2C] | dWf [B][C][C] | dcos [B][C][c] | cosm [B][C][c] | rq [B][C] | rk [B][C] | dTp [B][C]
+// ------------------------------------------------------------------------------------------------------
+struct MbArgs {
+  int B, C, heads, c, sf, sb;
+  const float* gram;      // forward: [B][sf][C][c]
+  const float* norm;      // forward: [B][sf][2][C]
+  const float* attn;      // forward: [B][heads][c][c]
+  const float* ws_b;      // [B*sb][C][C]
+  const float* colsum_b;  // [B*sb][C] or null
+  const float* temperature; const float* wo;
+  float inv_scale;
+  float *nrm, *dWf, *dcos, *cosm, *rq, *rk, *dTp;
+  float *dst_wo, *dst_temp, *dst_bias;
+};
+
+__device__ __forceinline__ float sum_strided(const float* p, size_t stride, int n) {
+  float s0 = 0.f, s1 = 0.f;
+  int i = 0;
+  for (; i + 2 <= n; i += 2) { s0 += p[(size_t)i * stride]; s1 += p[(size_t)(i + 1) * stride]; }
+  if (i < n) s0 += p[(size_t)i * stride];
+  return s0 + s1;
+}
+
+// k1: norms and the per-image dWfold.  grid (ceil(C*C/256), B)
+__global__ void __launch_bounds__(256) mdta_bwd_reduce_kernel(const MbArgs a) {
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e < a.C * a.C) a.dWf[(size_t)b * a.C * a.C + e] = sum_strided(a.ws_b + (size_t)b * a.sb * a.C * a.C + e, (size_t)a.C * a.C, a.sb);
+  if (e < 2 * a.C)
+    a.nrm[(size_t)b * 2 * a.C + e] = fmaxf(sqrtf(sum_strided(a.norm + (size_t)b * a.sf * 2 * a.C + e, (size_t)2 * a.C, a.sf)), 1e-12f);
+}
+
+// k2: one warp per attention row (b, r = h*c + i): dA -> softmax backward -> dcos, cos, rq, temperature partial.  c <= 256
+__global__ void __launch_bounds__(256) mdta_bwd_rows_kernel(const MbArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  const int b = blockIdx.y;
+  if (r >= a.C) return;
+  const int c = a.c, C = a.C;
+  const int h = r / c, i = r - h * c;
+  const float qn = a.nrm[(size_t)b * 2 * C + r];
+  const float T = a.temperature[h];
+  const float* dWf = a.dWf + (size_t)b * C * C + h * c;
+  float dA[8], A[8], cs[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) dA[t] = 0.f;
+  for (int o = 0; o < C; ++o) {
+    const float w = __ldg(a.wo + (size_t)o * C + r);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int j = lane + t * 32;
+      if (j < c) dA[t] = fmaf(w, dWf[(size_t)o * C + j], dA[t]);
+    }
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int j = lane + t * 32;
+    A[t] = 0.f; cs[t] = 0.f;
+    if (j < c) {
+      A[t] = a.attn[((size_t)(b * a.heads + h) * c + i) * c + j];
+      const float kn = a.nrm[(size_t)b * 2 * C + C + h * c + j];
+      cs[t] = sum_strided(a.gram + ((size_t)b * a.sf * C + r) * c + j, (size_t)C * c, a.sf) / (qn * kn);
+      dot = fmaf(dA[t], A[t], dot);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  float dT = 0.f, rq = 0.f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int j = lane + t * 32;
+    if (j < c) {
+      const float dS = A[t] * (dA[t] - dot);
+      dT = fmaf(dS, cs[t], dT);
+      const float dc = dS * T;
+      rq = fmaf(dc, cs[t], rq);
+      a.dcos[((size_t)b * C + r) * c + j] = dc;
+      a.cosm[((size_t)b * C + r) * c + j] = cs[t];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { dT += __shfl_xor_sync(0xffffffffu, dT, o); rq += __shfl_xor_sync(0xffffffffu, rq, o); }
+  if (lane == 0) {
+    a.dTp[(size_t)b * C + r] = dT;
+    a.rq[(size_t)b * C + r] = rq / (qn * qn);
+  }
+}
+
+// k3: rk[b][h*c + j] = sum_i dcos[i][j] cos[i][j] / kn_j^2.  one thread per (b, channel)
+__global__ void __launch_bounds__(256) mdta_bwd_cols_kernel(const MbArgs a) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= a.B * a.C) return;
+  const int b = e / a.C, ch = e % a.C;
+  const int h = ch / a.c, j = ch - h * a.c;
+  const size_t base = ((size_t)b * a.C + h * a.c) * a.c + j;
+  float s = 0.f;
+  for (int i = 0; i < a.c; ++i) s = fmaf(a.dcos[base + (size_t)i * a.c], a.cosm[base + (size_t)i * a.c], s);
+  const float kn = a.nrm[(size_t)b * 2 * a.C + a.C + ch];
+  a.rk[e] = s / (kn * kn);
+}
+
+// k4: the two per-image weight sets.  grid (ceil(2C*2C/256), B): wqk;  grid.z == 1 slice handles wft
+template <class T>
+__global__ void __launch_bounds__(256) mdta_bwd_weights_kernel(const MbArgs a, unsigned short* __restrict__ wqk, int kpad2,
+                                                               unsigned short* __restrict__ wft, int kpad1) {
+  const int b = blockIdx.y;
+  const int C = a.C, c = a.c;
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  const float* nrm = a.nrm + (size_t)b * 2 * C;
+  if (blockIdx.z == 0) {
+    if (e >= (long long)4 * C * C) return;
+    const int n = (int)(e / (2 * C)), k = (int)(e % (2 * C));
+    float v = 0.f;
+    if (n < C) {
+      if (k < C) { if (k == n) v = -a.rq[(size_t)b * C + n]; }
+      else {
+        const int kk = k - C;
+        if (kk / c == n / c) v = a.dcos[((size_t)b * C + n) * c + kk % c] / (nrm[n] * nrm[C + kk]);
+      }
+    } else {
+      const int jg = n - C;
+      if (k < C) { if (k / c == jg / c) v = a.dcos[((size_t)b * C + k) * c + jg % c] / (nrm[k] * nrm[C + jg]); }
+      else if (k == n) v = -a.rk[(size_t)b * C + jg];
+    }
+    wqk[((size_t)b * 2 * C + n) * kpad2 + k] = to16<T>(v);
+  } else {
+    if (e >= (long long)C * C) return;
+    const int jg = (int)(e / C), o = (int)(e % C);        // wft[b][jg][o] = sum_i Wo[o][h*c + i] A[b,h][i][j]
+    const int h = jg / c, j = jg - h * c;
+    const float* A = a.attn + (size_t)(b * a.heads + h) * c * c + j;
+    const float* w = a.wo + (size_t)o * C + h * c;
+    float s = 0.f;
+    for (int i = 0; i < c; ++i) s = fmaf(__ldg(w + i), A[(size_t)i * c], s);
+    wft[((size_t)b * C + jg) * kpad1 + o] = to16<T>(s);
+  }
+}
+
+// k5: dWo[o][h*c + i] = inv * sum_b sum_j dWf[b][o][h*c + j] A[b,h][i][j].  one thread per (o, channel)
+__global__ void __launch_bounds__(256) mdta_bwd_dwo_kernel(const MbArgs a) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= a.C * a.C) return;
+  const int o = e / a.C, ch = e % a.C;
+  const int h = ch / a.c, i = ch - h * a.c;
+  float s = 0.f;
+  for (int b = 0; b < a.B; ++b) {
+    const float* d = a.dWf + ((size_t)b * a.C + o) * a.C + h * a.c;
+    const float* A = a.attn + ((size_t)(b * a.heads + h) * a.c + i) * a.c;
+    float t = 0.f;
+    for (int j = 0; j < a.c; ++j) t = fmaf(d[j], A[j], t);
+    s += t;
+  }
+  a.dst_wo[e] = s * a.inv_scale;
+}
+
+// k6: temperature gradient (one warp per head) and project_out bias gradient
+__global__ void __launch_bounds__(256) mdta_bwd_small_kernel(const MbArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0) {
+    if (warp < a.heads) {
+      float s = 0.f;
+      for (int e = lane; e < a.B * a.c; e += 32) s += a.dTp[(size_t)(e / a.c) * a.C + warp * a.c + e % a.c];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) a.dst_temp[warp] = s * a.inv_scale;
+    }
+  } else if (a.dst_bias) {
+    const int o = (blockIdx.x - 1) * 256 + threadIdx.x;
+    if (o < a.C) a.dst_bias[o] = sum_strided(a.colsum_b + o, (size_t)a.C, a.B * a.sb) * a.inv_scale;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// PromptGenBlock backward.  scratch: dmix [B][S][S][D] | dw [B][L] | emb [B][C]
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilinear_src(int y, float scale, int S, int* y0, int* y1, float* ly) {
+  const float fy = fmaxf(scale * ((float)y + 0.5f) - 0.5f, 0.f);
+  *y0 = min((int)fy, S - 1);
+  *y1 = *y0 + (*y0 < S - 1 ? 1 : 0);
+  *ly = fminf(fmaxf(fy - (float)*y0, 0.f), 1.f);
+}
+
+// dmix[b][s][t][d] = sum over destination pixels whose bilinear footprint contains (s, t).  one thread per (b, s, t, 8 channels)
+template <class T>
+__global__ void __launch_bounds__(256)
+prompt_bwd_dmix_kernel(const unsigned short* __restrict__ dup, long long pitch, long long bs, int H, int W, int D, int S, float* __restrict__ dmix,
+                       long long total) {
+  const int chunks = D >> 3;
+  const float sh = (float)S / (float)H, sw = (float)S / (float)W;
+  const int ry = (int)ceilf(1.0f / sh) + 1, rx = (int)ceilf(1.0f / sw) + 1;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % chunks);
+    long long p = e / chunks;
+    const int t = (int)(p % S); p /= S;
+    const int s = (int)(p % S);
+    const int b = (int)(p / S);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const int yc = (int)(((float)s + 0.5f) / sh), xc = (int)(((float)t + 0.5f) / sw);
+    for (int y = max(yc - 2 * ry, 0); y <= min(yc + 2 * ry, H - 1); ++y) {
+      int y0, y1; float ly;
+      bilinear_src(y, sh, S, &y0, &y1, &ly);
+      const float wy = (y0 == s ? 1.f - ly : 0.f) + (y1 == s ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int x = max(xc - 2 * rx, 0); x <= min(xc + 2 * rx, W - 1); ++x) {
+        int x0, x1; float lx;
+        bilinear_src(x, sw, S, &x0, &x1, &lx);
+        const float wx = (x0 == t ? 1.f - lx : 0.f) + (x1 == t ? lx : 0.f);
+        if (wx == 0.f) continue;
+        float f[8];
+        unpack8t<T>(__ldg(reinterpret_cast<const uint4*>(dup + (size_t)b * bs + ((size_t)y * W + x) * pitch + ch * 8)), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wy * wx, f[i], acc[i]);
+      }
+    }
+    float* o = dmix + (((size_t)b * S + s) * S + t) * D + ch * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+// dw[b][l] = <dmix[b], prompt[l]>.  grid (L, B), block 256
+__global__ void __launch_bounds__(256)
+prompt_bwd_dot_kernel(const float* __restrict__ dmix, const float* __restrict__ prompt, long long n, int L, float* __restrict__ dw) {
+  __shared__ float red[8];
+  const int l = blockIdx.x, b = blockIdx.y;
+  const float4* a = reinterpret_cast<const float4*>(dmix + (size_t)b * n);
+  const float4* p = reinterpret_cast<const float4*>(prompt + (size_t)l * n);
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n / 4; i += 256) {
+    const float4 u = a[i], v = __ldg(p + i);
+    s += u.x * v.x + u.y * v.y + u.z * v.z + u.w * v.w;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    dw[b * L + l] = t;
+  }
+}
+
+// softmax / linear / mean-pool backward.  one block; B*L <= 8*... small
+__global__ void __launch_bounds__(256)
+prompt_bwd_small_kernel(const float* __restrict__ dw, const float* __restrict__ wts, const float* __restrict__ pool_ws, int nchunks, int B, int L,
+                        int C, int HW, const float* __restrict__ lin_w, float inv_scale, float* __restrict__ dlog_s, float* __restrict__ demb,
+                        float* __restrict__ dst_lin_w, float* __restrict__ dst_lin_b) {
+  // dlog[b][l] = w (dw - sum_l w dw)
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float dot = 0.f;
+    for (int l = 0; l < L; ++l) dot = fmaf(wts[b * L + l], dw[b * L + l], dot);
+    for (int l = 0; l < L; ++l) dlog_s[b * L + l] = wts[b * L + l] * (dw[b * L + l] - dot);
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dlog_s[b * L + l];
+    dst_lin_b[l] = s * inv_scale;
+  }
+  const float invHW = 1.0f / (float)HW;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float gl[kMaxLTrain];
+    for (int l = 0; l < L; ++l) gl[l] = 0.f;
+    for (int b = 0; b < B; ++b) {
+      float emb = 0.f;
+      for (int k = 0; k < nchunks; ++k) emb += pool_ws[((size_t)b * nchunks + k) * C + c];
+      emb *= invHW;
+      float de = 0.f;
+      for (int l = 0; l < L; ++l) {
+        gl[l] = fmaf(dlog_s[b * L + l], emb, gl[l]);
+        de = fmaf(dlog_s[b * L + l], lin_w[(size_t)l * C + c], de);
+      }
+      demb[(size_t)b * C + c] = de * invHW;
+    }
+    for (int l = 0; l < L; ++l) dst_lin_w[(size_t)l * C + c] = gl[l] * inv_scale;
+  }
+}
+
+// dprompt[0][l][d][s][t] = inv * sum_b w[b][l] dmix[b][s][t][d].  one thread per (d, s*S + t), all L
+__global__ void __launch_bounds__(256)
+prompt_bwd_param_kernel(const float* __restrict__ dmix, const float* __restrict__ wts, int B, int L, int D, int SS, float inv_scale,
+                        float* __restrict__ dst) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= (long long)D * SS) return;
+  const int st = (int)(e % SS), d = (int)(e / SS);
+  float acc[kMaxLTrain];
+  for (int l = 0; l < L; ++l) acc[l] = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float v = dmix[((size_t)b * SS + st) * D + d];
+    for (int l = 0; l < L; ++l) acc[l] = fmaf(wts[b * L + l], v, acc[l]);
+  }
+  for (int l = 0; l < L; ++l) dst[((size_t)l * D + d) * SS + st] = acc[l] * inv_scale;
+}
+
+static inline unsigned grid_for(long long total, int threads = 256, int cap = 148 * 16) {
+  long long b = (total + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace pir
+
+using namespace pir;
+
+#define PIR_BY_DTYPE(dt, expr_bf, expr_fp) \
+  do { if ((dt) == PIR_DTYPE_BF16) { expr_bf; } else { expr_fp; } } while (0)
+
+extern "C" int pir_ln_fwd(const PirLn* d, void* stream) {
+  if (int e = check_ln(d, false, "pir_ln_fwd")) return e;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return d->dtype == PIR_DTYPE_BF16 ? launch_ln<BF16>(d, false, s) : launch_ln<FP16>(d, false, s);
+}
+
+extern "C" int pir_ln_bwd(const PirLn* d, void* stream) {
+  if (int e = check_ln(d, true, "pir_ln_bwd")) return e;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  return d->dtype == PIR_DTYPE_BF16 ? launch_ln<BF16>(d, true, s) : launch_ln<FP16>(d, true, s);
+}
+
+extern "C" int pir_gate_bwd(const PirGateBwd* d, void* stream) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_gate_bwd: null descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0) return pir_fail(PIR_ERR_ARG, "pir_gate_bwd: empty problem");
+  if ((d->C % 8) || (d->y_pitch % 8) || (d->dg_pitch % 8) || (d->y_bstride % 8) || (d->dg_bstride % 8) || ((uintptr_t)d->y & 15) ||
+      ((uintptr_t)d->dg & 15) || !d->y || !d->dg)
+    return pir_fail(PIR_ERR_ARG, "pir_gate_bwd: tensors missing or not 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)d->B * d->H * d->W * (d->C / 8);
+  auto* y = reinterpret_cast<unsigned short*>(d->y);
+  auto* dg = reinterpret_cast<const unsigned short*>(d->dg);
+  PIR_BY_DTYPE(d->dtype,
+               (gate_bwd_kernel<BF16><<<grid_for(total), 256, 0, s>>>(y, d->y_pitch, d->y_bstride, dg, d->dg_pitch, d->dg_bstride, d->H * d->W, d->C, total)),
+               (gate_bwd_kernel<FP16><<<grid_for(total), 256, 0, s>>>(y, d->y_pitch, d->y_bstride, dg, d->dg_pitch, d->dg_bstride, d->H * d->W, d->C, total)));
+  return pir_check_launch("pir_gate_bwd");
+}
+
+extern "C" int pir_pixel_shuffle(const PirShuffle* d, void* stream) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_pixel_shuffle: null descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0) return pir_fail(PIR_ERR_ARG, "pir_pixel_shuffle: empty problem");
+  if ((d->C % 32) || (d->in_pitch % 8) || (d->out_pitch % 8) || (d->in_bstride % 8) || (d->out_bstride % 8) || ((uintptr_t)d->in & 15) ||
+      ((uintptr_t)d->out & 15) || !d->in || !d->out)
+    return pir_fail(PIR_ERR_ARG, "pir_pixel_shuffle: the 4c side needs C %% 32 == 0 and 16-byte aligned tensors");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int c = d->C / 4;
+  const long long total = (long long)d->B * d->H * d->W * (c / 8);
+  shuffle_kernel<<<grid_for(total), 256, 0, s>>>(reinterpret_cast<const unsigned short*>(d->in), d->in_pitch, d->in_bstride,
+                                                 reinterpret_cast<unsigned short*>(d->out), d->out_pitch, d->out_bstride, d->H, d->W, c, d->up, total);
+  return pir_check_launch("pir_pixel_shuffle");
+}
+
+extern "C" int pir_bcast_add(const PirBcastAdd* d, void* stream) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_bcast_add: null descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0) return pir_fail(PIR_ERR_ARG, "pir_bcast_add: empty problem");
+  if ((d->C % 8) || (d->g_pitch % 8) || (d->g_bstride % 8) || ((uintptr_t)d->g & 15) || !d->g || !d->v)
+    return pir_fail(PIR_ERR_ARG, "pir_bcast_add: tensors missing or not 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)d->B * d->H * d->W * (d->C / 8);
+  auto* g = reinterpret_cast<unsigned short*>(d->g);
+  PIR_BY_DTYPE(d->dtype, (bcast_add_kernel<BF16><<<grid_for(total), 256, 0, s>>>(g, d->g_pitch, d->g_bstride, d->v, d->H * d->W, d->C, total)),
+               (bcast_add_kernel<FP16><<<grid_for(total), 256, 0, s>>>(g, d->g_pitch, d->g_bstride, d->v, d->H * d->W, d->C, total)));
+  return pir_check_launch("pir_bcast_add");
+}
+
+extern "C" int pir_nchw32_to_nhwc16(const PirToNhwc16* d, void* stream) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_nchw32_to_nhwc16: null descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0) return pir_fail(PIR_ERR_ARG, "pir_nchw32_to_nhwc16: empty problem");
+  if (d->Cpad != 8 || d->C > 8) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_nchw32_to_nhwc16: C <= 8 = Cpad only");
+  if ((d->out_pitch % 8) || (d->out_bstride % 8) || ((uintptr_t)d->out & 15) || !d->out || !d->src)
+    return pir_fail(PIR_ERR_ARG, "pir_nchw32_to_nhwc16: tensors missing or not 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)d->B * d->H * d->W;
+  auto* o = reinterpret_cast<unsigned short*>(d->out);
+  PIR_BY_DTYPE(d->dtype, (to_nhwc16_kernel<BF16><<<grid_for(total), 256, 0, s>>>(d->src, o, d->out_pitch, d->out_bstride, d->C, d->H * d->W, d->scale, total)),
+               (to_nhwc16_kernel<FP16><<<grid_for(total), 256, 0, s>>>(d->src, o, d->out_pitch, d->out_bstride, d->C, d->H * d->W, d->scale, total)));
+  return pir_check_launch("pir_nchw32_to_nhwc16");
+}
+
+extern "C" int pir_dw_wgrad_parts(int32_t B, int32_t H, int32_t W, int32_t C) {
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0) return 1;
+  const int cgroups = (C + 63) / 64;
+  int parts = (148 * 4 + cgroups - 1) / cgroups;
+  if (parts > B * H) parts = B * H;
+  return parts < 1 ? 1 : parts;
+}
+
+extern "C" int pir_dw_wgrad(const PirDwWgrad* d, void* stream) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_dw_wgrad: null descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->parts <= 0 || d->R <= 0) return pir_fail(PIR_ERR_ARG, "pir_dw_wgrad: empty problem");
+  if ((d->C % 8) || (d->x_pitch % 8) || (d->dy_pitch % 8) || (d->x_bstride % 8) || (d->dy_bstride % 8) || ((uintptr_t)d->x & 15) ||
+      ((uintptr_t)d->dy & 15) || !d->x || !d->dy || !d->ws || !d->dst_w)
+    return pir_fail(PIR_ERR_ARG, "pir_dw_wgrad: tensors missing or not 16-byte aligned");
+  if ((d->R > d->half ? d->R - d->half + d->half_pad : d->R) > d->C) return pir_fail(PIR_ERR_ARG, "pir_dw_wgrad: parameter larger than the tensor");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)d->parts, (unsigned)((d->C + 63) / 64));
+  auto* x = reinterpret_cast<const unsigned short*>(d->x);
+  auto* dy = reinterpret_cast<const unsigned short*>(d->dy);
+  PIR_BY_DTYPE(d->dtype, (dw_wgrad_kernel<BF16><<<grid, 256, 0, s>>>(x, d->x_pitch, d->x_bstride, dy, d->dy_pitch, d->dy_bstride, d->B, d->H, d->W, d->C, d->ws)),
+               (dw_wgrad_kernel<FP16><<<grid, 256, 0, s>>>(x, d->x_pitch, d->x_bstride, dy, d->dy_pitch, d->dy_bstride, d->B, d->H, d->W, d->C, d->ws)));
+  if (int e = pir_check_launch("pir_dw_wgrad")) return e;
+  dw_wgrad_fin_kernel<<<(unsigned)((d->R * 10 + 255) / 256), 256, 0, s>>>(d->ws, d->parts, d->C, d->R, d->half, d->half_pad, d->inv_scale, d->dst_w,
+                                                                         d->dst_bias);
+  return pir_check_launch("pir_dw_wgrad(finalize)");
+}
+
+extern "C" int64_t pir_mdta_bwd_ws_floats(int32_t B, int32_t C, int32_t heads) {
+  if (B <= 0 || C <= 0 || heads <= 0) return 0;
+  const int64_t c = C / heads;
+  return (int64_t)B * (2 * C + (int64_t)C * C + 2 * C * c + 3 * C);
+}
+
+extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: null descriptor");
+  if (d->B <= 0 || d->C <= 0 || d->heads <= 0 || d->splits_f <= 0 || d->splits_b <= 0) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: empty problem");
+  if (d->C % d->heads) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: C must be divisible by heads");
+  if (d->C / d->heads > 256 || d->heads > 8) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_mdta_bwd: head dim > 256 or heads > 8");
+  if (!d->ws_f || !d->ws_b || !d->temperature || !d->wo || !d->scratch || !d->wft || !d->wqk || !d->dst_wo || !d->dst_temp)
+    return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: missing pointers");
+  if (d->dst_bias && !d->colsum_b) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: bias gradient needs the column sums");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  MbArgs a{};
+  const int B = d->B, C = d->C, c = C / d->heads;
+  a.B = B; a.C = C; a.heads = d->heads; a.c = c; a.sf = d->splits_f; a.sb = d->splits_b;
+  a.gram = d->ws_f;
+  a.norm = d->ws_f + (size_t)B * a.sf * C * c;
+  a.attn = d->ws_f + (size_t)B * a.sf * ((size_t)C * c + 2 * C);
+  a.ws_b = d->ws_b; a.colsum_b = d->colsum_b; a.temperature = d->temperature; a.wo = d->wo; a.inv_scale = d->inv_scale;
+  float* p = d->scratch;
+  a.nrm = p; p += (size_t)B * 2 * C;
+  a.dWf = p; p += (size_t)B * C * C;
+  a.dcos = p; p += (size_t)B * C * c;
+  a.cosm = p; p += (size_t)B * C * c;
+  a.rq = p; p += (size_t)B * C;
+  a.rk = p; p += (size_t)B * C;
+  a.dTp = p;
+  a.dst_wo = d->dst_wo; a.dst_temp = d->dst_temp; a.dst_bias = d->dst_bias;
+  mdta_bwd_reduce_kernel<<<dim3((C * C + 255) / 256, B), 256, 0, s>>>(a);
+  if (int e = pir_check_launch("pir_mdta_bwd(reduce)")) return e;
+  mdta_bwd_rows_kernel<<<dim3((C + 7) / 8, B), 256, 0, s>>>(a);
+  if (int e = pir_check_launch("pir_mdta_bwd(rows)")) return e;
+  mdta_bwd_cols_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(a);
+  if (int e = pir_check_launch("pir_mdta_bwd(cols)")) return e;
+  const int kpad1 = (C + 63) / 64 * 64, kpad2 = (2 * C + 63) / 64 * 64;
+  dim3 gw((4 * C * C + 255) / 256, B, 2);
+  PIR_BY_DTYPE(d->dtype,
+               (mdta_bwd_weights_kernel<BF16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2, reinterpret_cast<unsigned short*>(d->wft), kpad1)),
+               (mdta_bwd_weights_kernel<FP16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2, reinterpret_cast<unsigned short*>(d->wft), kpad1)));
+  if (int e = pir_check_launch("pir_mdta_bwd(weights)")) return e;
+  mdta_bwd_dwo_kernel<<<(C * C + 255) / 256, 256, 0, s>>>(a);
+  if (int e = pir_check_launch("pir_mdta_bwd(dwo)")) return e;
+  mdta_bwd_small_kernel<<<1 + (d->dst_bias ? (C + 255) / 256 : 0), 256, 0, s>>>(a);
+  return pir_check_launch("pir_mdta_bwd(small)");
+}
+
+extern "C" int64_t pir_prompt_bwd_ws_floats(int32_t B, int32_t L, int32_t D, int32_t S) {
+  if (B <= 0 || L <= 0 || D <= 0 || S <= 0) return 0;
+  return (int64_t)B * ((int64_t)S * S * D + 2 * L);
+}
+
+extern "C" int pir_prompt_bwd(const PirPromptBwd* d, void* stream) {
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_prompt_bwd: null descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->C <= 0 || d->D <= 0 || d->S <= 0) return pir_fail(PIR_ERR_ARG, "pir_prompt_bwd: empty problem");
+  if (d->L < 1 || d->L > kMaxLTrain) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_prompt_bwd: 1 <= L <= 8");
+  if ((d->D % 8) || (d->dup_pitch % 8) || (d->dup_bstride % 8) || ((uintptr_t)d->dup & 15) || ((uintptr_t)d->scratch & 15))
+    return pir_fail(PIR_ERR_ARG, "pir_prompt_bwd: tensors not 16-byte aligned");
+  if (!d->dup || !d->prompt || !d->weights || !d->pool_ws || !d->lin_w || !d->scratch || !d->demb || !d->dst_prompt || !d->dst_lin_w || !d->dst_lin_b)
+    return pir_fail(PIR_ERR_ARG, "pir_prompt_bwd: missing pointers");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long n = (long long)d->S * d->S * d->D;
+  float* dmix = d->scratch;
+  float* dw = dmix + (size_t)d->B * n;
+  float* dlog = dw + (size_t)d->B * d->L;
+  const long long total = (long long)d->B * d->S * d->S * (d->D / 8);
+  auto* dup = reinterpret_cast<const unsigned short*>(d->dup);
+  PIR_BY_DTYPE(d->dtype, (prompt_bwd_dmix_kernel<BF16><<<grid_for(total), 256, 0, s>>>(dup, d->dup_pitch, d->dup_bstride, d->H, d->W, d->D, d->S, dmix, total)),
+               (prompt_bwd_dmix_kernel<FP16><<<grid_for(total), 256, 0, s>>>(dup, d->dup_pitch, d->dup_bstride, d->H, d->W, d->D, d->S, dmix, total)));
+  if (int e = pir_check_launch("pir_prompt_bwd(dmix)")) return e;
+  prompt_bwd_dot_kernel<<<dim3(d->L, d->B), 256, 0, s>>>(dmix, d->prompt, n, d->L, dw);
+  if (int e = pir_check_launch("pir_prompt_bwd(dot)")) return e;
+  const int HW = d->H * d->W;
+  int nchunks = (HW + 255) / 256;                       // pool_chunks() of pir_prompt_gen
+  nchunks = nchunks > 64 ? 64 : (nchunks < 1 ? 1 : nchunks);
+  prompt_bwd_small_kernel<<<1, 256, 0, s>>>(dw, d->weights, d->pool_ws, nchunks, d->B, d->L, d->C, HW, d->lin_w, d->inv_scale, dlog, d->demb,
+                                            d->dst_lin_w, d->dst_lin_b);
+  if (int e = pir_check_launch("pir_prompt_bwd(small)")) return e;
+  prompt_bwd_param_kernel<<<(unsigned)(((long long)d->D * d->S * d->S + 255) / 256), 256, 0, s>>>(dmix, d->weights, d->B, d->L, d->D, d->S * d->S,
+                                                                                                   d->inv_scale, d->dst_prompt);
+  return pir_check_launch("pir_prompt_bwd(param)");
+}

@@ -198,3 +198,210 @@ def tile_blend(tiles: torch.Tensor, ys: torch.Tensor, xs: torch.Tensor, out: tor
     _lib.check(lib.pir_tile_blend(tiles.data_ptr(), ny, nx, ys.data_ptr(), xs.data_ptr(), Cc, th, tw, out.data_ptr(),
                                   out.shape[-2], out.shape[-1], stream), "pir_tile_blend")
     _lib.launch_count += 1
+
+
+# ----------------------------------------------------------------------------------------------------
+# training ops (see train_engine.py).  The multi-output ones take the engine's record dict.
+# ----------------------------------------------------------------------------------------------------
+def _f32ptr(t: Optional[torch.Tensor], what: str) -> Optional[int]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError(f"{what}: expected a contiguous float32 tensor, got {t.dtype} strides {t.stride()}")
+    return t.data_ptr()
+
+
+def _ln_desc(x, xhat, rstd, ln_mode, g=None):
+    px, B, H, W, Cc, xp, xbs = _nhwc(x, "ln.x")
+    ph, hB, hH, hW, hC, hp, hbs = _nhwc(xhat, "ln.xhat")
+    assert (hB, hH, hW, hC) == (B, H, W, Cc) and xhat.dtype == x.dtype and rstd.numel() == B * H * W
+    d = _lib.PirLn()
+    d.dtype, d.ln_mode = dtype_code(x.dtype), ln_mode
+    d.B, d.H, d.W, d.C = B, H, W, Cc
+    d.x, d.x_pitch, d.x_bstride = px, xp, xbs
+    d.xhat, d.xh_pitch, d.xh_bstride = ph, hp, hbs
+    d.rstd = _f32ptr(rstd, "ln.rstd")
+    if g is not None:
+        pg, gB, gH, gW, gC, gp, gbs = _nhwc(g, "ln.g")
+        assert (gB, gH, gW, gC) == (B, H, W, Cc) and g.dtype == x.dtype
+        d.g, d.g_pitch, d.g_bstride = pg, gp, gbs
+    return d
+
+
+def ln_fwd(x, xhat, rstd, ln_mode) -> Launch:
+    return _prepared("pir_ln_fwd", _ln_desc(x, xhat, rstd, ln_mode), (x, xhat, rstd))
+
+
+def ln_bwd(d, xhat, rstd, g, ln_mode) -> Launch:
+    """g += LayerNorm backward of d = dL/d(xhat)."""
+    return _prepared("pir_ln_bwd", _ln_desc(d, xhat, rstd, ln_mode, g), (d, xhat, rstd, g))
+
+
+def wgrad_splits(B: int, HW: int, M: int, N: int, taps: int, per_image: bool) -> int:
+    return int(_lib.load().pir_wgrad_splits(B, HW, M, N, taps, int(per_image)))
+
+
+def _wg_layout(rec):
+    """float offsets of (partials, colsum) of a wgrad record inside the shared workspace."""
+    n = rec["P"] * rec["taps"] * rec["M"] * rec["N"]
+    return 0, (n if rec["colsum"] else None)
+
+
+def wgrad(ws: torch.Tensor, rec: dict) -> Launch:
+    a, b = rec["a"], rec["b"]
+    pa, B, H, W, M, ap, abs_ = _nhwc(a, "wgrad.a")
+    pb, bB, bH, bW, N, bp, bbs = _nhwc(b, "wgrad.b")
+    assert (bB, bH, bW) == (B, H, W) and a.dtype == b.dtype and (M, N) == (rec["M"], rec["N"])
+    off_p, off_c = _wg_layout(rec)
+    need = rec["P"] * rec["taps"] * M * N + (rec["P"] * M if rec["colsum"] else 0)
+    assert ws.dtype == torch.float32 and ws.numel() >= need
+    d = _lib.PirWgrad()
+    d.dtype = dtype_code(a.dtype)
+    d.B, d.H, d.W, d.M, d.N, d.taps = B, H, W, M, N, rec["taps"]
+    d.per_image, d.splits = int(rec["per_image"]), rec["splits"]
+    d.a, d.a_pitch, d.a_bstride = pa, ap, abs_
+    d.b, d.b_pitch, d.b_bstride = pb, bp, bbs
+    d.ws = ws.data_ptr() + 4 * off_p
+    d.colsum = None if off_c is None else ws.data_ptr() + 4 * off_c
+    return _prepared("pir_wgrad", d, (a, b, ws))
+
+
+def wgrad_finalize(ws: torch.Tensor, rec: dict) -> Launch:
+    wg, dst = rec["wg"], rec["dst_w"]
+    off_p, off_c = _wg_layout(wg)
+    d = _lib.PirWgradFin()
+    d.P, d.M, d.N, d.taps = wg["P"], wg["M"], wg["N"], wg["taps"]
+    d.R, d.Cc, d.half, d.half_pad = dst.shape[0], dst.shape[1], rec["half"], rec["half_pad"]
+    assert dst.numel() == d.R * d.Cc * d.taps
+    d.ws = ws.data_ptr() + 4 * off_p
+    d.colsum = None if off_c is None else ws.data_ptr() + 4 * off_c
+    d.inv_scale = rec["inv_scale"]
+    d.gamma, d.beta, d.w = _f32ptr(rec["gamma"], "fin.gamma"), _f32ptr(rec["beta"], "fin.beta"), _f32ptr(rec["w"], "fin.w")
+    d.dst_w = _f32ptr(dst, "fin.dst_w")
+    d.dst_gamma, d.dst_beta, d.dst_bias = (_f32ptr(rec[k], "fin." + k) for k in ("dst_gamma", "dst_beta", "dst_bias"))
+    keep = (ws, dst, rec["gamma"], rec["beta"], rec["w"], rec["dst_gamma"], rec["dst_beta"], rec["dst_bias"])
+    return _prepared("pir_wgrad_finalize", d, keep, kernels=2 if (rec["gamma"] is not None or rec["dst_bias"] is not None) else 1)
+
+
+def dw_wgrad_parts(B: int, H: int, W: int, Cp: int) -> int:
+    return int(_lib.load().pir_dw_wgrad_parts(B, H, W, Cp))
+
+
+def dw_wgrad(ws: torch.Tensor, rec: dict) -> Launch:
+    x, dy, dst = rec["x"], rec["dy"], rec["dst_w"]
+    px, B, H, W, Cp, xp, xbs = _nhwc(x, "dw_wgrad.x")
+    pd, dB, dH, dW, dC, dp, dbs = _nhwc(dy, "dw_wgrad.dy")
+    assert (dB, dH, dW, dC) == (B, H, W, Cp) and x.dtype == dy.dtype and ws.numel() >= rec["parts"] * 10 * Cp
+    d = _lib.PirDwWgrad()
+    d.dtype = dtype_code(x.dtype)
+    d.B, d.H, d.W, d.C = B, H, W, Cp
+    d.parts, d.R, d.half, d.half_pad = rec["parts"], dst.shape[0], rec["half"], rec["half_pad"]
+    assert dst.numel() == d.R * 9
+    d.x, d.x_pitch, d.x_bstride = px, xp, xbs
+    d.dy, d.dy_pitch, d.dy_bstride = pd, dp, dbs
+    d.ws, d.inv_scale = ws.data_ptr(), rec["inv_scale"]
+    d.dst_w, d.dst_bias = _f32ptr(dst, "dw_wgrad.dst_w"), _f32ptr(rec["dst_bias"], "dw_wgrad.dst_bias")
+    return _prepared("pir_dw_wgrad", d, (x, dy, ws, dst, rec["dst_bias"]), kernels=2)
+
+
+def gate_bwd(y: torch.Tensor, dgt: torch.Tensor) -> Launch:
+    py, B, H, W, C2, yp, ybs = _nhwc(y, "gate_bwd.y")
+    pg, gB, gH, gW, Cc, gp, gbs = _nhwc(dgt, "gate_bwd.dg")
+    assert (gB, gH, gW) == (B, H, W) and C2 == 2 * Cc and y.dtype == dgt.dtype
+    d = _lib.PirGateBwd()
+    d.dtype = dtype_code(y.dtype)
+    d.B, d.H, d.W, d.C = B, H, W, Cc
+    d.y, d.y_pitch, d.y_bstride = py, yp, ybs
+    d.dg, d.dg_pitch, d.dg_bstride = pg, gp, gbs
+    return _prepared("pir_gate_bwd", d, (y, dgt))
+
+
+def mdta_bwd_ws_floats(B: int, Cdim: int, heads: int) -> int:
+    return int(_lib.load().pir_mdta_bwd_ws_floats(B, Cdim, heads))
+
+
+def mdta_bwd(ws: torch.Tensor, rec: dict) -> Launch:
+    wg = rec["wg"]
+    B, Cdim, heads = rec["B"], rec["C"], rec["heads"]
+    off_p, off_c = _wg_layout(wg)
+    off_s = wg["P"] * Cdim * Cdim + (wg["P"] * Cdim if wg["colsum"] else 0)
+    assert ws.numel() >= off_s + mdta_bwd_ws_floats(B, Cdim, heads)
+    wft, wqk = rec["wft"], rec["wqk"]
+    assert wft.is_contiguous() and wqk.is_contiguous() and wft.numel() == B * Cdim * ((Cdim + 63) // 64 * 64)
+    assert wqk.numel() == B * 2 * Cdim * ((2 * Cdim + 63) // 64 * 64)
+    d = _lib.PirMdtaBwd()
+    d.dtype = dtype_code(wft.dtype)
+    d.B, d.C, d.heads, d.splits_f, d.splits_b = B, Cdim, heads, rec["splits"], wg["splits"]
+    d.ws_f = _f32ptr(rec["fws"], "mdta_bwd.fws")
+    d.ws_b = ws.data_ptr() + 4 * off_p
+    d.colsum_b = None if off_c is None else ws.data_ptr() + 4 * off_c
+    d.temperature, d.wo = _f32ptr(rec["temperature"].reshape(-1), "mdta_bwd.temperature"), _f32ptr(rec["wo"], "mdta_bwd.wo")
+    d.inv_scale = rec["inv_scale"]
+    d.scratch = ws.data_ptr() + 4 * off_s
+    d.wft, d.wqk = wft.data_ptr(), wqk.data_ptr()
+    d.dst_wo, d.dst_temp, d.dst_bias = _f32ptr(rec["dst_wo"], "dst_wo"), _f32ptr(rec["dst_temp"], "dst_temp"), _f32ptr(rec["dst_bias"], "dst_bias")
+    keep = (ws, rec["fws"], rec["temperature"], rec["wo"], wft, wqk, rec["dst_wo"], rec["dst_temp"], rec["dst_bias"])
+    return _prepared("pir_mdta_bwd", d, keep, kernels=6)
+
+
+def pixel_shuffle(x: torch.Tensor, out: torch.Tensor, *, up: bool) -> Launch:
+    """up: x [B,H,W,4c] -> out [B,2H,2W,c];  not up: x [B,2H,2W,c] -> out [B,H,W,4c]."""
+    px, xB, xH, xW, xC, xp, xbs = _nhwc(x, "shuffle.in")
+    po, oB, oH, oW, oC, op, obs = _nhwc(out, "shuffle.out")
+    big = (xH, xW, xC) if up else (oH, oW, oC)
+    small = (oH, oW, oC) if up else (xH, xW, xC)
+    assert xB == oB and small == (2 * big[0], 2 * big[1], big[2] // 4) and x.dtype == out.dtype
+    d = _lib.PirShuffle()
+    d.dtype, d.up = dtype_code(x.dtype), int(up)
+    d.B, d.H, d.W, d.C = xB, big[0], big[1], big[2]
+    d.in_, d.in_pitch, d.in_bstride = px, xp, xbs
+    d.out, d.out_pitch, d.out_bstride = po, op, obs
+    return _prepared("pir_pixel_shuffle", d, (x, out))
+
+
+def prompt_bwd_ws_floats(B: int, L: int, D: int, S: int) -> int:
+    return int(_lib.load().pir_prompt_bwd_ws_floats(B, L, D, S))
+
+
+def prompt_bwd(ws: torch.Tensor, rec: dict) -> Launch:
+    dup, prm = rec["dup"], rec["prompt"]
+    pd, B, H, W, D, dp, dbs = _nhwc(dup, "prompt_bwd.dup")
+    L, S = prm.shape[0], prm.shape[1]
+    assert tuple(prm.shape) == (L, S, S, D) and ws.numel() >= prompt_bwd_ws_floats(B, L, D, S)
+    assert rec["dst_prompt"].numel() == prm.numel() and tuple(rec["demb"].shape) == (B, rec["C"])
+    d = _lib.PirPromptBwd()
+    d.dtype = dtype_code(dup.dtype)
+    d.B, d.H, d.W, d.C, d.L, d.D, d.S = B, H, W, rec["C"], L, D, S
+    d.dup, d.dup_pitch, d.dup_bstride = pd, dp, dbs
+    d.prompt, d.weights = _f32ptr(prm, "prompt"), _f32ptr(rec["weights"], "weights")
+    d.pool_ws, d.lin_w = _f32ptr(rec["pool_ws"], "pool_ws"), _f32ptr(rec["lin_w"], "lin_w")
+    d.inv_scale = rec["inv_scale"]
+    d.scratch, d.demb = ws.data_ptr(), _f32ptr(rec["demb"], "demb")
+    d.dst_prompt, d.dst_lin_w, d.dst_lin_b = (_f32ptr(rec[k], k) for k in ("dst_prompt", "dst_lin_w", "dst_lin_b"))
+    keep = (ws, dup, prm, rec["weights"], rec["pool_ws"], rec["lin_w"], rec["demb"], rec["dst_prompt"], rec["dst_lin_w"], rec["dst_lin_b"])
+    return _prepared("pir_prompt_bwd", d, keep, kernels=4)
+
+
+def bcast_add(g: torch.Tensor, v: torch.Tensor) -> Launch:
+    pg, B, H, W, Cc, gp, gbs = _nhwc(g, "bcast_add.g")
+    assert tuple(v.shape) == (B, Cc)
+    d = _lib.PirBcastAdd()
+    d.dtype = dtype_code(g.dtype)
+    d.B, d.H, d.W, d.C = B, H, W, Cc
+    d.g, d.g_pitch, d.g_bstride = pg, gp, gbs
+    d.v = _f32ptr(v, "bcast_add.v")
+    return _prepared("pir_bcast_add", d, (g, v))
+
+
+def nchw32_to_nhwc16(src: torch.Tensor, out: torch.Tensor, scale: float) -> Launch:
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.is_cuda
+    B, Cc, H, W = src.shape
+    po, oB, oH, oW, oC, op, obs = _nhwc(out, "to_nhwc16.out")
+    assert (oB, oH, oW, oC) == (B, H, W, 8) and Cc <= 8
+    d = _lib.PirToNhwc16()
+    d.dtype = dtype_code(out.dtype)
+    d.B, d.C, d.H, d.W, d.Cpad = B, Cc, H, W, 8
+    d.src = src.data_ptr()
+    d.out, d.out_pitch, d.out_bstride = po, op, obs
+    d.scale = scale
+    return _prepared("pir_nchw32_to_nhwc16", d, (src, out))

@@ -128,3 +128,216 @@ def run_program(engine, img):
     for r in engine.ops:
         DISPATCH[r["kind"]](r)
     return engine.out.clone()
+
+
+# ----------------------------------------------------------------------------------------------------
+# training ops (promptir_b200/train_engine.py): forward extras and the backward kernels
+# ----------------------------------------------------------------------------------------------------
+def emu_ln_fwd(r):
+    x = r["x"].float()
+    mu = x.mean(-1, keepdim=True)
+    rstd = torch.rsqrt(((x - mu) ** 2).mean(-1, keepdim=True) + 1e-5)
+    xh = x * rstd if r["ln_mode"] == LN_BIASFREE else (x - mu) * rstd
+    r["xhat"].copy_(xh.to(r["xhat"].dtype))
+    r["rstd"].copy_(rstd.reshape(-1))
+
+
+def emu_ln_bwd(r):
+    d, xh, g = r["d"].float(), r["xhat"].float(), r["g"]
+    rstd = r["rstd"].view(*d.shape[:3], 1)
+    m = (d * xh).mean(-1, keepdim=True)
+    if r["ln_mode"] == LN_BIASFREE:
+        dx = rstd * (d - (xh - xh.mean(-1, keepdim=True)) * m)
+    else:
+        dx = rstd * (d - d.mean(-1, keepdim=True) - xh * m)
+    g.copy_((g.float() + dx).to(g.dtype))
+
+
+def _shifted(b, taps):
+    """b[p + off(tap)] for every tap (zero outside the image).  tap = ky*3 + kx, off = (ky-1, kx-1)."""
+    B, H, W, _ = b.shape
+    if taps == 1:
+        return [b]
+    bp = F.pad(b, (0, 0, 1, 1, 1, 1))
+    return [bp[:, t // 3:t // 3 + H, t % 3:t % 3 + W] for t in range(9)]
+
+
+def _wg_views(ws, r):
+    P, taps, M, N = r["P"], r["taps"], r["M"], r["N"]
+    part = ws[:P * taps * M * N].view(P, taps, M, N)
+    cs = ws[P * taps * M * N:P * taps * M * N + P * M].view(P, M) if r["colsum"] else None
+    return part, cs
+
+
+def emu_wgrad(r):
+    a, b = r["a"].float(), r["b"].float()
+    part, cs = _wg_views(r["ws"], r)
+    part.zero_()
+    sp = r["splits"]
+    for t, bs in enumerate(_shifted(b, r["taps"])):
+        if r["per_image"]:
+            part[::sp, t] = torch.einsum("bhwm,bhwn->bmn", a, bs)
+        else:
+            part[0, t] = torch.einsum("bhwm,bhwn->mn", a, bs)
+    if cs is not None:
+        cs.zero_()
+        if r["per_image"]:
+            cs[::sp] = a.sum((1, 2))
+        else:
+            cs[0] = a.sum((0, 1, 2))
+
+
+def _prow(R, half, half_pad, device):
+    idx = torch.arange(R, device=device)
+    return torch.where(idx < half, idx, idx - half + half_pad)
+
+
+def emu_wgrad_fin(r):
+    part, cs = _wg_views(r["ws"], r["wg"])
+    dst = r["dst_w"]
+    R, Cc = dst.shape[0], dst.shape[1]
+    inv = r["inv_scale"]
+    prow = _prow(R, r["half"], r["half_pad"], dst.device)
+    G = part.sum(0)[:, prow, :Cc] * inv                     # [taps, R, Cc]
+    s = cs.sum(0)[prow] * inv if cs is not None else None
+    if r["gamma"] is not None:
+        g0, w = G[0], r["w"].reshape(R, Cc).float()
+        dW = r["gamma"].view(1, -1) * g0
+        if r["beta"] is not None:
+            dW = dW + r["beta"].view(1, -1) * s.view(-1, 1)
+            r["dst_beta"].copy_((w * s.view(-1, 1)).sum(0))
+        r["dst_gamma"].copy_((w * g0).sum(0))
+        dst.copy_(dW.reshape(dst.shape))
+    else:
+        dst.copy_(G.permute(1, 2, 0).reshape(dst.shape))
+    if r["dst_bias"] is not None:
+        r["dst_bias"].copy_(s)
+
+
+def emu_dw_wgrad(r):
+    x, dy = r["x"].float(), r["dy"].float()
+    dst = r["dst_w"]
+    R = dst.shape[0]
+    prow = _prow(R, r["half"], r["half_pad"], dst.device)
+    taps = torch.stack([(xs * dy).sum((0, 1, 2)) for xs in _shifted(x, 9)])        # [9, Cp]
+    dst.copy_((taps[:, prow].t() * r["inv_scale"]).reshape(dst.shape))
+    if r["dst_bias"] is not None:
+        r["dst_bias"].copy_(dy.sum((0, 1, 2))[prow] * r["inv_scale"])
+
+
+def emu_gate_bwd(r):
+    y, dg = r["y"], r["dgt"].float()
+    c = dg.shape[-1]
+    y1, y2 = y[..., :c].float(), y[..., c:].float()
+    cdf = 0.5 * (1.0 + torch.erf(y1 * 0.7071067811865476))
+    pdf = torch.exp(-0.5 * y1 * y1) * 0.3989422804014327
+    d1 = dg * y2 * (cdf + y1 * pdf)
+    d2 = dg * y1 * cdf
+    y.copy_(torch.cat([d1, d2], -1).to(y.dtype))
+
+
+def emu_mdta_bwd(r):
+    qkv, heads, wo = r["qkv"], r["heads"], r["wo"]
+    B, H, W, c3 = qkv.shape
+    C = c3 // 3
+    c = C // heads
+    inv = r["inv_scale"]
+    part, cs = _wg_views(r["ws"], r["wg"])
+    dWf = part.view(B, -1, C, C).sum(1)                                               # [B, o, j']
+    q = qkv[..., :C].float().reshape(B, H * W, heads, c).permute(0, 2, 3, 1)
+    k = qkv[..., C:2 * C].float().reshape(B, H * W, heads, c).permute(0, 2, 3, 1)
+    qn = q.norm(dim=-1).clamp_min(1e-12)
+    kn = k.norm(dim=-1).clamp_min(1e-12)
+    nn_ = qn[..., :, None] * kn[..., None, :]
+    cos = (q @ k.transpose(-1, -2)) / nn_
+    T = r["temperature"].float().view(1, heads, 1, 1)
+    A = torch.softmax(cos * T, dim=-1)
+    wo_h = wo.view(C, heads, c)
+    dWf_h = dWf.view(B, C, heads, c)
+    dA = torch.einsum("ohi,bohj->bhij", wo_h, dWf_h)
+    r["dst_wo"].copy_(torch.einsum("bohj,bhij->ohi", dWf_h, A).reshape(C, C) * inv)
+    dS = A * (dA - (dA * A).sum(-1, keepdim=True))
+    r["dst_temp"].copy_((dS * cos).sum((0, 2, 3)) * inv)
+    dcos = dS * T
+    Mx = dcos / nn_
+    rq = (dcos * cos).sum(-1) / (qn * qn)                                             # [B, h, i]
+    rk = (dcos * cos).sum(-2) / (kn * kn)                                             # [B, h, j]
+    full = torch.zeros(B, 2 * C, 2 * C)
+    for h in range(heads):
+        s = slice(h * c, (h + 1) * c)
+        sk = slice(C + h * c, C + (h + 1) * c)
+        full[:, s, sk] = Mx[:, h]
+        full[:, sk, s] = Mx[:, h].transpose(-1, -2)
+        full[:, s, s] = torch.diag_embed(-rq[:, h])
+        full[:, sk, sk] = torch.diag_embed(-rk[:, h])
+    wqk, wft = r["wqk"], r["wft"]
+    wqk.view(B, 2 * C, -1)[:, :, :2 * C] = full.to(wqk.dtype)
+    fold = torch.einsum("ohi,bhij->bohj", wo_h, A).reshape(B, C, C)
+    wft.view(B, C, -1)[:, :, :C] = fold.transpose(1, 2).to(wft.dtype)
+    if r["dst_bias"] is not None:
+        r["dst_bias"].copy_(cs.sum(0) * inv)
+
+
+def emu_shuffle(r):
+    x, out = r["x"], r["out"]
+    f = F.pixel_shuffle if r["up"] else F.pixel_unshuffle
+    out.copy_(_nhwc(f(x.float().permute(0, 3, 1, 2), 2)).to(out.dtype))
+
+
+def emu_prompt_train(r):
+    """prompt forward that also leaves the pooled sums and softmax weights where pir_prompt_gen leaves them."""
+    emu_prompt(r)
+    x, lw, lb = r["x"], r["lin_w"], r["lin_b"]
+    B, H, W, C = x.shape
+    ws = r["ws"][:].view(B, -1, C)
+    ws.zero_()
+    ws[:, 0] = x.float().sum(dim=(1, 2))
+    if r.get("weights_out") is not None:
+        r["weights_out"].copy_(torch.softmax(x.float().mean(dim=(1, 2)) @ lw.t() + lb, dim=1))
+
+
+def emu_prompt_bwd(r):
+    dup, prm, wts, lw = r["dup"].float(), r["prompt"], r["weights"], r["lin_w"]
+    B, H, W, D = dup.shape
+    L, S = prm.shape[0], prm.shape[1]
+    inv = r["inv_scale"]
+    emb = r["pool_ws"].view(B, -1, r["C"]).sum(1) / r["HW"]
+    with torch.enable_grad():
+        mix = torch.zeros(B, D, S, S, requires_grad=True)
+        up = F.interpolate(mix, (H, W), mode="bilinear")
+        (dmix,) = torch.autograd.grad(up, mix, dup.permute(0, 3, 1, 2))
+    r["dst_prompt"].copy_(torch.einsum("bl,bdst->ldst", wts, dmix).unsqueeze(0) * inv)
+    dw = torch.einsum("bdst,lstd->bl", dmix, prm)
+    dlog = wts * (dw - (wts * dw).sum(1, keepdim=True))
+    r["dst_lin_w"].copy_(dlog.t() @ emb * inv)
+    r["dst_lin_b"].copy_(dlog.sum(0) * inv)
+    r["demb"].copy_(dlog @ lw / r["HW"])
+
+
+def emu_bcast_add(r):
+    g = r["g"]
+    g.copy_((g.float() + r["v"][:, None, None, :]).to(g.dtype))
+
+
+def emu_to_nhwc16(r):
+    src, out = r["src"], r["out"]
+    out.zero_()
+    out[..., :src.shape[1]] = (src.permute(0, 2, 3, 1) * r["scale"]).to(out.dtype)
+
+
+DISPATCH.update({"ln_fwd": emu_ln_fwd, "ln_bwd": emu_ln_bwd, "wgrad": emu_wgrad, "wgrad_fin": emu_wgrad_fin, "dw_wgrad": emu_dw_wgrad,
+                 "gate_bwd": emu_gate_bwd, "mdta_bwd": emu_mdta_bwd, "shuffle": emu_shuffle, "prompt_bwd": emu_prompt_bwd,
+                 "bcast_add": emu_bcast_add, "to_nhwc16": emu_to_nhwc16})
+
+
+@torch.no_grad()
+def run_train(engine, img, d_out):
+    """Emulated training forward + backward.  -> (out, {name: grad})."""
+    engine.img_in.copy_(img)
+    for r in engine.fwd_ops:
+        (emu_prompt_train if r["kind"] == "prompt" else DISPATCH[r["kind"]])(r)
+    out = engine.out.clone()
+    engine.d_out.copy_(d_out)
+    for r in engine.bwd_ops:
+        DISPATCH[r["kind"]](r)
+    return out, {k: v.clone() for k, v in engine.grads.items()}
