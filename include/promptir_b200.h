@@ -208,7 +208,7 @@ int pir_wgrad(const PirWgrad* d, void* stream);
 typedef struct PirWgradFin {
   int32_t P, M, N, taps;
   int32_t R, Cc, half, half_pad;
-  const float* ws; const float* colsum;
+  float* ws; float* colsum;                /* consumed: the LayerNorm path reduces them in place into partial 0 */
   float inv_scale;
   const float* gamma; const float* beta; const float* w;
   float* dst_w; float* dst_gamma; float* dst_beta; float* dst_bias;

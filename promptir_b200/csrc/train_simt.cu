@@ -401,7 +401,7 @@ dw_wgrad_fin_kernel(const float* __restrict__ ws, int parts, int C, int R, int h
 
 // ------------------------------------------------------------------------------------------------------
 // MDTA backward on the channel x channel matrices.  Scratch layout (floats), per pir_mdta_bwd_ws_floats():
-//   nrm [B][2C] | dWf [B][C][C] | dcos [B][C][c] | cosm [B][C][c] | rq [B][C] | rk [B][C] | dTp [B][C]
+//   nrm [B][2C] | dWf [B][C][C] | dcos [B][C][c] | cosm [B][C][c] | rq [B][C] | rk [B][C] | dTp [B][C] | dWoP [B][C][C]
 // ------------------------------------------------------------------------------------------------------
 struct MbArgs {
   int B, C, heads, c, sf, sb;
@@ -412,7 +412,7 @@ struct MbArgs {
   const float* colsum_b;  // [B*sb][C] or null
   const float* temperature; const float* wo;
   float inv_scale;
-  float *nrm, *dWf, *dcos, *cosm, *rq, *rk, *dTp;
+  float *nrm, *dWf, *dcos, *cosm, *rq, *rk, *dTp, *dWoP;
   float *dst_wo, *dst_temp, *dst_bias;
 };
 
@@ -539,21 +539,26 @@ __global__ void __launch_bounds__(256) mdta_bwd_weights_kernel(const MbArgs a, u
   }
 }
 
-// k5: dWo[o][h*c + i] = inv * sum_b sum_j dWf[b][o][h*c + j] A[b,h][i][j].  one thread per (o, channel)
-__global__ void __launch_bounds__(256) mdta_bwd_dwo_kernel(const MbArgs a) {
+// k5a: per-image dWoP[b][o][h*c + i] = sum_j dWf[b][o][h*c + j] A[b,h][i][j].  grid (ceil(C*C/256), B)
+__global__ void __launch_bounds__(256) mdta_bwd_dwo_part_kernel(const MbArgs a) {
   const int e = blockIdx.x * 256 + threadIdx.x;
+  const int b = blockIdx.y;
   if (e >= a.C * a.C) return;
   const int o = e / a.C, ch = e % a.C;
   const int h = ch / a.c, i = ch - h * a.c;
-  float s = 0.f;
-  for (int b = 0; b < a.B; ++b) {
-    const float* d = a.dWf + ((size_t)b * a.C + o) * a.C + h * a.c;
-    const float* A = a.attn + ((size_t)(b * a.heads + h) * a.c + i) * a.c;
-    float t = 0.f;
-    for (int j = 0; j < a.c; ++j) t = fmaf(d[j], A[j], t);
-    s += t;
-  }
-  a.dst_wo[e] = s * a.inv_scale;
+  const float* d = a.dWf + ((size_t)b * a.C + o) * a.C + h * a.c;
+  const float* A = a.attn + ((size_t)(b * a.heads + h) * a.c + i) * a.c;
+  float t0 = 0.f, t1 = 0.f;
+  int j = 0;
+  for (; j + 2 <= a.c; j += 2) { t0 = fmaf(d[j], A[j], t0); t1 = fmaf(d[j + 1], A[j + 1], t1); }
+  if (j < a.c) t0 = fmaf(d[j], A[j], t0);
+  a.dWoP[(size_t)b * a.C * a.C + e] = t0 + t1;
+}
+// k5b: dWo = inv * sum_b dWoP[b]
+__global__ void __launch_bounds__(256) mdta_bwd_dwo_kernel(const MbArgs a) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= a.C * a.C) return;
+  a.dst_wo[e] = sum_strided(a.dWoP + e, (size_t)a.C * a.C, a.B) * a.inv_scale;
 }
 
 // k6: temperature gradient (one warp per head) and project_out bias gradient
@@ -811,7 +816,7 @@ extern "C" int pir_dw_wgrad(const PirDwWgrad* d, void* stream) {
 extern "C" int64_t pir_mdta_bwd_ws_floats(int32_t B, int32_t C, int32_t heads) {
   if (B <= 0 || C <= 0 || heads <= 0) return 0;
   const int64_t c = C / heads;
-  return (int64_t)B * (2 * C + (int64_t)C * C + 2 * C * c + 3 * C);
+  return (int64_t)B * (2 * C + 2 * (int64_t)C * C + 2 * C * c + 3 * C);
 }
 
 extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
@@ -837,7 +842,8 @@ extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
   a.cosm = p; p += (size_t)B * C * c;
   a.rq = p; p += (size_t)B * C;
   a.rk = p; p += (size_t)B * C;
-  a.dTp = p;
+  a.dTp = p; p += (size_t)B * C;
+  a.dWoP = p;
   a.dst_wo = d->dst_wo; a.dst_temp = d->dst_temp; a.dst_bias = d->dst_bias;
   mdta_bwd_reduce_kernel<<<dim3((C * C + 255) / 256, B), 256, 0, s>>>(a);
   if (int e = pir_check_launch("pir_mdta_bwd(reduce)")) return e;
@@ -851,6 +857,8 @@ extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
                (mdta_bwd_weights_kernel<BF16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2, reinterpret_cast<unsigned short*>(d->wft), kpad1)),
                (mdta_bwd_weights_kernel<FP16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2, reinterpret_cast<unsigned short*>(d->wft), kpad1)));
   if (int e = pir_check_launch("pir_mdta_bwd(weights)")) return e;
+  mdta_bwd_dwo_part_kernel<<<dim3((C * C + 255) / 256, B), 256, 0, s>>>(a);
+  if (int e = pir_check_launch("pir_mdta_bwd(dwo part)")) return e;
   mdta_bwd_dwo_kernel<<<(C * C + 255) / 256, 256, 0, s>>>(a);
   if (int e = pir_check_launch("pir_mdta_bwd(dwo)")) return e;
   mdta_bwd_small_kernel<<<1 + (d->dst_bias ? (C + 255) / 256 : 0), 256, 0, s>>>(a);

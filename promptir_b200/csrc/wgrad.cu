@@ -282,42 +282,64 @@ wgrad_fin_kernel(const PirWgradFin f) {
   const int pr = prow_of(r, f.half, f.half_pad);
   const size_t pstride = (size_t)f.taps * f.M * f.N;
   for (int t = 0; t < f.taps; ++t) {
-    float G = sum_parts(f.ws + ((size_t)t * f.M + pr) * f.N + k, pstride, f.P) * f.inv_scale;
-    if (f.gamma) {
-      G *= f.gamma[k];
-      if (f.beta) G += f.beta[k] * sum_parts(f.colsum + pr, (size_t)f.M, f.P) * f.inv_scale;
-    }
+    const float G = sum_parts(f.ws + ((size_t)t * f.M + pr) * f.N + k, pstride, f.P) * f.inv_scale;
     f.dst_w[((size_t)r * f.Cc + k) * f.taps + t] = G;
   }
 }
 
-// dgamma / dbeta: one warp per input channel k, lanes stride over the rows.  dbias: one thread per row (blocks after the k blocks)
+// LayerNorm-folded weights, step 1: reduce the P partials IN PLACE into partial 0 (and colsum 0).  Blocks [0, nmain) take the
+// matrix, the rest the column sums.
 __global__ void __launch_bounds__(256)
-wgrad_fin_vec_kernel(const PirWgradFin f, int kblocks) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if ((int)blockIdx.x < kblocks) {
-    const int k = blockIdx.x * 8 + warp;
-    if (k >= f.Cc || !f.gamma) return;
-    float dg = 0.f, db = 0.f;
-    for (int r = lane; r < f.R; r += 32) {
-      const int pr = prow_of(r, f.half, f.half_pad);
-      const float w = f.w[(size_t)r * f.Cc + k];
-      dg = fmaf(w, sum_parts(f.ws + (size_t)pr * f.N + k, (size_t)f.M * f.N, f.P), dg);
-      if (f.dst_beta) db = fmaf(w, sum_parts(f.colsum + pr, (size_t)f.M, f.P), db);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      dg += __shfl_xor_sync(0xffffffffu, dg, o);
-      db += __shfl_xor_sync(0xffffffffu, db, o);
-    }
-    if (lane == 0) {
-      f.dst_gamma[k] = dg * f.inv_scale;
-      if (f.dst_beta) f.dst_beta[k] = db * f.inv_scale;
-    }
-  } else if (f.dst_bias) {
-    const int r = ((int)blockIdx.x - kblocks) * 256 + threadIdx.x;
-    if (r < f.R) f.dst_bias[r] = sum_parts(f.colsum + prow_of(r, f.half, f.half_pad), (size_t)f.M, f.P) * f.inv_scale;
+wgrad_reduce_inplace_kernel(float* __restrict__ ws, float* __restrict__ colsum, int P, long long MN, int M, int nmain) {
+  if ((int)blockIdx.x < nmain) {
+    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (e < MN) ws[e] = sum_parts(ws + e, (size_t)MN, P);
+  } else if (colsum) {
+    const int m = ((int)blockIdx.x - nmain) * 256 + threadIdx.x;
+    if (m < M) colsum[m] = sum_parts(colsum + m, (size_t)M, P);
   }
+}
+
+// step 2: dW = gamma G + beta s, and the column reductions dgamma[k] = sum_r W G, dbeta[k] = sum_r W s.  One block per 32 input
+// channels (lane = channel: coalesced), 8 warps stride over the rows; block 0 also writes dbias.
+__global__ void __launch_bounds__(256)
+wgrad_ln_apply_kernel(const PirWgradFin f) {
+  __shared__ float sg[8][32], sb[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 32 + lane;
+  float dg = 0.f, db = 0.f;
+  if (k < f.Cc) {
+    const float gam = f.gamma[k], bet = f.beta ? f.beta[k] : 0.f;
+#pragma unroll 4
+    for (int r = warp; r < f.R; r += 8) {
+      const int pr = prow_of(r, f.half, f.half_pad);
+      const float G = f.ws[(size_t)pr * f.N + k] * f.inv_scale;
+      const float s = f.colsum ? f.colsum[pr] * f.inv_scale : 0.f;
+      const float w = f.w[(size_t)r * f.Cc + k];
+      f.dst_w[(size_t)r * f.Cc + k] = fmaf(gam, G, bet * s);
+      dg = fmaf(w, G, dg);
+      db = fmaf(w, s, db);
+    }
+  }
+  sg[warp][lane] = dg;
+  sb[warp][lane] = db;
+  __syncthreads();
+  if (warp == 0 && k < f.Cc) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += sg[w][lane]; b += sb[w][lane]; }
+    f.dst_gamma[k] = a;
+    if (f.dst_beta) f.dst_beta[k] = b;
+  }
+  if (blockIdx.x == 0 && f.dst_bias)
+    for (int r = threadIdx.x; r < f.R; r += 256) f.dst_bias[r] = f.colsum[prow_of(r, f.half, f.half_pad)] * f.inv_scale;
+}
+
+// plain weights: bias gradient, one thread per row
+__global__ void __launch_bounds__(256)
+wgrad_fin_bias_kernel(const PirWgradFin f) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r < f.R) f.dst_bias[r] = sum_parts(f.colsum + prow_of(r, f.half, f.half_pad), (size_t)f.M, f.P) * f.inv_scale;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -441,14 +463,20 @@ extern "C" int pir_wgrad_finalize(const PirWgradFin* d, void* stream) {
   if ((d->beta || d->dst_bias || d->dst_beta) && !d->colsum) return pir_fail(PIR_ERR_ARG, "pir_wgrad_finalize: beta / bias gradients need the column sums");
   if ((d->dst_beta != nullptr) != (d->beta != nullptr)) return pir_fail(PIR_ERR_ARG, "pir_wgrad_finalize: beta and dst_beta go together");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (d->gamma) {                                         // LayerNorm-folded 1x1 conv: reduce in place, then apply + column sums
+    const long long MN = (long long)d->M * d->N;
+    const int nmain = (int)((MN + 255) / 256), ncs = d->colsum ? (d->M + 255) / 256 : 0;
+    pir::wgrad_reduce_inplace_kernel<<<(unsigned)(nmain + ncs), 256, 0, s>>>(d->ws, d->colsum, d->P, MN, d->M, nmain);
+    if (int e = pir_check_launch("pir_wgrad_finalize(reduce)")) return e;
+    pir::wgrad_ln_apply_kernel<<<(unsigned)((d->Cc + 31) / 32), 256, 0, s>>>(*d);
+    return pir_check_launch("pir_wgrad_finalize(ln)");
+  }
   const long long total = (long long)d->R * d->Cc;
   pir::wgrad_fin_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*d);
   if (int e = pir_check_launch("pir_wgrad_finalize")) return e;
-  if (d->gamma || d->dst_bias) {
-    const int kblocks = d->gamma ? (d->Cc + 7) / 8 : 0;
-    const int rblocks = d->dst_bias ? (d->R + 255) / 256 : 0;
-    pir::wgrad_fin_vec_kernel<<<(unsigned)(kblocks + rblocks), 256, 0, s>>>(*d, kblocks);
-    return pir_check_launch("pir_wgrad_finalize(vec)");
+  if (d->dst_bias) {
+    pir::wgrad_fin_bias_kernel<<<(unsigned)((d->R + 255) / 256), 256, 0, s>>>(*d);
+    return pir_check_launch("pir_wgrad_finalize(bias)");
   }
   return PIR_OK;
 }

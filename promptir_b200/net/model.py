@@ -100,6 +100,33 @@ def _blocks(n: int, dim: int, heads: int, f: float, bias: bool, ln: str) -> nn.S
 
 
 # ----------------------------------------------------------------------------------------------------
+class _PromptIRFunction(torch.autograd.Function):
+    """Autograd node of the whole network: forward = the training launch program, backward = the hand-written backward program
+    (promptir_b200/train_engine.py).  Replaces the ~5000 ATen backward kernels autograd runs for net/model.py under train.py:41-46."""
+
+    @staticmethod
+    def forward(ctx, module, eng, img, *params):
+        out = eng.forward(img, use_graph=module.use_cuda_graph)
+        eng.generation += 1
+        ctx.module, ctx.eng, ctx.generation = module, eng, eng.generation
+        ctx.need_img = img.requires_grad
+        ctx.need = [p.requires_grad for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        eng, module = ctx.eng, ctx.module
+        if eng.generation != ctx.generation:
+            raise RuntimeError("promptir_b200: the activations kept for this backward were overwritten by a later differentiable "
+                               "forward of the same shape; call backward() before the next forward (as train.py does)")
+        eng.backward(d_out.contiguous().float(), use_graph=module.use_cuda_graph)
+        grads = []
+        for (name, _), need in zip(module.named_parameters(), ctx.need):
+            # parameters the forward never reads (chnl_reduce*, reduce_noise_channel_*: model.py:271-287) get no gradient, like autograd
+            grads.append(eng.grads[name] if (need and name in eng.live_params) else None)
+        return (None, None, eng.d_img.clone() if ctx.need_img else None, *grads)
+
+
 class PromptIR(nn.Module):
     def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4,
                  heads=[1, 2, 4, 8], ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias", decoder=False):
@@ -146,6 +173,8 @@ class PromptIR(nn.Module):
         self.compute_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[os.environ.get("PROMPTIR_B200_DTYPE", "bf16")]
         self.use_cuda_graph = os.environ.get("PROMPTIR_B200_GRAPH", "1") != "0"
         self._engines: Dict[Tuple, object] = {}
+        self._train_engine = None
+        self.grad_scale: Optional[float] = None             # static loss scale of the 16-bit backward (None: 1 for bf16, 65536 for fp16)
 
     # -- engine cache ------------------------------------------------------------------------------
     def engine_for(self, batch: int, height: int, width: int, device: torch.device):
@@ -162,8 +191,19 @@ class PromptIR(nn.Module):
             self._engines[key] = eng
         return eng
 
+    def train_engine_for(self, batch: int, height: int, width: int, device: torch.device, input_grad: bool = False):
+        """The forward+backward program for this shape (one is kept: it holds every block's activations)."""
+        from ..train_engine import TrainEngine
+        key = (batch, height, width, str(device), self.compute_dtype, input_grad, self.grad_scale)
+        if self._train_engine is None or self._train_engine[0] != key:
+            self._train_engine = None                       # free the old arena before building the new one
+            self._train_engine = (key, TrainEngine(self, batch, height, width, device, self.compute_dtype,
+                                                   grad_scale=self.grad_scale, input_grad=input_grad))
+        return self._train_engine[1]
+
     def _apply(self, fn, *a, **k):                          # .to()/.cuda() moves parameters -> caches are stale
         self._engines = {}
+        self._train_engine = None
         return super()._apply(fn, *a, **k)
 
     def forward(self, inp_img: torch.Tensor, noise_emb=None) -> torch.Tensor:   # model.py:322 (noise_emb is ignored there too)
@@ -180,12 +220,13 @@ class PromptIR(nn.Module):
         if h % 8 or w % 8:
             raise RuntimeError(f"pixel_unshuffle expects height and width to be divisible by 8 across the three "
                                f"downsamples, got {h}x{w} (same constraint as the reference; see demo.py pad_input)")
-        if torch.is_grad_enabled() and (inp_img.requires_grad or any(p.requires_grad for p in self.parameters())):
-            if self.training:
-                raise NotImplementedError(
-                    "promptir_b200: the sm_100a backward kernels are not built yet (SURVEY.md §8f-1); run the forward "
-                    "under torch.no_grad() / module.eval(), as test.py and demo.py do")
-        eng = self.engine_for(b, h, w, inp_img.device)
         x = inp_img if (inp_img.dtype == torch.float32 and inp_img.is_contiguous()) else inp_img.float().contiguous()
+        if torch.is_grad_enabled() and (inp_img.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # differentiable call (train.py:41): the training program keeps activations and autograd gets a hand-written backward
+            eng = self.train_engine_for(b, h, w, inp_img.device, input_grad=inp_img.requires_grad)
+            params = [p for _, p in self.named_parameters()]
+            out = _PromptIRFunction.apply(self, eng, x, *params)
+            return out if inp_img.dtype == torch.float32 else out.to(inp_img.dtype)
+        eng = self.engine_for(b, h, w, inp_img.device)
         out = eng.run(x, use_graph=self.use_cuda_graph)
         return out if inp_img.dtype == torch.float32 else out.to(inp_img.dtype)

@@ -255,6 +255,14 @@ class TrainEngine(Engine):
             fn()
         self._bwd_stack = []
         self.ops = self.fwd_ops + self.bwd_ops
+        # parameters that receive a gradient = those some backward record writes (the reference's 6 dead convs get none)
+        written = set()
+        for r in self.bwd_ops:
+            for k, v in r.items():
+                if k.startswith("dst_") and v is not None:
+                    written.add(v.data_ptr())
+        self.live_params = {n for n, gview in self.grads.items() if gview.data_ptr() in written}
+        self.generation = 0
         self._param_version = self._current_version()
         self.fwd_launches = [r["launch"] for r in self.fwd_ops]
         self.bwd_launches = [r["launch"] for r in self.bwd_ops]
@@ -508,5 +516,5 @@ class TrainEngine(Engine):
         self._run("fwd", self.fwd_launches, use_graph)
 
     def kernels_per_step(self) -> int:
-        per = {"mdta_finalize": 2, "prompt": 2, "wgrad_fin": 2, "dw_wgrad": 2, "mdta_bwd": 5, "prompt_bwd": 4}
+        per = {"mdta_finalize": 2, "prompt": 2, "wgrad_fin": 2, "dw_wgrad": 2, "mdta_bwd": 7, "prompt_bwd": 4}
         return sum(per.get(r["kind"], 1) for r in self.ops)

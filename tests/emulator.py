@@ -262,7 +262,7 @@ def emu_mdta_bwd(r):
     Mx = dcos / nn_
     rq = (dcos * cos).sum(-1) / (qn * qn)                                             # [B, h, i]
     rk = (dcos * cos).sum(-2) / (kn * kn)                                             # [B, h, j]
-    full = torch.zeros(B, 2 * C, 2 * C)
+    full = torch.zeros(B, 2 * C, 2 * C, device=qkv.device)
     for h in range(heads):
         s = slice(h * c, (h + 1) * c)
         sk = slice(C + h * c, C + (h + 1) * c)
@@ -303,7 +303,7 @@ def emu_prompt_bwd(r):
     inv = r["inv_scale"]
     emb = r["pool_ws"].view(B, -1, r["C"]).sum(1) / r["HW"]
     with torch.enable_grad():
-        mix = torch.zeros(B, D, S, S, requires_grad=True)
+        mix = torch.zeros(B, D, S, S, device=dup.device, requires_grad=True)
         up = F.interpolate(mix, (H, W), mode="bilinear")
         (dmix,) = torch.autograd.grad(up, mix, dup.permute(0, 3, 1, 2))
     r["dst_prompt"].copy_(torch.einsum("bl,bdst->ldst", wts, dmix).unsqueeze(0) * inv)
