@@ -310,61 +310,91 @@ to_nhwc16_kernel(const float* __restrict__ src, unsigned short* __restrict__ out
 }
 
 // ------------------------------------------------------------------------------------------------------
-// depthwise 3x3 weight gradient.  grid (parts, channel groups of 64); block 256 = 32 pixel lanes x 8 channel lanes.
-// A CTA takes a contiguous range of image rows; each thread walks x = lane, lane + 32, ... and keeps 9 + 1 fp32 accumulators
-// for each of its 8 channels (FHFMA: 16-bit x 16-bit -> fp32).  Neighbour loads overlap in L1.
+// depthwise 3x3 weight gradient  dw[c][tap] = sum_p dy[p, c] x[p + off(tap), c]  (+ bias gradient sum_p dy).
+// Same structure as the forward stencil (dwconv.cu): persistent CTAs per 64-channel chunk walk (image, 8 x 32 pixel tile) items;
+// one 4-D TMA box brings the x tile with its halo and one the dy tile into a double buffer (zero fill outside the image = the
+// conv's zero padding, and zero dy outside = no contribution).  A thread owns a pixel column and 8 channels, walks down the rows
+// with the last three dy rows in registers and keeps its 9 + 1 fp32 accumulators x 8 channels for the CTA's whole lifetime
+// (FHFMA: 16-bit x 16-bit + fp32); one deterministic block reduction at the end writes ws[cta][10][C].
 // ------------------------------------------------------------------------------------------------------
-template <class T>
+struct DwwArgs {
+  int H, W, C;
+  int tiles_x, tiles_y, n_sp;
+  float* ws;
+};
+
+template <class T, int TH>
 __global__ void __launch_bounds__(256)
-dw_wgrad_kernel(const unsigned short* __restrict__ x, long long xpitch, long long xbs, const unsigned short* __restrict__ dy, long long dpitch,
-                long long dbs, int B, int H, int W, int C, float* __restrict__ ws) {
+dw_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD, const DwwArgs a) {
+  constexpr int SW = 34, RB = 128;
+  constexpr uint32_t XT = (TH + 2) * SW * RB, DT = TH * 32 * RB, BUF = XT + DT;
+  extern __shared__ uint8_t dww_raw[];
+  __shared__ __align__(8) uint64_t bar[2];
   __shared__ float red[8][10][64];
-  const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  const int warp = threadIdx.x >> 5;
-  const int c = blockIdx.y * 64 + cl * 8;
-  const bool c_ok = c < C;
-  const int rows = B * H;
-  const int per = (rows + gridDim.x - 1) / gridDim.x;
-  const int r_begin = blockIdx.x * per, r_end = min(r_begin + per, rows);
+  uint8_t* sm = dww_raw + ((128u - (smem_u32(dww_raw) & 127u)) & 127u);
+  const int tid = threadIdx.x, cg = tid & 7, tx = tid >> 3, warp = tid >> 5;
+  const int c0 = blockIdx.y * 64;
+  const uint32_t bar_a[2] = {smem_u32(&bar[0]), smem_u32(&bar[1])};
+  const int per_img = a.tiles_x * a.tiles_y;
+  auto issue = [&](int sp, int buf) {      // thread 0 only
+    const int b = sp / per_img, r = sp % per_img;
+    const int x0 = (r % a.tiles_x) * 32, y0 = (r / a.tiles_x) * TH;
+    mbar_expect_tx(bar_a[buf], BUF);
+    tma_load_4d(smem_u32(sm) + buf * BUF, &tmX, bar_a[buf], c0, x0 - 1, y0 - 1, b);
+    tma_load_4d(smem_u32(sm) + buf * BUF + XT, &tmD, bar_a[buf], c0, x0, y0, b);
+  };
+  if (tid == 0) {
+    mbar_init(bar_a[0], 1);
+    mbar_init(bar_a[1], 1);
+    fence_barrier_init();
+    if ((int)blockIdx.x < a.n_sp) issue(blockIdx.x, 0);
+  }
   float acc[10][8];
 #pragma unroll
   for (int t = 0; t < 10; ++t)
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
-  if (c_ok) {
-    for (int r = r_begin; r < r_end; ++r) {
-      const int b = r / H, yy = r % H;
-      const unsigned short* xb = x + (size_t)b * xbs + c;
-      const unsigned short* db = dy + (size_t)b * dbs + c;
-      for (int xx = pl; xx < W; xx += 32) {
-        const uint4 dv = __ldg(reinterpret_cast<const uint4*>(db + ((size_t)yy * W + xx) * dpitch));
-        const uint32_t dw4[4] = {dv.x, dv.y, dv.z, dv.w};
-        float df[8];
-        unpack8t<T>(dv, df);
+  __syncthreads();
+  int it = 0;
+  for (int sp = blockIdx.x; sp < a.n_sp; sp += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (tid == 0 && sp + (int)gridDim.x < a.n_sp) issue(sp + gridDim.x, buf ^ 1);
+    mbar_wait(bar_a[buf], (it >> 1) & 1);
+    const uint8_t* xs = sm + (size_t)buf * BUF + (size_t)tx * RB + cg * 16;
+    const uint8_t* ds = sm + (size_t)buf * BUF + XT + (size_t)tx * RB + cg * 16;
+    uint4 dyv[3];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[9][i] += df[i];
+    for (int r = 0; r < TH + 2; ++r) {
+      if (r < TH) {
+        dyv[r % 3] = *reinterpret_cast<const uint4*>(ds + (size_t)r * 32 * RB);
+        const uint32_t dq[4] = {dyv[r % 3].x, dyv[r % 3].y, dyv[r % 3].z, dyv[r % 3].w};
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int sy = yy + ky - 1;
-          if (sy < 0 || sy >= H) continue;
+        for (int q = 0; q < 4; ++q) { acc[9][2 * q] += unpack_lo<T>(dq[q]); acc[9][2 * q + 1] += unpack_hi<T>(dq[q]); }
+      }
+      uint4 xv[3];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) xv[kx] = *reinterpret_cast<const uint4*>(xs + ((size_t)r * SW + kx) * RB);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int o = r - ky;                        // x row r is tap row ky of output row o
+        if (o >= 0 && o < TH) {
+          const uint32_t dq[4] = {dyv[o % 3].x, dyv[o % 3].y, dyv[o % 3].z, dyv[o % 3].w};
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const int sx = xx + kx - 1;
-            if (sx < 0 || sx >= W) continue;
-            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)sy * W + sx) * xpitch));
-            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-            float* a = acc[ky * 3 + kx];
+            const uint32_t xw[4] = {xv[kx].x, xv[kx].y, xv[kx].z, xv[kx].w};
+            float* ac = acc[ky * 3 + kx];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              a[2 * q] = fma16<T>(lo16(xw[q]), lo16(dw4[q]), a[2 * q]);
-              a[2 * q + 1] = fma16<T>(hi16(xw[q]), hi16(dw4[q]), a[2 * q + 1]);
+              ac[2 * q] = fma16<T>(lo16(xw[q]), lo16(dq[q]), ac[2 * q]);
+              ac[2 * q + 1] = fma16<T>(hi16(xw[q]), hi16(dq[q]), ac[2 * q + 1]);
             }
           }
         }
       }
     }
+    __syncthreads();                 // everyone is done with this buffer before it is refilled
   }
-  // reduce over the 4 pixel lanes of a warp, then over the 8 warps
+  // reduce over the 4 pixel columns of a warp, then over the 8 warps
 #pragma unroll
   for (int t = 0; t < 10; ++t)
 #pragma unroll
@@ -372,16 +402,15 @@ dw_wgrad_kernel(const unsigned short* __restrict__ x, long long xpitch, long lon
       float v = acc[t][i];
       v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((threadIdx.x & 31) < 8) red[warp][t][cl * 8 + i] = v;
+      if ((tid & 31) < 8) red[warp][t][cg * 8 + i] = v;
     }
   __syncthreads();
-  for (int e = threadIdx.x; e < 10 * 64; e += 256) {
+  for (int e = tid; e < 10 * 64; e += 256) {
     const int t = e >> 6, ch = e & 63;
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][t][ch];
-    const int cc = blockIdx.y * 64 + ch;
-    if (cc < C) ws[((size_t)blockIdx.x * 10 + t) * C + cc] = s;
+    if (c0 + ch < a.C) a.ws[((size_t)blockIdx.x * 10 + t) * a.C + c0 + ch] = s;
   }
 }
 
@@ -433,7 +462,69 @@ __global__ void __launch_bounds__(256) mdta_bwd_reduce_kernel(const MbArgs a) {
     a.nrm[(size_t)b * 2 * a.C + e] = fmaxf(sqrtf(sum_strided(a.norm + (size_t)b * a.sf * 2 * a.C + e, (size_t)2 * a.C, a.sf)), 1e-12f);
 }
 
-// k2: one warp per attention row (b, r = h*c + i): dA -> softmax backward -> dcos, cos, rq, temperature partial.  c <= 256
+// Strided, batched fp32 GEMM for the channel x channel products of the MDTA backward (three per block, up to 704 x 176 x 704 per
+// image): out[z][m][n] = sum_k A[z][m][k] B[z][k][n], z = (image, head).  64 x 64 tile, K chunks of 16, 256 threads x (4 x 4) outputs.
+// Operand strides are free (the matrices are transposed / head-sliced views), so tile loads pick the unit-stride axis for coalescing.
+struct SgArgs {
+  int M, N, K, heads;
+  const float* A; long long a_sm, a_sk, a_sb, a_sh;
+  const float* B; long long b_sk, b_sn, b_sb, b_sh;
+  float* out; unsigned short* out16; long long o_sm, o_sn, o_sb, o_sh;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) sgemm_strided_kernel(const SgArgs g) {
+  __shared__ __align__(16) float As[16][64];
+  __shared__ __align__(16) float Bs[16][64];
+  const int z = blockIdx.z, b = z / g.heads, h = z % g.heads;
+  const float* A = g.A + (size_t)b * g.a_sb + (size_t)h * g.a_sh;
+  const float* Bm = g.B + (size_t)b * g.b_sb + (size_t)h * g.b_sh;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < g.K; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m, k;
+      if (g.a_sm == 1) { m = t & 63; k = (t >> 6) + 4 * i; } else { k = t & 15; m = (t >> 4) + 16 * i; }
+      As[k][m] = (m0 + m < g.M && k0 + k < g.K) ? A[(size_t)(m0 + m) * g.a_sm + (size_t)(k0 + k) * g.a_sk] : 0.f;
+      int n, kb;
+      if (g.b_sn == 1) { n = t & 63; kb = (t >> 6) + 4 * i; } else { kb = t & 15; n = (t >> 4) + 16 * i; }
+      Bs[kb][n] = (n0 + n < g.N && k0 + kb < g.K) ? Bm[(size_t)(k0 + kb) * g.b_sk + (size_t)(n0 + n) * g.b_sn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      const size_t o = (size_t)b * g.o_sb + (size_t)h * g.o_sh + (size_t)m * g.o_sm + (size_t)n * g.o_sn;
+      if (g.out16) g.out16[o] = to16<T>(acc[i][j]);
+      else g.out[o] = acc[i][j];
+    }
+  }
+}
+
+// k2: one warp per attention row (b, r = h*c + i): softmax backward of dA (in place -> dcos), cos, rq, temperature partial.  c <= 256
 __global__ void __launch_bounds__(256) mdta_bwd_rows_kernel(const MbArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
@@ -443,17 +534,11 @@ __global__ void __launch_bounds__(256) mdta_bwd_rows_kernel(const MbArgs a) {
   const int h = r / c, i = r - h * c;
   const float qn = a.nrm[(size_t)b * 2 * C + r];
   const float T = a.temperature[h];
-  const float* dWf = a.dWf + (size_t)b * C * C + h * c;
   float dA[8], A[8], cs[8];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) dA[t] = 0.f;
-  for (int o = 0; o < C; ++o) {
-    const float w = __ldg(a.wo + (size_t)o * C + r);
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int j = lane + t * 32;
-      if (j < c) dA[t] = fmaf(w, dWf[(size_t)o * C + j], dA[t]);
-    }
+  for (int t = 0; t < 8; ++t) {                       // dA = Wo_h^T dWf_h was left in the dcos buffer by the SGEMM
+    const int j = lane + t * 32;
+    dA[t] = j < c ? a.dcos[((size_t)b * C + r) * c + j] : 0.f;
   }
   float dot = 0.f;
 #pragma unroll
@@ -503,15 +588,14 @@ __global__ void __launch_bounds__(256) mdta_bwd_cols_kernel(const MbArgs a) {
   a.rk[e] = s / (kn * kn);
 }
 
-// k4: the two per-image weight sets.  grid (ceil(2C*2C/256), B): wqk;  grid.z == 1 slice handles wft
+// k4: wqk[b] (softmax / cosine / normalisation backward as a 2C x 2C matrix).  grid (ceil(2C*2C/256), B)
 template <class T>
-__global__ void __launch_bounds__(256) mdta_bwd_weights_kernel(const MbArgs a, unsigned short* __restrict__ wqk, int kpad2,
-                                                               unsigned short* __restrict__ wft, int kpad1) {
+__global__ void __launch_bounds__(256) mdta_bwd_weights_kernel(const MbArgs a, unsigned short* __restrict__ wqk, int kpad2) {
   const int b = blockIdx.y;
   const int C = a.C, c = a.c;
   const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
   const float* nrm = a.nrm + (size_t)b * 2 * C;
-  if (blockIdx.z == 0) {
+  {
     if (e >= (long long)4 * C * C) return;
     const int n = (int)(e / (2 * C)), k = (int)(e % (2 * C));
     float v = 0.f;
@@ -527,33 +611,9 @@ __global__ void __launch_bounds__(256) mdta_bwd_weights_kernel(const MbArgs a, u
       else if (k == n) v = -a.rk[(size_t)b * C + jg];
     }
     wqk[((size_t)b * 2 * C + n) * kpad2 + k] = to16<T>(v);
-  } else {
-    if (e >= (long long)C * C) return;
-    const int jg = (int)(e / C), o = (int)(e % C);        // wft[b][jg][o] = sum_i Wo[o][h*c + i] A[b,h][i][j]
-    const int h = jg / c, j = jg - h * c;
-    const float* A = a.attn + (size_t)(b * a.heads + h) * c * c + j;
-    const float* w = a.wo + (size_t)o * C + h * c;
-    float s = 0.f;
-    for (int i = 0; i < c; ++i) s = fmaf(__ldg(w + i), A[(size_t)i * c], s);
-    wft[((size_t)b * C + jg) * kpad1 + o] = to16<T>(s);
   }
 }
 
-// k5a: per-image dWoP[b][o][h*c + i] = sum_j dWf[b][o][h*c + j] A[b,h][i][j].  grid (ceil(C*C/256), B)
-__global__ void __launch_bounds__(256) mdta_bwd_dwo_part_kernel(const MbArgs a) {
-  const int e = blockIdx.x * 256 + threadIdx.x;
-  const int b = blockIdx.y;
-  if (e >= a.C * a.C) return;
-  const int o = e / a.C, ch = e % a.C;
-  const int h = ch / a.c, i = ch - h * a.c;
-  const float* d = a.dWf + ((size_t)b * a.C + o) * a.C + h * a.c;
-  const float* A = a.attn + ((size_t)(b * a.heads + h) * a.c + i) * a.c;
-  float t0 = 0.f, t1 = 0.f;
-  int j = 0;
-  for (; j + 2 <= a.c; j += 2) { t0 = fmaf(d[j], A[j], t0); t1 = fmaf(d[j + 1], A[j + 1], t1); }
-  if (j < a.c) t0 = fmaf(d[j], A[j], t0);
-  a.dWoP[(size_t)b * a.C * a.C + e] = t0 + t1;
-}
 // k5b: dWo = inv * sum_b dWoP[b]
 __global__ void __launch_bounds__(256) mdta_bwd_dwo_kernel(const MbArgs a) {
   const int e = blockIdx.x * 256 + threadIdx.x;
@@ -786,12 +846,55 @@ extern "C" int pir_nchw32_to_nhwc16(const PirToNhwc16* d, void* stream) {
   return pir_check_launch("pir_nchw32_to_nhwc16");
 }
 
+static void dww_plan(int B, int H, int W, int C, int* tiles_x, int* tiles_y, int* n_sp, int* chunks, int* workers) {
+  constexpr int TH = 8;
+  *tiles_x = (W + 31) / 32;
+  *tiles_y = (H + TH - 1) / TH;
+  *n_sp = *tiles_x * *tiles_y * B;
+  *chunks = (C + 63) / 64;
+  int w = (148 + *chunks - 1) / *chunks;            // one CTA per SM (the double buffer fills shared memory)
+  if (w > *n_sp) w = *n_sp;
+  *workers = w < 1 ? 1 : w;
+}
+
 extern "C" int pir_dw_wgrad_parts(int32_t B, int32_t H, int32_t W, int32_t C) {
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0) return 1;
-  const int cgroups = (C + 63) / 64;
-  int parts = (148 * 4 + cgroups - 1) / cgroups;
-  if (parts > B * H) parts = B * H;
-  return parts < 1 ? 1 : parts;
+  int tx, ty, n_sp, chunks, workers;
+  dww_plan(B, H, W, C, &tx, &ty, &n_sp, &chunks, &workers);
+  return workers;
+}
+
+template <class T>
+static int launch_dw_wgrad(const PirDwWgrad* d, cudaStream_t s) {
+  constexpr int TH = 8;
+  DwwArgs a{};
+  int chunks, workers;
+  dww_plan(d->B, d->H, d->W, d->C, &a.tiles_x, &a.tiles_y, &a.n_sp, &chunks, &workers);
+  if (workers != d->parts) return pir_fail(PIR_ERR_ARG, "pir_dw_wgrad: parts must be pir_dw_wgrad_parts(B, H, W, C) = %d", workers);
+  a.H = d->H; a.W = d->W; a.C = d->C; a.ws = d->ws;
+  const CUtensorMapDataType dt = T::kFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+  CUtensorMap tmX, tmD;
+  {
+    const uint64_t strides[3] = {(uint64_t)d->x_pitch * 2, (uint64_t)d->x_pitch * 2 * d->W, (uint64_t)d->x_bstride * 2};
+    const uint32_t box[4] = {64, 34, TH + 2, 1};
+    if (int e = pir_make_tmap(&tmX, dt, 4, d->x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+  }
+  {
+    const uint64_t strides[3] = {(uint64_t)d->dy_pitch * 2, (uint64_t)d->dy_pitch * 2 * d->W, (uint64_t)d->dy_bstride * 2};
+    const uint32_t box[4] = {64, 32, TH, 1};
+    if (int e = pir_make_tmap(&tmD, dt, 4, d->dy, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+  }
+  const size_t smem = (size_t)2 * ((TH + 2) * 34 + TH * 32) * 128 + 128;
+  static bool set[2] = {false, false};
+  if (!set[T::kFmt]) {
+    if (cudaFuncSetAttribute(dw_wgrad_kernel<T, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return pir_fail(PIR_ERR_CUDA, "pir_dw_wgrad: cannot raise dynamic shared memory limit");
+    set[T::kFmt] = true;
+  }
+  dim3 grid((unsigned)workers, (unsigned)chunks);
+  dw_wgrad_kernel<T, TH><<<grid, 256, smem, s>>>(tmX, tmD, a);
+  return pir_check_launch("pir_dw_wgrad");
 }
 
 extern "C" int pir_dw_wgrad(const PirDwWgrad* d, void* stream) {
@@ -802,12 +905,7 @@ extern "C" int pir_dw_wgrad(const PirDwWgrad* d, void* stream) {
     return pir_fail(PIR_ERR_ARG, "pir_dw_wgrad: tensors missing or not 16-byte aligned");
   if ((d->R > d->half ? d->R - d->half + d->half_pad : d->R) > d->C) return pir_fail(PIR_ERR_ARG, "pir_dw_wgrad: parameter larger than the tensor");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  dim3 grid((unsigned)d->parts, (unsigned)((d->C + 63) / 64));
-  auto* x = reinterpret_cast<const unsigned short*>(d->x);
-  auto* dy = reinterpret_cast<const unsigned short*>(d->dy);
-  PIR_BY_DTYPE(d->dtype, (dw_wgrad_kernel<BF16><<<grid, 256, 0, s>>>(x, d->x_pitch, d->x_bstride, dy, d->dy_pitch, d->dy_bstride, d->B, d->H, d->W, d->C, d->ws)),
-               (dw_wgrad_kernel<FP16><<<grid, 256, 0, s>>>(x, d->x_pitch, d->x_bstride, dy, d->dy_pitch, d->dy_bstride, d->B, d->H, d->W, d->C, d->ws)));
-  if (int e = pir_check_launch("pir_dw_wgrad")) return e;
+  if (int e = d->dtype == PIR_DTYPE_BF16 ? launch_dw_wgrad<BF16>(d, s) : launch_dw_wgrad<FP16>(d, s)) return e;
   dw_wgrad_fin_kernel<<<(unsigned)((d->R * 10 + 255) / 256), 256, 0, s>>>(d->ws, d->parts, d->C, d->R, d->half, d->half_pad, d->inv_scale, d->dst_w,
                                                                          d->dst_bias);
   return pir_check_launch("pir_dw_wgrad(finalize)");
@@ -845,20 +943,50 @@ extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
   a.dTp = p; p += (size_t)B * C;
   a.dWoP = p;
   a.dst_wo = d->dst_wo; a.dst_temp = d->dst_temp; a.dst_bias = d->dst_bias;
+  const bool bf = d->dtype == PIR_DTYPE_BF16;
+  const int kpad1 = (C + 63) / 64 * 64, kpad2 = (2 * C + 63) / 64 * 64;
+  const int heads = d->heads;
+  auto sgemm = [&](const SgArgs& g) {
+    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, B * heads);
+    if (bf) sgemm_strided_kernel<BF16><<<grid, 256, 0, s>>>(g); else sgemm_strided_kernel<FP16><<<grid, 256, 0, s>>>(g);
+  };
   mdta_bwd_reduce_kernel<<<dim3((C * C + 255) / 256, B), 256, 0, s>>>(a);
   if (int e = pir_check_launch("pir_mdta_bwd(reduce)")) return e;
+  {   // dA_h[i][j] = sum_o Wo[o][hc+i] dWf[b][o][hc+j]  -> dcos buffer
+    SgArgs g{};
+    g.M = c; g.N = c; g.K = C; g.heads = heads;
+    g.A = d->wo; g.a_sm = 1; g.a_sk = C; g.a_sb = 0; g.a_sh = c;
+    g.B = a.dWf; g.b_sk = C; g.b_sn = 1; g.b_sb = (long long)C * C; g.b_sh = c;
+    g.out = a.dcos; g.o_sm = c; g.o_sn = 1; g.o_sb = (long long)C * c; g.o_sh = (long long)c * c;
+    sgemm(g);
+    if (int e = pir_check_launch("pir_mdta_bwd(dA)")) return e;
+  }
   mdta_bwd_rows_kernel<<<dim3((C + 7) / 8, B), 256, 0, s>>>(a);
   if (int e = pir_check_launch("pir_mdta_bwd(rows)")) return e;
   mdta_bwd_cols_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(a);
   if (int e = pir_check_launch("pir_mdta_bwd(cols)")) return e;
-  const int kpad1 = (C + 63) / 64 * 64, kpad2 = (2 * C + 63) / 64 * 64;
-  dim3 gw((4 * C * C + 255) / 256, B, 2);
-  PIR_BY_DTYPE(d->dtype,
-               (mdta_bwd_weights_kernel<BF16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2, reinterpret_cast<unsigned short*>(d->wft), kpad1)),
-               (mdta_bwd_weights_kernel<FP16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2, reinterpret_cast<unsigned short*>(d->wft), kpad1)));
+  dim3 gw((4 * C * C + 255) / 256, B);
+  if (bf) mdta_bwd_weights_kernel<BF16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2);
+  else mdta_bwd_weights_kernel<FP16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2);
   if (int e = pir_check_launch("pir_mdta_bwd(weights)")) return e;
-  mdta_bwd_dwo_part_kernel<<<dim3((C * C + 255) / 256, B), 256, 0, s>>>(a);
-  if (int e = pir_check_launch("pir_mdta_bwd(dwo part)")) return e;
+  {   // wft[b][hc+j][o] = sum_i A[b,h][i][j] Wo[o][hc+i]
+    SgArgs g{};
+    g.M = c; g.N = C; g.K = c; g.heads = heads;
+    g.A = a.attn; g.a_sm = 1; g.a_sk = c; g.a_sb = (long long)heads * c * c; g.a_sh = (long long)c * c;
+    g.B = d->wo; g.b_sk = 1; g.b_sn = C; g.b_sb = 0; g.b_sh = c;
+    g.out16 = reinterpret_cast<unsigned short*>(d->wft); g.o_sm = kpad1; g.o_sn = 1; g.o_sb = (long long)C * kpad1; g.o_sh = (long long)c * kpad1;
+    sgemm(g);
+    if (int e = pir_check_launch("pir_mdta_bwd(fold)")) return e;
+  }
+  {   // dWoP[b][o][hc+i] = sum_j dWf[b][o][hc+j] A[b,h][i][j]
+    SgArgs g{};
+    g.M = C; g.N = c; g.K = c; g.heads = heads;
+    g.A = a.dWf; g.a_sm = C; g.a_sk = 1; g.a_sb = (long long)C * C; g.a_sh = c;
+    g.B = a.attn; g.b_sk = 1; g.b_sn = c; g.b_sb = (long long)heads * c * c; g.b_sh = (long long)c * c;
+    g.out = a.dWoP; g.o_sm = C; g.o_sn = 1; g.o_sb = (long long)C * C; g.o_sh = c;
+    sgemm(g);
+    if (int e = pir_check_launch("pir_mdta_bwd(dwo part)")) return e;
+  }
   mdta_bwd_dwo_kernel<<<(C * C + 255) / 256, 256, 0, s>>>(a);
   if (int e = pir_check_launch("pir_mdta_bwd(dwo)")) return e;
   mdta_bwd_small_kernel<<<1 + (d->dst_bias ? (C + 255) / 256 : 0), 256, 0, s>>>(a);
