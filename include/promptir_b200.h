@@ -138,6 +138,7 @@ typedef struct PirPrompt {
   const float* prompt; const float* lin_w; const float* lin_b;
   void* out; int64_t out_pitch, out_bstride;
   float* ws; float* weights_out;
+  int32_t align_corners;    /* bilinear rule: 0 = net/model.py:231 (PromptGenBlock), 1 = prompt_xrestormer.py:350 (PromptBlock)  */
 } PirPrompt;
 int64_t pir_prompt_ws_floats(int32_t B, int32_t HW, int32_t C);
 int pir_prompt_gen(const PirPrompt* d, void* stream);
@@ -304,6 +305,23 @@ typedef struct PirToNhwc16 {
   float scale;
 } PirToNhwc16;
 int pir_nchw32_to_nhwc16(const PirToNhwc16* d, void* stream);
+
+/* ---- OCAB: overlapping cross-attention of PromptXRestormer (net/prompt_xrestormer.py:189-235, RelPosEmb :25-73) -----------
+ * qkv: NHWC 16-bit [B,H,W,3*inner] from the 1x1 qkv conv (inner = heads*dim_head; q = [0,inner), k = [inner,2 inner), v = rest;
+ * head h = channels [h*dim_head, (h+1)*dim_head)).  For every ws x ws query window and head:
+ *   out = softmax( qs.k^T + qs.rel_w[kc - y + ows - 1] + qs.rel_h[kr - x + ows - 1] ) . v,    qs = q * dim_head^-0.5
+ * over the ows x ows key window centred on it; keys outside the image are ZERO vectors that still take part in the softmax
+ * (nn.Unfold padding).  rel_h / rel_w: fp32 [2*ows - 1][dim_head].  out: NHWC 16-bit [B,H,W,inner] (project_out follows as a
+ * pir_gemm).  Built for ws = 8, ows = 12, dim_head = 16 (the only values the reference constructs).                           */
+typedef struct PirOcab {
+  int32_t dtype;
+  int32_t B, H, W;
+  int32_t heads, dim_head, ws, ows;
+  const void* qkv; int64_t qkv_pitch, qkv_bstride;
+  const float* rel_h; const float* rel_w;
+  void* out; int64_t out_pitch, out_bstride;
+} PirOcab;
+int pir_ocab(const PirOcab* d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,7 +54,14 @@ class PirPrompt(C.Structure):
                 ("x", vp), ("x_pitch", i64), ("x_bstride", i64),
                 ("prompt", vp), ("lin_w", vp), ("lin_b", vp),
                 ("out", vp), ("out_pitch", i64), ("out_bstride", i64),
-                ("ws", vp), ("weights_out", vp)]
+                ("ws", vp), ("weights_out", vp), ("align_corners", i32)]
+
+
+class PirOcab(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("heads", i32), ("dim_head", i32), ("ws", i32), ("ows", i32),
+                ("qkv", vp), ("qkv_pitch", i64), ("qkv_bstride", i64),
+                ("rel_h", vp), ("rel_w", vp),
+                ("out", vp), ("out_pitch", i64), ("out_bstride", i64)]
 
 
 class PirPatchEmbed(C.Structure):
@@ -166,6 +173,7 @@ SYMBOLS = {
     "pir_prompt_bwd": (i32, [C.POINTER(PirPromptBwd), vp]),
     "pir_bcast_add": (i32, [C.POINTER(PirBcastAdd), vp]),
     "pir_nchw32_to_nhwc16": (i32, [C.POINTER(PirToNhwc16), vp]),
+    "pir_ocab": (i32, [C.POINTER(PirOcab), vp]),
 }
 
 _lib = None

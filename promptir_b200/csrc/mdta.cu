@@ -269,6 +269,7 @@ __device__ __forceinline__ float sum_splits(const float* p, size_t stride, int s
   return (s0 + s1) + (s2 + s3);
 }
 
+template <int NT>
 __global__ void __launch_bounds__(256)
 mdta_softmax_kernel(const float* __restrict__ ws_gram, const float* __restrict__ ws_norm, const float* __restrict__ temperature,
                     float* __restrict__ attn, int C, int heads, int splits) {
@@ -282,11 +283,11 @@ mdta_softmax_kernel(const float* __restrict__ ws_gram, const float* __restrict__
   const float* nbase = ws_norm + (size_t)b * splits * 2 * C;                   // + sp * 2 * C
   const float qn = fmaxf(sqrtf(sum_splits(nbase + r, (size_t)2 * C, splits)), 1e-12f);   // F.normalize: x / max(||x||, eps)
   const float temp = temperature[h];
-  // c <= 256 supported: up to 8 columns per lane
-  float v[8];
+  // c <= 32 * NT: up to NT columns per lane (NT = 8 for the usual 48-wide heads, 24 for the single-head prompt blocks)
+  float v[NT];
   float mx = -INFINITY;
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
+  for (int t = 0; t < NT; ++t) {
     const int j = lane + t * 32;
     v[t] = -INFINITY;
     if (j < c) {
@@ -300,7 +301,7 @@ mdta_softmax_kernel(const float* __restrict__ ws_gram, const float* __restrict__
   for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sum = 0.f;
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
+  for (int t = 0; t < NT; ++t) {
     const int j = lane + t * 32;
     if (j < c) { v[t] = expf(v[t] - mx); sum += v[t]; }
   }
@@ -309,7 +310,7 @@ mdta_softmax_kernel(const float* __restrict__ ws_gram, const float* __restrict__
   const float inv = 1.0f / sum;
   float* arow = attn + ((size_t)(b * heads + h) * c + i) * c;
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
+  for (int t = 0; t < NT; ++t) {
     const int j = lane + t * 32;
     if (j < c) arow[j] = v[t] * inv;
   }
@@ -401,7 +402,7 @@ static int check_mdta(const PirMdta* d, const char* who) {
   if (!d) return pir_fail(PIR_ERR_ARG, "%s: null descriptor", who);
   if (d->B <= 0 || d->HW <= 0 || d->C <= 0 || d->heads <= 0 || d->splits <= 0) return pir_fail(PIR_ERR_ARG, "%s: empty problem", who);
   if (d->C % d->heads) return pir_fail(PIR_ERR_ARG, "%s: C must be divisible by heads", who);
-  if (d->C / d->heads > 256) return pir_fail(PIR_ERR_UNSUPPORTED, "%s: head dim > 256", who);
+  if (d->C / d->heads > 768) return pir_fail(PIR_ERR_UNSUPPORTED, "%s: head dim > 768", who);
   if ((d->C % 8) || (d->qkv_pitch % 8) || (d->qkv_bstride % 8) || ((uintptr_t)d->qkv & 15)) return pir_fail(PIR_ERR_ARG, "%s: qkv not 16-byte aligned", who);
   if (!d->ws) return pir_fail(PIR_ERR_ARG, "%s: workspace missing", who);
   return PIR_OK;
@@ -445,7 +446,8 @@ extern "C" int pir_mdta_finalize(const PirMdta* d, void* stream) {
   const float* ws_gram = d->ws;
   const float* ws_norm = d->ws + (size_t)d->B * d->splits * d->C * c;
   float* attn = d->ws + (size_t)d->B * d->splits * ((size_t)d->C * c + 2 * d->C);
-  pir::mdta_softmax_kernel<<<dim3((d->C + 7) / 8, d->B), 256, 0, s>>>(ws_gram, ws_norm, d->temperature, attn, d->C, d->heads, d->splits);
+  if (c <= 256) pir::mdta_softmax_kernel<8><<<dim3((d->C + 7) / 8, d->B), 256, 0, s>>>(ws_gram, ws_norm, d->temperature, attn, d->C, d->heads, d->splits);
+  else pir::mdta_softmax_kernel<24><<<dim3((d->C + 7) / 8, d->B), 256, 0, s>>>(ws_gram, ws_norm, d->temperature, attn, d->C, d->heads, d->splits);
   if (int e = pir_check_launch("pir_mdta_finalize(softmax)")) return e;
   const int kpad = (d->C + 63) / 64 * 64;
   dim3 grid((d->C + 31) / 32, d->heads * ((c + 31) / 32), d->B);

@@ -1,0 +1,159 @@
+// OCAB -- overlapping cross-attention of PromptXRestormer for sm_100a.    Reference: net/prompt_xrestormer.py:189-235 (OCAB),
+// :25-73 (RelPosEmb: rel_to_abs / relative_logits_1d).
+//
+// One CTA per (8 x 8 query window, head): 64 queries x 144 keys x 16 channels.  The reference materialises the 12 x 12 key/value
+// windows with nn.Unfold (2.25x the k/v tensors) and runs two bmm + ~10 elementwise kernels; here the window is gathered straight
+// from the NHWC qkv tensor into shared memory (zero vectors outside the image, exactly what Unfold's zero padding produces --
+// such keys still enter the softmax with logit = relative-position bias) and the whole head is finished in registers:
+//   thread = (query i, part s in 0..3) owns keys j = s + 4t, t = 0..35, i.e. key row a = t / 3 and key column s + 4 (t % 3)
+//   logit  = qs.k_j + qs.rel_w[kc - y + 11] + qs.rel_h[kr - x + 11]           (rel_to_abs reduces to this index shift)
+//   softmax over the 4 x 36 logits of the query (two shuffle steps), out = sum p_j v_j reduced the same way.
+// The relative-position terms need only 3 + 12 dot products per thread.  HBM traffic is the algorithmic minimum plus the 2.25x key
+// halo, which stays in L2.
+#include "common.cuh"
+#include "host.h"
+
+namespace pir {
+
+constexpr int kOcWs = 8, kOcOws = 12, kOcDh = 16, kOcKeys = kOcOws * kOcOws, kOcRel = 2 * kOcOws - 1;
+constexpr int kOcRow = 20;                 // shared-memory row stride in floats: 80 B keeps float4 reads of 4 consecutive rows conflict free
+
+struct OcArgs {
+  int H, W, heads, inner;
+  const unsigned short* qkv; long long qpitch, qbs;
+  const float* rel_h; const float* rel_w;
+  unsigned short* out; long long opitch, obs;
+};
+
+template <class T>
+__device__ __forceinline__ void load16(const unsigned short* p, float (&f)[16]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { f[2 * q] = unpack_lo<T>(w[q]); f[2 * q + 1] = unpack_hi<T>(w[q]); }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+ocab_kernel(const OcArgs a) {
+  __shared__ __align__(16) float sK[kOcKeys][kOcRow];
+  __shared__ __align__(16) float sV[kOcKeys][kOcRow];
+  __shared__ __align__(16) float sRw[kOcRel][kOcDh];
+  __shared__ __align__(16) float sRh[kOcRel][kOcDh];
+  const int tid = threadIdx.x;
+  const int nw = a.W / kOcWs;
+  const int wy = blockIdx.x / nw, wx = blockIdx.x % nw;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const unsigned short* base = a.qkv + (size_t)b * a.qbs;
+
+  // ---- gather the 12 x 12 key / value window of this head (zero outside the image) ----
+  for (int e = tid; e < kOcKeys * 4; e += 256) {
+    const int j = e >> 2, which = (e >> 1) & 1, half = e & 1;
+    const int py = wy * kOcWs - (kOcOws - kOcWs) / 2 + j / kOcOws, px = wx * kOcWs - (kOcOws - kOcWs) / 2 + j % kOcOws;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (py >= 0 && py < a.H && px >= 0 && px < a.W)
+      v = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)py * a.W + px) * a.qpitch + (size_t)(1 + which) * a.inner + h * kOcDh + half * 8));
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    float* dst = (which ? sV[j] : sK[j]) + half * 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { dst[2 * q] = unpack_lo<T>(w4[q]); dst[2 * q + 1] = unpack_hi<T>(w4[q]); }
+  }
+  for (int e = tid; e < kOcRel * kOcDh; e += 256) {
+    sRw[e / kOcDh][e % kOcDh] = __ldg(a.rel_w + e);
+    sRh[e / kOcDh][e % kOcDh] = __ldg(a.rel_h + e);
+  }
+  // ---- this thread's query ----
+  const int i = tid >> 2, s = tid & 3;
+  const int x = i >> 3, y = i & 7;                      // row / column inside the window
+  const size_t qpix = (size_t)(wy * kOcWs + x) * a.W + wx * kOcWs + y;
+  float qs[16];
+  load16<T>(base + qpix * a.qpitch + h * kOcDh, qs);
+#pragma unroll
+  for (int d = 0; d < 16; ++d) qs[d] *= 0.25f;           // dim_head^-0.5
+  __syncthreads();
+
+  auto dot16 = [&](const float* r) {
+    const float4 r0 = *reinterpret_cast<const float4*>(r), r1 = *reinterpret_cast<const float4*>(r + 4);
+    const float4 r2 = *reinterpret_cast<const float4*>(r + 8), r3 = *reinterpret_cast<const float4*>(r + 12);
+    float t0 = qs[0] * r0.x, t1 = qs[1] * r0.y, t2 = qs[2] * r0.z, t3 = qs[3] * r0.w;
+    t0 = fmaf(qs[4], r1.x, t0); t1 = fmaf(qs[5], r1.y, t1); t2 = fmaf(qs[6], r1.z, t2); t3 = fmaf(qs[7], r1.w, t3);
+    t0 = fmaf(qs[8], r2.x, t0); t1 = fmaf(qs[9], r2.y, t1); t2 = fmaf(qs[10], r2.z, t2); t3 = fmaf(qs[11], r2.w, t3);
+    t0 = fmaf(qs[12], r3.x, t0); t1 = fmaf(qs[13], r3.y, t1); t2 = fmaf(qs[14], r3.z, t2); t3 = fmaf(qs[15], r3.w, t3);
+    return (t0 + t1) + (t2 + t3);
+  };
+  float tw[3], th[12];
+#pragma unroll
+  for (int bb = 0; bb < 3; ++bb) tw[bb] = dot16(sRw[s + 4 * bb - y + kOcOws - 1]);
+#pragma unroll
+  for (int aa = 0; aa < 12; ++aa) th[aa] = dot16(sRh[aa - x + kOcOws - 1]);
+
+  float lg[36];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < 36; ++t) {
+    const int j = s + 4 * t;                            // key row t / 3, key column s + 4 (t % 3)
+    lg[t] = dot16(sK[j]) + tw[t % 3] + th[t / 3];
+    mx = fmaxf(mx, lg[t]);
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 36; ++t) { lg[t] = exp2f((lg[t] - mx) * 1.4426950408889634f); sum += lg[t]; }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  float o[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 36; ++t) {
+    const float* r = sV[s + 4 * t];
+    const float p = lg[t];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const float4 v = *reinterpret_cast<const float4*>(r + 4 * q4);
+      o[4 * q4] = fmaf(p, v.x, o[4 * q4]); o[4 * q4 + 1] = fmaf(p, v.y, o[4 * q4 + 1]);
+      o[4 * q4 + 2] = fmaf(p, v.z, o[4 * q4 + 2]); o[4 * q4 + 3] = fmaf(p, v.w, o[4 * q4 + 3]);
+    }
+  }
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    o[d] += __shfl_xor_sync(0xffffffffu, o[d], 1);
+    o[d] += __shfl_xor_sync(0xffffffffu, o[d], 2);
+    o[d] *= inv;
+  }
+  // part s stores channels [4s, 4s + 4) of the head (8 bytes): the four parts of a query write one 32-byte run
+  float c4[4];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) c4[d] = s == 0 ? o[d] : (s == 1 ? o[4 + d] : (s == 2 ? o[8 + d] : o[12 + d]));
+  uint2 pk;
+  pk.x = pack2<T>(c4[0], c4[1]);
+  pk.y = pack2<T>(c4[2], c4[3]);
+  *reinterpret_cast<uint2*>(a.out + (size_t)b * a.obs + qpix * a.opitch + h * kOcDh + 4 * s) = pk;
+}
+
+}  // namespace pir
+
+extern "C" int pir_ocab(const PirOcab* d, void* stream) {
+  using namespace pir;
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_ocab: null descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->heads <= 0) return pir_fail(PIR_ERR_ARG, "pir_ocab: empty problem");
+  if (d->ws != kOcWs || d->ows != kOcOws || d->dim_head != kOcDh)
+    return pir_fail(PIR_ERR_UNSUPPORTED, "pir_ocab: built for window 8, overlapping window 12, head dim 16 (got %d, %d, %d)", d->ws, d->ows, d->dim_head);
+  if ((d->H % kOcWs) || (d->W % kOcWs)) return pir_fail(PIR_ERR_ARG, "pir_ocab: H and W must be multiples of the window size");
+  if ((d->qkv_pitch % 8) || (d->qkv_bstride % 8) || (d->out_pitch % 4) || (d->out_bstride % 4) || ((uintptr_t)d->qkv & 15) || ((uintptr_t)d->out & 7) ||
+      !d->qkv || !d->out || !d->rel_h || !d->rel_w)
+    return pir_fail(PIR_ERR_ARG, "pir_ocab: tensors missing or not vector aligned");
+  if (d->heads > 65535 || d->B > 65535) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_ocab: grid too large");
+  OcArgs a{};
+  a.H = d->H; a.W = d->W; a.heads = d->heads; a.inner = d->heads * kOcDh;
+  a.qkv = reinterpret_cast<const unsigned short*>(d->qkv); a.qpitch = d->qkv_pitch; a.qbs = d->qkv_bstride;
+  a.rel_h = d->rel_h; a.rel_w = d->rel_w;
+  a.out = reinterpret_cast<unsigned short*>(d->out); a.opitch = d->out_pitch; a.obs = d->out_bstride;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)((d->H / kOcWs) * (d->W / kOcWs)), (unsigned)d->heads, (unsigned)d->B);
+  if (d->dtype == PIR_DTYPE_BF16) ocab_kernel<BF16><<<grid, 256, 0, s>>>(a);
+  else ocab_kernel<FP16><<<grid, 256, 0, s>>>(a);
+  return pir_check_launch("pir_ocab");
+}

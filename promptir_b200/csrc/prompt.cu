@@ -52,7 +52,7 @@ template <class T>
 __global__ void __launch_bounds__(256)
 prompt_mix_kernel(const float* __restrict__ partial, int nchunks, int HW, int C, const float* __restrict__ lin_w,
                   const float* __restrict__ lin_b, int L, const float* __restrict__ prompt, int D, int S, int H, int W,
-                  unsigned short* __restrict__ out, long long pitch, long long bstride, float* __restrict__ weights_out) {
+                  unsigned short* __restrict__ out, long long pitch, long long bstride, float* __restrict__ weights_out, int align) {
   extern __shared__ float semb[];            // [C]
   __shared__ float slog[kMaxL];
   const int b = blockIdx.y;
@@ -84,12 +84,15 @@ prompt_mix_kernel(const float* __restrict__ partial, int nchunks, int HW, int C,
 
   const int groups = D >> 3;
   const long long total = (long long)H * W * groups;
-  const float sh = (float)S / (float)H, sw = (float)S / (float)W;
+  // align_corners = False: src = scale * (dst + 0.5) - 0.5, scale = S / H;  True: src = dst * (S - 1) / (H - 1)   (ATen upsample_bilinear2d)
+  const float sh = align ? (H > 1 ? (float)(S - 1) / (float)(H - 1) : 0.f) : (float)S / (float)H;
+  const float sw = align ? (W > 1 ? (float)(S - 1) / (float)(W - 1) : 0.f) : (float)S / (float)W;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int dg = (int)(e % groups);
     const int p = (int)(e / groups);
     const int y = p / W, x = p % W;
-    float fy = fmaxf(sh * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * ((float)x + 0.5f) - 0.5f, 0.f);
+    float fy = align ? sh * (float)y : fmaxf(sh * ((float)y + 0.5f) - 0.5f, 0.f);
+    float fx = align ? sw * (float)x : fmaxf(sw * ((float)x + 0.5f) - 0.5f, 0.f);
     const int y0 = min((int)fy, S - 1), x0 = min((int)fx, S - 1);
     const int y1 = y0 + (y0 < S - 1 ? 1 : 0), x1 = x0 + (x0 < S - 1 ? 1 : 0);
     const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
@@ -144,7 +147,7 @@ static int launch_prompt(const PirPrompt* d, cudaStream_t s) {
   if (blocks > cap) blocks = cap;
   prompt_mix_kernel<T><<<dim3(blocks, d->B), 256, d->C * sizeof(float), s>>>(
       d->ws, nchunks, HW, d->C, d->lin_w, d->lin_b, d->L, d->prompt, d->D, d->S, d->H, d->W,
-      reinterpret_cast<unsigned short*>(d->out), d->out_pitch, d->out_bstride, d->weights_out);
+      reinterpret_cast<unsigned short*>(d->out), d->out_pitch, d->out_bstride, d->weights_out, d->align_corners);
   return pir_check_launch("pir_prompt_gen(mix)");
 }
 

@@ -157,7 +157,7 @@ def prompt_ws_floats(B: int, HW: int, Cdim: int) -> int:
 
 
 def prompt_gen(x: torch.Tensor, prompt: torch.Tensor, lin_w: torch.Tensor, lin_b: torch.Tensor, out: torch.Tensor,
-               ws: torch.Tensor, weights_out: Optional[torch.Tensor] = None) -> Launch:
+               ws: torch.Tensor, weights_out: Optional[torch.Tensor] = None, align_corners: bool = False) -> Launch:
     """prompt: fp32 [L, S, S, D] (components, channels last)."""
     px, B, H, W, Cdim, xp, xbs = _nhwc(x, "prompt.x")
     po, oB, oH, oW, D, op, obs = _nhwc(out, "prompt.out")
@@ -172,6 +172,7 @@ def prompt_gen(x: torch.Tensor, prompt: torch.Tensor, lin_w: torch.Tensor, lin_b
     d.prompt, d.lin_w, d.lin_b = prompt.data_ptr(), lin_w.data_ptr(), lin_b.data_ptr()
     d.out, d.out_pitch, d.out_bstride = po, op, obs
     d.ws, d.weights_out = ws.data_ptr(), _ptr(weights_out)
+    d.align_corners = int(align_corners)
     return _prepared("pir_prompt_gen", d, (x, prompt, lin_w, lin_b, out, ws, weights_out), kernels=2)
 
 
@@ -405,3 +406,20 @@ def nchw32_to_nhwc16(src: torch.Tensor, out: torch.Tensor, scale: float) -> Laun
     d.out, d.out_pitch, d.out_bstride = po, op, obs
     d.scale = scale
     return _prepared("pir_nchw32_to_nhwc16", d, (src, out))
+
+
+def ocab(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, out: torch.Tensor, *, heads: int, dim_head: int = 16, ws: int = 8,
+         ows: int = 12) -> Launch:
+    """Overlapping cross-attention core (pir_ocab): qkv NHWC [B,H,W,3*heads*dim_head] -> out NHWC [B,H,W,heads*dim_head]."""
+    pq, B, H, W, C3, qp, qbs = _nhwc(qkv, "ocab.qkv")
+    po, oB, oH, oW, oC, op, obs = _nhwc(out, "ocab.out")
+    inner = heads * dim_head
+    assert C3 == 3 * inner and (oB, oH, oW, oC) == (B, H, W, inner) and out.dtype == qkv.dtype
+    assert tuple(rel_h.shape) == tuple(rel_w.shape) == (2 * ows - 1, dim_head)
+    d = _lib.PirOcab()
+    d.dtype = dtype_code(qkv.dtype)
+    d.B, d.H, d.W, d.heads, d.dim_head, d.ws, d.ows = B, H, W, heads, dim_head, ws, ows
+    d.qkv, d.qkv_pitch, d.qkv_bstride = pq, qp, qbs
+    d.rel_h, d.rel_w = _f32ptr(rel_h, "ocab.rel_h"), _f32ptr(rel_w, "ocab.rel_w")
+    d.out, d.out_pitch, d.out_bstride = po, op, obs
+    return _prepared("pir_ocab", d, (qkv, rel_h, rel_w, out))

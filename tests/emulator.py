@@ -111,7 +111,7 @@ def emu_prompt(r):
     emb = x.float().mean(dim=(1, 2))
     wts = torch.softmax(emb @ lw.t() + lb, dim=1)
     mix = torch.einsum("bl,lstd->bdst", wts, prm)
-    out.copy_(_nhwc(F.interpolate(mix, (H, W), mode="bilinear")).to(out.dtype))
+    out.copy_(_nhwc(F.interpolate(mix, (H, W), mode="bilinear", align_corners=bool(r.get("align_corners", False)))).to(out.dtype))
 
 
 def emu_patch_embed(r):
@@ -341,3 +341,15 @@ def run_train(engine, img, d_out):
     for r in engine.bwd_ops:
         DISPATCH[r["kind"]](r)
     return out, {k: v.clone() for k, v in engine.grads.items()}
+
+
+def emu_ocab(r):
+    """pir_ocab: the attention core of prompt_xrestormer.py:215-232 on the NHWC qkv tensor."""
+    from oracle.xrestormer_oracle import ocab_core
+    qkv, out = r["qkv"], r["out"]
+    q, k, v = _nchw(qkv).chunk(3, dim=1)
+    o = ocab_core(q.contiguous(), k.contiguous(), v.contiguous(), r["rel_h"], r["rel_w"], r["heads"])
+    out.copy_(_nhwc(o).to(out.dtype))
+
+
+DISPATCH["ocab"] = emu_ocab
