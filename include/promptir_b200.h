@@ -323,6 +323,18 @@ typedef struct PirOcab {
 } PirOcab;
 int pir_ocab(const PirOcab* d, void* stream);
 
+/* ---- evaluation I/O on the device (test.py:100-114, utils/val_utils.py:50-66, utils/dataset_utils.py:195-198) ----------------
+ * pir_mirror_pad: out[p][y][x] = in[p][y < H ? y : 2H-1-y][x < W ? x : 2W-1-x] for `planes` = B*C fp32 planes (the reference's
+ *   torch.cat([x, flip(x)])[:Hp] padding); H <= Hp <= 2H.
+ * pir_psnr_ssim: per image, on clip(., 0, 1) fp32 NCHW tensors: out[2b] = skimage peak_signal_noise_ratio(data_range=1),
+ *   out[2b+1] = skimage structural_similarity(win_size=7 uniform, sample covariance, K1=.01, K2=.03, data_range=1, channel mean).
+ *   ws: pir_psnr_ssim_ws_bytes() bytes of scratch.  H, W >= 7.
+ * pir_add_noise: out = floor(clip(clean255 + sigma * N(0,1), 0, 255)) / 255 (clean255 holds 0..255 values); Philox stream (seed, index). */
+int pir_mirror_pad(const float* in, float* out, int32_t planes, int32_t H, int32_t W, int32_t Hp, int32_t Wp, void* stream);
+int64_t pir_psnr_ssim_ws_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
+int pir_psnr_ssim(const float* restored, const float* clean, int32_t B, int32_t C, int32_t H, int32_t W, void* ws, double* out, void* stream);
+int pir_add_noise(const float* clean255, float* out, int64_t n, float sigma, uint64_t seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,6 +174,10 @@ SYMBOLS = {
     "pir_bcast_add": (i32, [C.POINTER(PirBcastAdd), vp]),
     "pir_nchw32_to_nhwc16": (i32, [C.POINTER(PirToNhwc16), vp]),
     "pir_ocab": (i32, [C.POINTER(PirOcab), vp]),
+    "pir_mirror_pad": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "pir_psnr_ssim_ws_bytes": (i64, [i32, i32, i32, i32]),
+    "pir_psnr_ssim": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+    "pir_add_noise": (i32, [vp, vp, i64, f32, C.c_uint64, vp]),
 }
 
 _lib = None
