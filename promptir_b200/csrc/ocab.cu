@@ -10,6 +10,8 @@
 //   softmax over the 4 x 36 logits of the query (two shuffle steps), out = sum p_j v_j reduced the same way.
 // The relative-position terms need only 3 + 12 dot products per thread.  HBM traffic is the algorithmic minimum plus the 2.25x key
 // halo, which stays in L2.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -35,7 +37,7 @@ __device__ __forceinline__ void load16(const unsigned short* p, float (&f)[16]) 
 
 template <class T>
 __global__ void __launch_bounds__(256)
-ocab_kernel(const OcArgs a) {
+ocab_simt_kernel(const OcArgs a) {
   __shared__ __align__(16) float sK[kOcKeys][kOcRow];
   __shared__ __align__(16) float sV[kOcKeys][kOcRow];
   __shared__ __align__(16) float sRw[kOcRel][kOcDh];
@@ -133,6 +135,171 @@ ocab_kernel(const OcArgs a) {
   *reinterpret_cast<uint2*>(a.out + (size_t)b * a.obs + qpix * a.opitch + h * kOcDh + 4 * s) = pk;
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Tensor-core version (default).  One CTA of 4 warps per (window, head); warp w owns queries 16w .. 16w+15 (window rows 2w, 2w+1).
+//   S = Qs K^T      : 18 x mma.m16n8k16 (A = Qs by ldmatrix, B = K rows by ldmatrix), fp32 accumulators stay in registers
+//   + relative bias : Tw[i][r] = qs_i . rel_w[r], Th[i][r] = qs_i . rel_h[r] computed once per query in fp32 (19 + 19 dot products,
+//                     the parameters stay fp32) and looked up per logit
+//   softmax         : on the accumulator fragments, row reductions over the 4 lanes of a quad
+//   O = P V         : P re-used in place as the A fragments (16-bit), V by ldmatrix.trans; 18 x mma
+// The 64 x 144 x 16 products are far too small for a tcgen05 pipeline (one UMMA per product, TMEM round trip in between);
+// warp-level MMA keeps everything in registers.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kOcRowH = 24;                // 16-bit row stride (48 B): ldmatrix rows hit distinct banks
+constexpr int kOcTs = 25;                  // fp32 row stride of the bias tables
+
+template <class T> __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma16816<BF16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <> __device__ __forceinline__ void mma16816<FP16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+template <class T>
+__global__ void __launch_bounds__(128)
+ocab_kernel(const OcArgs a) {
+  __shared__ __align__(16) unsigned short sQ[64][kOcRowH];
+  __shared__ __align__(16) unsigned short sK[kOcKeys][kOcRowH];
+  __shared__ __align__(16) unsigned short sV[kOcKeys][kOcRowH];
+  __shared__ __align__(16) float sRel[2][kOcRel][kOcDh];       // [0] rel_w, [1] rel_h
+  __shared__ float sT[2][64][kOcTs];                           // [0] Tw, [1] Th
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nw = a.W / kOcWs;
+  const int wy = blockIdx.x / nw, wx = blockIdx.x % nw;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const unsigned short* base = a.qkv + (size_t)b * a.qbs;
+
+  // ---- gather: keys / values of the 12 x 12 window (zero outside the image), the 64 queries (scaled by 1/4: exact), rel tables ----
+  for (int e = tid; e < kOcKeys * 4; e += 128) {
+    const int j = e >> 2, which = (e >> 1) & 1, half = e & 1;
+    const int py = wy * kOcWs - (kOcOws - kOcWs) / 2 + j / kOcOws, px = wx * kOcWs - (kOcOws - kOcWs) / 2 + j % kOcOws;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (py >= 0 && py < a.H && px >= 0 && px < a.W)
+      v = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)py * a.W + px) * a.qpitch + (size_t)(1 + which) * a.inner + h * kOcDh + half * 8));
+    *reinterpret_cast<uint4*>((which ? sV[j] : sK[j]) + half * 8) = v;
+  }
+  {
+    const int i = tid >> 1, half = tid & 1;                    // 64 queries x 2 halves = 128 threads
+    const size_t qpix = (size_t)(wy * kOcWs + (i >> 3)) * a.W + wx * kOcWs + (i & 7);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + qpix * a.qpitch + h * kOcDh + half * 8));
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    uint4 o;
+    o.x = pack2<T>(unpack_lo<T>(w4[0]) * 0.25f, unpack_hi<T>(w4[0]) * 0.25f);
+    o.y = pack2<T>(unpack_lo<T>(w4[1]) * 0.25f, unpack_hi<T>(w4[1]) * 0.25f);
+    o.z = pack2<T>(unpack_lo<T>(w4[2]) * 0.25f, unpack_hi<T>(w4[2]) * 0.25f);
+    o.w = pack2<T>(unpack_lo<T>(w4[3]) * 0.25f, unpack_hi<T>(w4[3]) * 0.25f);
+    *reinterpret_cast<uint4*>(sQ[i] + half * 8) = o;
+  }
+  for (int e = tid; e < kOcRel * kOcDh; e += 128) {
+    sRel[0][e / kOcDh][e % kOcDh] = __ldg(a.rel_w + e);
+    sRel[1][e / kOcDh][e % kOcDh] = __ldg(a.rel_h + e);
+  }
+  __syncthreads();
+  // ---- bias tables: thread (query i, which) -> T[which][i][r], r = 4..22 (the reachable shifts) ----
+  {
+    const int i = tid >> 1, which = tid & 1;
+    float q[16];
+#pragma unroll
+    for (int d2 = 0; d2 < 8; ++d2) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(&sQ[i][2 * d2]);
+      q[2 * d2] = unpack_lo<T>(w);
+      q[2 * d2 + 1] = unpack_hi<T>(w);
+    }
+#pragma unroll
+    for (int r = 4; r < kOcRel; ++r) {
+      const float* rr = sRel[which][r];
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; d += 2) { t0 = fmaf(q[d], rr[d], t0); t1 = fmaf(q[d + 1], rr[d + 1], t1); }
+      sT[which][i][r] = t0 + t1;
+    }
+  }
+  __syncthreads();
+
+  // ---- S = Qs K^T ----
+  const int g = lane >> 2, q4 = lane & 3;
+  uint32_t af[4];
+  ldsm_x4(af, smem_u32(&sQ[warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]));
+  float c[18][4];
+#pragma unroll
+  for (int n = 0; n < 18; ++n) { c[n][0] = c[n][1] = c[n][2] = c[n][3] = 0.f; }
+#pragma unroll
+  for (int n2 = 0; n2 < 9; ++n2) {                             // 16 keys per ldmatrix.x4: two n8 tiles
+    uint32_t bf[4];
+    ldsm_x4(bf, smem_u32(&sK[n2 * 16 + (lane & 7) + 8 * (lane >> 4)][8 * ((lane >> 3) & 1)]));
+    mma16816<T>(c[2 * n2], af, bf[0], bf[1]);
+    mma16816<T>(c[2 * n2 + 1], af, bf[2], bf[3]);
+  }
+  // ---- + relative-position bias, row max.  This thread: rows i0 = 16 warp + g (window row 2 warp, column g) and i0 + 8 ----
+  const int i0 = warp * 16 + g;
+  const float* tw0 = sT[0][i0] + (kOcOws - 1 - g);             // + kc
+  const float* tw1 = sT[0][i0 + 8] + (kOcOws - 1 - g);
+  const float* th0 = sT[1][i0] + (kOcOws - 1 - 2 * warp);      // + kr
+  const float* th1 = sT[1][i0 + 8] + (kOcOws - 1 - (2 * warp + 1));
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < 18; ++n) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int v = (8 * n) % 12 + 2 * q4 + e;                 // key j = 8 n + 2 q4 + e -> (kr, kc) = (j / 12, j % 12)
+      const int wrap = v >= 12 ? 1 : 0;
+      const int kc = v - 12 * wrap, kr = (8 * n) / 12 + wrap;
+      c[n][e] += tw0[kc] + th0[kr];
+      c[n][2 + e] += tw1[kc] + th1[kr];
+      m0 = fmaxf(m0, c[n][e]);
+      m1 = fmaxf(m1, c[n][2 + e]);
+    }
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float s0 = 0.f, s1 = 0.f;
+  const float L2E = 1.4426950408889634f;
+#pragma unroll
+  for (int n = 0; n < 18; ++n) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      c[n][e] = exp2f((c[n][e] - m0) * L2E); s0 += c[n][e];
+      c[n][2 + e] = exp2f((c[n][2 + e] - m1) * L2E); s1 += c[n][2 + e];
+    }
+  }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  // ---- O = P V ----
+  float o[2][4];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) { o[t][0] = o[t][1] = o[t][2] = o[t][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < 9; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack2<T>(c[2 * kk][0], c[2 * kk][1]);
+    pa[1] = pack2<T>(c[2 * kk][2], c[2 * kk][3]);
+    pa[2] = pack2<T>(c[2 * kk + 1][0], c[2 * kk + 1][1]);
+    pa[3] = pack2<T>(c[2 * kk + 1][2], c[2 * kk + 1][3]);
+    uint32_t vf[4];
+    ldsm_x4_trans(vf, smem_u32(&sV[kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]));
+    mma16816<T>(o[0], pa, vf[0], vf[1]);
+    mma16816<T>(o[1], pa, vf[2], vf[3]);
+  }
+  const float r0 = 1.0f / s0, r1 = 1.0f / s1;
+  const size_t pix0 = (size_t)(wy * kOcWs + 2 * warp) * a.W + wx * kOcWs + g;
+  unsigned short* op = a.out + (size_t)b * a.obs + h * kOcDh + 2 * q4;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    *reinterpret_cast<uint32_t*>(op + pix0 * a.opitch + 8 * t) = pack2<T>(o[t][0] * r0, o[t][1] * r0);
+    *reinterpret_cast<uint32_t*>(op + (pix0 + a.W) * a.opitch + 8 * t) = pack2<T>(o[t][2] * r1, o[t][3] * r1);
+  }
+}
+
 }  // namespace pir
 
 extern "C" int pir_ocab(const PirOcab* d, void* stream) {
@@ -142,7 +309,7 @@ extern "C" int pir_ocab(const PirOcab* d, void* stream) {
   if (d->ws != kOcWs || d->ows != kOcOws || d->dim_head != kOcDh)
     return pir_fail(PIR_ERR_UNSUPPORTED, "pir_ocab: built for window 8, overlapping window 12, head dim 16 (got %d, %d, %d)", d->ws, d->ows, d->dim_head);
   if ((d->H % kOcWs) || (d->W % kOcWs)) return pir_fail(PIR_ERR_ARG, "pir_ocab: H and W must be multiples of the window size");
-  if ((d->qkv_pitch % 8) || (d->qkv_bstride % 8) || (d->out_pitch % 4) || (d->out_bstride % 4) || ((uintptr_t)d->qkv & 15) || ((uintptr_t)d->out & 7) ||
+  if ((d->qkv_pitch % 8) || (d->qkv_bstride % 8) || (d->out_pitch % 8) || (d->out_bstride % 8) || ((uintptr_t)d->qkv & 15) || ((uintptr_t)d->out & 15) ||
       !d->qkv || !d->out || !d->rel_h || !d->rel_w)
     return pir_fail(PIR_ERR_ARG, "pir_ocab: tensors missing or not vector aligned");
   if (d->heads > 65535 || d->B > 65535) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_ocab: grid too large");
@@ -153,7 +320,13 @@ extern "C" int pir_ocab(const PirOcab* d, void* stream) {
   a.out = reinterpret_cast<unsigned short*>(d->out); a.opitch = d->out_pitch; a.obs = d->out_bstride;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid((unsigned)((d->H / kOcWs) * (d->W / kOcWs)), (unsigned)d->heads, (unsigned)d->B);
-  if (d->dtype == PIR_DTYPE_BF16) ocab_kernel<BF16><<<grid, 256, 0, s>>>(a);
-  else ocab_kernel<FP16><<<grid, 256, 0, s>>>(a);
+  static const bool simt = getenv("PIR_OCAB_SIMT") != nullptr;      // A/B: the fp32 SIMT version
+  if (simt) {
+    if (d->dtype == PIR_DTYPE_BF16) ocab_simt_kernel<BF16><<<grid, 256, 0, s>>>(a);
+    else ocab_simt_kernel<FP16><<<grid, 256, 0, s>>>(a);
+  } else {
+    if (d->dtype == PIR_DTYPE_BF16) ocab_kernel<BF16><<<grid, 128, 0, s>>>(a);
+    else ocab_kernel<FP16><<<grid, 128, 0, s>>>(a);
+  }
   return pir_check_launch("pir_ocab");
 }
