@@ -88,29 +88,32 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference(steps: int, warmup: int, sample_side: int = SIDE):
+def cpu_reference(steps: int, warmup: int, sample_side: int = SIDE, x=None, sd=None):
     """The reference's CPU path for this workload = oracle port (torch fp32 restatement, all host threads).
-    Bounded sample: ONE 256x256 image of the batch-16 workload per step."""
+    Bounded sample: ONE 256x256 image of the batch-16 workload per step.  This leg is the only place bench.py touches oracle/;
+    its last output is returned so the caller can check the GPU result of the same image against it."""
     from oracle import promptir_oracle as O
-    from promptir_b200 import PromptIR
+    from promptir_b200 import PromptIR, synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    sd = {k: v.detach() for k, v in PromptIR(decoder=True).state_dict().items()}
-    x, _ = O.synthetic_batch(1, sample_side, sample_side, seed=1)
+    if sd is None:
+        torch.manual_seed(0)
+        sd = {k: v.detach() for k, v in PromptIR(decoder=True).state_dict().items()}
+    if x is None:
+        x = synth.synthetic_batch(BATCH, sample_side, sample_side, seed=1)[0][:1]
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t = time.perf_counter()
-            O.promptir_forward(sd, x)
+            y = O.promptir_forward(sd, x)
             dt = time.perf_counter() - t
             if i >= warmup:
                 times.append(dt)
     sec = statistics.median(times)
     return {"value": sample_side * sample_side / 1e6 / sec, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 of the {BATCH} {sample_side}x{sample_side} images per step, fp32, median of {len(times)} forwards "
+            "sample": f"image 0 of the {BATCH} {sample_side}x{sample_side} images of a step, fp32, median of {len(times)} forwards "
                       f"({sec:.2f} s each), torch {torch.__version__} oneDNN",
-            "sec_per_step": sec}
+            "sec_per_step": sec, "output": y}
 
 
 def run_reference(args):
@@ -134,8 +137,7 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
-    from oracle import promptir_oracle as O
-    from promptir_b200 import PromptIR, _lib
+    from promptir_b200 import PromptIR, _lib, synth
     from promptir_b200.engine import op_cost
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -157,7 +159,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = PromptIR(decoder=True).eval().to(dev)
     model.compute_dtype = dt
-    x_host, clean = O.synthetic_batch(BATCH, SIDE, SIDE, seed=1 + rank)
+    x_host, clean = synth.synthetic_batch(BATCH, SIDE, SIDE, seed=1 + rank)
     x_pin = x_host.pin_memory()
     y_pin = torch.empty_like(x_host).pin_memory()
     eng = model.engine_for(BATCH, SIDE, SIDE, dev)
@@ -248,23 +250,18 @@ def run_ours(args):
     barrier()
     ms_e2e = c0.elapsed_time(c1) / K
 
-    # parity of exactly what was benchmarked (first image of the batch vs the CPU oracle, rank 0)
-    parity = None
-    if rank == 0:
-        with torch.no_grad():
-            sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-            ref = O.promptir_forward(sd, x_host[:1])
-        got = y_pin[:1]
-        parity = {"max_abs_clamped": float((got.clamp(0, 1) - ref.clamp(0, 1)).abs().max()),
-                  "dpsnr_db": abs(O.psnr(got, clean[:1]) - O.psnr(ref, clean[:1])), "oracle": "fp32 CPU port, image 0 of the batch"}
-
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
 
     if rank == 0:
-        cb = cpu_reference(2, 1)
+        # cpu_baseline leg: the oracle port timed on image 0 of this rank's batch; its output doubles as the parity check of exactly
+        # what was benchmarked (the e2e result of the same image)
+        cb = cpu_reference(2, 1, x=x_host[:1], sd={k: v.detach().cpu() for k, v in model.state_dict().items()})
+        ref, got = cb["output"], y_pin[:1]
+        parity = {"max_abs_clamped": float((got.clamp(0, 1) - ref.clamp(0, 1)).abs().max()),
+                  "dpsnr_db": abs(synth.psnr(got, clean[:1]) - synth.psnr(ref, clean[:1])), "oracle": "fp32 CPU port, image 0 of the batch"}
         line = {
             "metric": METRIC, "value": world * mp_step / ms * 1e3, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,

@@ -70,13 +70,17 @@ int pir_gemm(const PirGemm* d, void* stream);
 /* ---- depthwise 3x3 (pad 1), optionally fused with the GDFN gate ----------------------------------
  * gate == 0: out[b,p,c] = dw(in)[c] (+bias[c]),                c < C      (model.py:112,120  qkv_dwconv)
  * gate == 1: out[b,p,c] = gelu_erf(dw(in)[c]) * dw(in)[C + c], c < C      (model.py:90,96-97 GDFN)
- *            (in has 2*C channels).  w is [3][3][Cin] 16-bit (tap-major), bias fp32 [Cin] or NULL.     */
+ *            (in has 2*C channels).  w is [3][3][Cin] 16-bit (tap-major), bias fp32 [Cin] or NULL.
+ * gate == 2: backward of gate == 1 with the stencil recomputed: y = dw(in) (fp32, never stored),
+ *            out[c] = dg[c] y2 (Phi(y1) + y1 phi(y1)),  out[C + c] = dg[c] y1 Phi(y1)    (out has 2*C channels; training).
+ *            Phi comes from the forward gate's logistic-polynomial fit (|dPhi| <= 5.1e-5, a tenth of a 16-bit ulp of the result). */
 typedef struct PirDwConv {
   int32_t dtype, gate;
   int32_t B, H, W, C;       /* C = output channels; input channels = C (gate 0) or 2*C (gate 1)           */
   const void* in; int64_t in_pitch, in_bstride;
   const void* w; const float* bias;
   void* out; int64_t out_pitch, out_bstride;
+  const void* dg; int64_t dg_pitch, dg_bstride;   /* gate == 2 only */
 } PirDwConv;
 int pir_dwconv3x3(const PirDwConv* d, void* stream);
 

@@ -33,7 +33,8 @@ class PirDwConv(C.Structure):
     _fields_ = [("dtype", i32), ("gate", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32),
                 ("in_", vp), ("in_pitch", i64), ("in_bstride", i64),
                 ("w", vp), ("bias", vp),
-                ("out", vp), ("out_pitch", i64), ("out_bstride", i64)]
+                ("out", vp), ("out_pitch", i64), ("out_bstride", i64),
+                ("dg", vp), ("dg_pitch", i64), ("dg_bstride", i64)]
 
 
 class PirPwDw(C.Structure):

@@ -27,6 +27,8 @@ struct DwArgs {
   const float* bias;               // [Cin] or null
   void* out;
   long long out_pitch, out_bstride;
+  const void* dg;                  // gate backward only: gradient of the gated output [B,H,W,C]
+  long long dg_pitch, dg_bstride;
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -143,7 +145,9 @@ dwconv_plain_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
 // ------------------------------------------------------------------------------------------------------
 // gated: 32 output channels per tile (two 32-channel boxes: x1 at c0, x2 at C + c0); 4 channels per thread
 // ------------------------------------------------------------------------------------------------------
-template <class T, int TH>
+// BWD = true: the same stencil recomputes y1, y2 (fp32) and the epilogue is the gate's backward instead:
+//   out[c] = dg * y2 * (Phi(y1) + y1 phi(y1)),  out[C + c] = dg * y1 * Phi(y1)     (exact erf GELU; out has 2C channels)
+template <class T, int TH, bool BWD>
 __global__ void __launch_bounds__(256)
 dwconv_gate_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
   constexpr int CC = 32;
@@ -251,10 +255,29 @@ dwconv_gate_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
         if (c_ok && x_ok && y < a.H) {
           const float* pp = p[o % 3];
           const float* qq = q[o % 3];
-          uint2 ov;
-          ov.x = pack2<T>(gelu_erf(pp[0]) * qq[0], gelu_erf(pp[1]) * qq[1]);
-          ov.y = pack2<T>(gelu_erf(pp[2]) * qq[2], gelu_erf(pp[3]) * qq[3]);
-          *reinterpret_cast<uint2*>(outp + ((size_t)y * a.W + x) * a.out_pitch) = ov;
+          if (!BWD) {
+            uint2 ov;
+            ov.x = pack2<T>(gelu_erf(pp[0]) * qq[0], gelu_erf(pp[1]) * qq[1]);
+            ov.y = pack2<T>(gelu_erf(pp[2]) * qq[2], gelu_erf(pp[3]) * qq[3]);
+            *reinterpret_cast<uint2*>(outp + ((size_t)y * a.W + x) * a.out_pitch) = ov;
+          } else {
+            const uint2 dv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(a.dg) + (size_t)b * a.dg_bstride +
+                                                                  ((size_t)y * a.W + x) * a.dg_pitch + c));
+            const float d[4] = {unpack_lo<T>(dv.x), unpack_hi<T>(dv.x), unpack_lo<T>(dv.y), unpack_hi<T>(dv.y)};
+            float o1[4], o2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              // Phi from the same logistic-polynomial fit the forward gate uses (gelu = x * Phi: |x dPhi| <= 2.6e-5), phi from ex2.approx
+              const float u = fminf(pp[i] * pp[i], 25.0f);
+              const float cdf = rcp_approx(1.0f + ex2_approx(pp[i] * fmaf(u, fmaf(u, kGeluC, kGeluB), kGeluA)));
+              const float pdf = ex2_approx(-0.7213475204444817f * pp[i] * pp[i]) * 0.3989422804014327f;
+              o1[i] = d[i] * qq[i] * fmaf(pp[i], pdf, cdf);
+              o2[i] = d[i] * pp[i] * cdf;
+            }
+            unsigned short* op = outp + ((size_t)y * a.W + x) * a.out_pitch;
+            *reinterpret_cast<uint2*>(op) = make_uint2(pack2<T>(o1[0], o1[1]), pack2<T>(o1[2], o1[3]));
+            *reinterpret_cast<uint2*>(op + a.C) = make_uint2(pack2<T>(o2[0], o2[1]), pack2<T>(o2[2], o2[3]));
+          }
         }
       }
     }
@@ -285,6 +308,9 @@ static int launch_dwconv(const PirDwConv* d, cudaStream_t stream) {
     return w < 1 ? 1 : w;
   };
   a.w = d->w; a.bias = d->bias; a.out = d->out; a.out_pitch = d->out_pitch; a.out_bstride = d->out_bstride;
+  a.dg = d->dg; a.dg_pitch = d->dg_pitch; a.dg_bstride = d->dg_bstride;
+  if (d->gate == 2 && (!d->dg || (d->dg_pitch % 4) || (d->dg_bstride % 4) || ((uintptr_t)d->dg & 7)))
+    return pir_fail(PIR_ERR_ARG, "pir_dwconv3x3: gate backward needs dg (8-byte aligned)");
 
   const CUtensorMapDataType dt = T::kFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
@@ -294,14 +320,17 @@ static int launch_dwconv(const PirDwConv* d, cudaStream_t stream) {
     const uint32_t box[4] = {32, kDwTW + 2, TH + 2, 1};
     if (int e = pir_make_tmap(&tm, dt, 4, d->in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     const size_t smem = (size_t)2 * 2 * (TH + 2) * (kDwTW + 2) * 64 + 128;
-    static bool set[2] = {false, false};
-    if (!set[T::kFmt]) {
-      cudaFuncSetAttribute(dwconv_gate_kernel<T, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      set[T::kFmt] = true;
+    static bool set[2][2] = {{false, false}, {false, false}};
+    const int bw = d->gate == 2 ? 1 : 0;
+    if (!set[T::kFmt][bw]) {
+      if (bw) cudaFuncSetAttribute(dwconv_gate_kernel<T, TH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      else cudaFuncSetAttribute(dwconv_gate_kernel<T, TH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      set[T::kFmt][bw] = true;
     }
     const int chunks = (d->C + 31) / 32;
     dim3 grid((unsigned)workers_for(chunks, 2), (unsigned)chunks, 1);
-    dwconv_gate_kernel<T, TH><<<grid, 256, smem, stream>>>(tm, a);
+    if (bw) dwconv_gate_kernel<T, TH, true><<<grid, 256, smem, stream>>>(tm, a);
+    else dwconv_gate_kernel<T, TH, false><<<grid, 256, smem, stream>>>(tm, a);
   } else {
     const bool use48 = (d->C % 64 != 0) && (d->C % 48 == 0);
     const int cc = use48 ? 48 : 64;

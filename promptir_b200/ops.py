@@ -89,17 +89,27 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, n: int, taps: i
     return _prepared("pir_gemm", d, (a, w, out, res, ln_s, vec_t, img))
 
 
-def dwconv3x3(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, gate: bool, bias: Optional[torch.Tensor] = None) -> Launch:
+def dwconv3x3(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, gate, bias: Optional[torch.Tensor] = None,
+              dg: Optional[torch.Tensor] = None) -> Launch:
+    """gate: False plain, True GELU gate, 2 = gate backward with the stencil recomputed (needs dg; out has as many channels as x)."""
     px, B, H, W, Cin, xp, xbs = _nhwc(x, "dwconv.in")
     po, oB, oH, oW, Cout, op, obs = _nhwc(out, "dwconv.out")
+    gate = int(gate)
+    if gate == 2:
+        assert Cin == Cout and Cin % 2 == 0 and dg is not None
+        Cout = Cin // 2
     assert (oB, oH, oW) == (B, H, W) and Cin == (2 * Cout if gate else Cout)
     d = _lib.PirDwConv()
-    d.dtype, d.gate = dtype_code(x.dtype), int(gate)
+    d.dtype, d.gate = dtype_code(x.dtype), gate
     d.B, d.H, d.W, d.C = B, H, W, Cout
+    if dg is not None:
+        pg, gB, gH, gW, gC, gp, gbs = _nhwc(dg, "dwconv.dg")
+        assert (gB, gH, gW, gC) == (B, H, W, Cout) and dg.dtype == x.dtype
+        d.dg, d.dg_pitch, d.dg_bstride = pg, gp, gbs
     d.in_, d.in_pitch, d.in_bstride = px, xp, xbs
     d.w, d.bias = w.data_ptr(), _ptr(bias)
     d.out, d.out_pitch, d.out_bstride = po, op, obs
-    return _prepared("pir_dwconv3x3", d, (x, w, out, bias))
+    return _prepared("pir_dwconv3x3", d, (x, w, out, bias, dg))
 
 
 def pwdw_supported(c: int, n: int, gate: bool) -> bool:

@@ -14,8 +14,8 @@ forward (per TransformerBlock, net/model.py:192-196) -- the unfused kernels, bec
   The residual stream itself is NOT kept per block (LayerNorm backward works from xhat and rstd).
 
 backward (reverse order; g is the gradient of the residual stream, updated in place):
-    FFN   dgated = g . Wout^T            | wgrad(g, gated) -> dWout            | y = dwconv(hid_pre) (recomputed)
-          dy = gate_bwd(y, dgated)       | dw_wgrad(hid_pre, dy) -> d dwconv.w | dhid_pre = dwconv(dy, flipped taps)
+    FFN   dgated = g . Wout^T            | wgrad(g, gated) -> dWout            | dy = gate_bwd(dwconv(hid_pre), dgated): ONE kernel,
+          the stencil is recomputed      | dw_wgrad(hid_pre, dy) -> d dwconv.w | dhid_pre = dwconv(dy, flipped taps)
           dxhat = dhid_pre . Wg_in^T     | wgrad(dhid_pre, xhat2) -> dW_in, dgamma2, dbeta2       | g += ln_bwd(dxhat, xhat2, rstd2)
     MDTA  wgrad per image (g, v) -> dWfold[b]; mdta_bwd: softmax/cosine/temperature backward on the c x c matrices, produces
           dWo, dtemperature and two per-image weight sets so that the pixel-sized work is again GEMMs:
@@ -87,8 +87,9 @@ class TrainEngine(Engine):
         self._emit("ln_bwd", lambda: ops.ln_bwd(d, xhat, rstd, g, self.ln_mode), d=d, xhat=xhat, rstd=rstd, g=g, ln_mode=self.ln_mode,
                    tag=tag)
 
-    def _dw(self, x, w, out, *, gate, bias, tag):
-        self._emit("dwconv", lambda: ops.dwconv3x3(x, w, out, gate=gate, bias=bias), x=x, w=w, out=out, gate=gate, bias=bias, tag=tag)
+    def _dw(self, x, w, out, *, gate, bias, tag, dg=None):
+        self._emit("dwconv", lambda: ops.dwconv3x3(x, w, out, gate=gate, bias=bias, dg=dg), x=x, w=w, out=out, gate=gate, bias=bias, dg=dg,
+                   tag=tag)
 
     def _wgrad(self, a, b, *, taps=1, per_image=False, colsum=False, tag=""):
         """partials[img*splits + s][tap][m][n] = sum_{p in split} a[p, m] * b[p + off(tap), n]  (fp32, in self.wg_ws)."""
@@ -345,8 +346,7 @@ class TrainEngine(Engine):
             self._gemm(g, pout_wT, dgt, n=hp, tag="B7d")
             wg = self._wgrad(g, gated, colsum=ff.project_out.bias is not None, tag="B7w")
             self._wgrad_fin(wg, dst_w=G(ff.project_out.weight).view(c, hid), dst_bias=G(ff.project_out.bias), tag="B7f")
-            self._dw(hid_pre, dwf_w, y, gate=False, bias=dwf_b, tag="B6r")
-            self._emit("gate_bwd", lambda: ops.gate_bwd(y, dgt), y=y, dgt=dgt, tag="B6g")
+            self._dw(hid_pre, dwf_w, y, gate=2, bias=dwf_b, dg=dgt, tag="B6g")      # y = dw(hid_pre) recomputed, gate backward fused
             self._dw_wgrad(hid_pre, y, dst_w=G(ff.dwconv.weight), dst_bias=G(ff.dwconv.bias), half=hid, half_pad=hp, tag="B6w")
             self._dw(y, dwf_f, dhp, gate=False, bias=None, tag="B6d")
             self._gemm(dhp, pin_wT, dxh, n=c, tag="B5d")

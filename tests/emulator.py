@@ -62,7 +62,13 @@ def emu_dwconv(r):
     cin = x.shape[-1]
     cw = w.float().t().reshape(cin, 1, 3, 3)
     y = F.conv2d(_nchw(x), cw, r["bias"], padding=1, groups=cin)
-    if r["gate"]:
+    if int(r["gate"]) == 2:                            # gate backward on the recomputed (fp32) stencil output
+        c = cin // 2
+        y1, y2, dg = y[:, :c], y[:, c:], _nchw(r["dg"])
+        cdf = 0.5 * (1.0 + torch.erf(y1 * 0.7071067811865476))
+        pdf = torch.exp(-0.5 * y1 * y1) * 0.3989422804014327
+        y = torch.cat([dg * y2 * (cdf + y1 * pdf), dg * y1 * cdf], 1)
+    elif r["gate"]:
         c = cin // 2
         y = F.gelu(y[:, :c]) * y[:, c:]
     out.copy_(_nhwc(y).to(out.dtype))

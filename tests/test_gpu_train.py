@@ -223,3 +223,21 @@ def test_stale_backward_is_loud():
     out2.sum().backward()
     with pytest.raises(RuntimeError):
         out1.sum().backward()
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_gate_bwd_kernel(dt):
+    """pir_gate_bwd (the unfused gate backward, exact erf) on a channel-slice view."""
+    from promptir_b200 import ops
+    torch.manual_seed(0)
+    B, H, W, Cc = 2, 9, 13, 40
+    ybuf = (torch.randn(B, H, W, 2 * Cc + 8, device=DEV) * 1.5).to(dt)
+    y = ybuf[..., 8:]
+    dg = (torch.randn(B, H, W, Cc, device=DEV) * 0.3).to(dt)
+    ref = y.clone()
+    emulator.emu_gate_bwd(dict(y=ref, dgt=dg))
+    ops.gate_bwd(y, dg)(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    failures = []
+    _compare("gate_bwd", y, ref, failures)
+    assert not failures, failures

@@ -86,3 +86,21 @@ def test_gelu_sigmoid_polynomial_bound():
     y = x / (1.0 + torch.exp2(x * t))
     ref = torch.nn.functional.gelu(x.double()).float()
     assert (y - ref).abs().max().item() <= 2.6e-5
+
+
+def test_product_synthetic_data_is_the_oracles():
+    """bench.py / tools draw their inputs from promptir_b200.synth; the oracle keeps its own copy (golden generation) -- keep them equal."""
+    from promptir_b200 import synth
+    a, b = O.synthetic_batch(5, 32, 40, seed=3), synth.synthetic_batch(5, 32, 40, seed=3)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert O.psnr(a[0], a[1]) == synth.psnr(b[0], b[1])
+
+
+def test_gate_backward_phi_approximation_bound():
+    """pir_dwconv3x3(gate=2) evaluates Phi(x) with the forward gate's logistic-polynomial fit: |dPhi| <= 5.1e-5 everywhere."""
+    x = torch.linspace(-12, 12, 200001, dtype=torch.float64)
+    a, b, c = -2.301121339544986, -0.10677572399054727, 0.0010142630610895519          # kGeluA/B/C of csrc/common.cuh
+    u = torch.clamp(x * x, max=25.0)
+    approx = 1 / (1 + torch.exp2(x * (a + b * u + c * u * u)))
+    exact = 0.5 * (1 + torch.erf(x * 0.7071067811865476))
+    assert (approx - exact).abs().max().item() <= 5.1e-5

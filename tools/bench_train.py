@@ -41,8 +41,7 @@ def main():
     ap.add_argument("--ops-file", default="", help="write the per-launch timing list (tag, kind, shape, ms) here")
     args = ap.parse_args()
 
-    from oracle import promptir_oracle as O
-    from promptir_b200 import PromptIR, _lib
+    from promptir_b200 import PromptIR, _lib, synth
     from promptir_b200.train_engine import TrainEngine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -58,7 +57,7 @@ def main():
     torch.manual_seed(0)
     net = PromptIR(decoder=True).to(dev).train()
     net.compute_dtype = dt
-    x, y = O.synthetic_batch(B, S, S, seed=1 + rank)
+    x, y = synth.synthetic_batch(B, S, S, seed=1 + rank)
     x, y = x.to(dev), y.to(dev)
     eng = TrainEngine(net, B, S, S, dev, dt)
     params = [p for n, p in net.named_parameters() if n in eng.live_params]
@@ -162,6 +161,7 @@ def main():
 
     cpu = None
     if args.cpu_baseline and rank == 0:
+        from oracle import promptir_oracle as O          # the CPU leg is the only user of oracle/
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}

@@ -27,9 +27,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--dtype", default="bf16")
     args = ap.parse_args()
-    from oracle import promptir_oracle as O
-    from oracle import xrestormer_oracle as XO
-    from promptir_b200 import PromptXRestormer
+    from promptir_b200 import PromptXRestormer, synth
     from promptir_b200.xengine import x_op_cost
 
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -42,7 +40,7 @@ def main():
     net = PromptXRestormer().eval().to(dev)
     net.compute_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[args.dtype]
     B, S = args.batch, args.side
-    x, _ = O.synthetic_batch(B, S, S, seed=1 + rank)
+    x, _ = synth.synthetic_batch(B, S, S, seed=1 + rank)
     x = x.to(dev)
     eng = net.engine_for(B, S, S, dev)
     eng.img_in.copy_(x)
@@ -84,7 +82,8 @@ def main():
             k["ms"] = round(k["ms"], 3)
             k["share"] = round(k["ms"] / tot, 4)
         kernels = dict(sorted(kernels.items(), key=lambda kv: -kv[1]["ms"]))
-        # parity on a crop the CPU oracle finishes in seconds
+        # parity on a crop the CPU oracle finishes in seconds (checker leg: the only user of oracle/)
+        from oracle import xrestormer_oracle as XO
         xc = x[:1, :, :128, :128].contiguous()
         with torch.no_grad():
             yc = net(xc).cpu()

@@ -17,8 +17,7 @@ import torch.nn.functional as F  # noqa: E402
 
 
 def main():
-    from oracle import promptir_oracle as O
-    from promptir_b200 import PromptIR, ddp
+    from promptir_b200 import PromptIR, ddp, synth
     from promptir_b200.train_engine import TrainEngine
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -27,7 +26,7 @@ def main():
     torch.manual_seed(0)
     net = PromptIR(decoder=True).to(dev).train()
     B, S = 4, 64
-    x, y = O.synthetic_batch(B, S, S, seed=10 + rank)
+    x, y = synth.synthetic_batch(B, S, S, seed=10 + rank)
     x, y = x.to(dev), y.to(dev)
 
     model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], find_unused_parameters=True)
