@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--no-kernels", action="store_true")
     ap.add_argument("--ops-file", default="", help="write the per-launch timing list (tag, kind, shape, ms) here")
     args = ap.parse_args()
+    real_stdout = os.dup(1)          # libraries (NCCL banner) print to fd 1: keep stdout for the one JSON line
+    os.dup2(2, 1)
 
     from promptir_b200 import PromptIR, _lib, synth
     from promptir_b200.train_engine import TrainEngine
@@ -177,7 +179,7 @@ def main():
 
     if rank == 0:
         mp = world * B * S * S / 1e6
-        print(json.dumps({
+        os.write(real_stdout, (json.dumps({
             "metric": "promptir_train_step_megapixels_per_sec", "value": mp / (ms_eng / 1e3), "unit": "MP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_eng, "higher_is_better": True, "scaling": "weak",
             "dtype": args.dtype, "data": "synthetic",
@@ -187,7 +189,7 @@ def main():
             "images_per_sec": world * B / (ms_eng / 1e3), "ms_forward": ms_fwd, "ms_backward": ms_bwd,
             "api": {"ms_per_step": ms_api, "value": B * S * S / 1e6 / (ms_api / 1e3), "call": "loss = l1(net(x), y); loss.backward()"},
             "gpu_launches": eng.kernels_per_step(), "loss": loss, "loss_api": loss_api,
-            "saved_activation_GB": eng.saved_bytes / 1e9, "cpu_baseline": cpu, "kernels": kernels}))
+            "saved_activation_GB": eng.saved_bytes / 1e9, "cpu_baseline": cpu, "kernels": kernels}) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--dtype", default="bf16")
     args = ap.parse_args()
+    real_stdout = os.dup(1)          # libraries (NCCL banner) print to fd 1: keep stdout for the one JSON line
+    os.dup2(2, 1)
     from promptir_b200 import PromptXRestormer, synth
     from promptir_b200.xengine import x_op_cost
 
@@ -88,14 +90,14 @@ def main():
         with torch.no_grad():
             yc = net(xc).cpu()
             ref = XO.xrestormer_forward({k: v.detach().cpu() for k, v in net.state_dict().items()}, xc.cpu())
-        print(json.dumps({"metric": "prompt_xrestormer_fwd_megapixels_per_sec", "value": world * B * S * S / 1e6 / (ms / 1e3), "unit": "MP/s",
+        os.write(real_stdout, (json.dumps({"metric": "prompt_xrestormer_fwd_megapixels_per_sec", "value": world * B * S * S / 1e6 / (ms / 1e3), "unit": "MP/s",
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                           "scaling": "weak", "dtype": args.dtype, "data": "synthetic",
                           "config": {"workload": f"PromptXRestormer (dim 48, [4,6,6,8]) inference, batch {B} of {S}x{S} per GPU "
                                                  f"(BASELINE.json configs[4]), random-init weights seed 0",
                                      "parallelism": f"images sharded over {world} GPU(s), no data-path collective"},
                           "gpu_launches": eng.kernels_per_forward(), "kernels": kernels,
-                          "parity": {"max_abs_clamped": (yc.clamp(0, 1) - ref.clamp(0, 1)).abs().max().item(), "oracle": "fp32 CPU port, 128x128 crop"}}))
+                          "parity": {"max_abs_clamped": (yc.clamp(0, 1) - ref.clamp(0, 1)).abs().max().item(), "oracle": "fp32 CPU port, 128x128 crop"}}) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
