@@ -13,8 +13,8 @@ namespace pir {
 // ---------------------------------------------------------------------------------------------------
 // element types: the whole pipeline is templated on a 16-bit storage type (bf16 or fp16)
 // ---------------------------------------------------------------------------------------------------
-struct BF16 { static constexpr int kFmt = 1; };   // tcgen05 kind::f16 a/b format code
-struct FP16 { static constexpr int kFmt = 0; };
+struct BF16 { static constexpr int kFmt = 1; static constexpr unsigned short kOne = 0x3f80; };   // kFmt: tcgen05 kind::f16 a/b format code
+struct FP16 { static constexpr int kFmt = 0; static constexpr unsigned short kOne = 0x3c00; };   // kOne: 1.0 in the 16-bit type
 
 template <class T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
 template <> __device__ __forceinline__ uint32_t pack2<BF16>(float lo, float hi) {

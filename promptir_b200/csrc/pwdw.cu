@@ -19,17 +19,24 @@
 //     packed HFMA2 (fp16 inputs, taps and accumulation: the intermediate keeps 11 mantissa bits, more than the bf16
 //     tensor it replaces; values saturate at +-65504), applies the erf-GELU gate in fp32 and stores 16-bit NHWC.
 //
-// Warp roles (576 threads): 0 TMA producer | 1 TMEM alloc + MMA issue | 2-9 compute group 0 | 10-17 compute group 1.
+// Warp roles (576 threads): 0 TMA producer | 1 TMEM alloc + MMA issue | 2-17 compute warps in 2 groups of 8 or, where shared memory
+// allows a fourth fp16 tile, 4 groups of 4 (each thread then walks 6 output rows: 8 input rows per 6 outputs instead of 5 per 3).
 #include <stdlib.h>
 
 #include "common.cuh"
 #include "host.h"
 
+// PIR_PWDW_DBG what-if switches cost a few predicated branches per chunk: compiled in only with -DPIR_PWDW_DEBUG
+#ifdef PIR_PWDW_DEBUG
+#define FW_DBG(g) ((g).dbg)
+#else
+#define FW_DBG(g) 0
+#endif
+
 namespace pir {
 
 constexpr int kFwThreads = 576;
 constexpr int kFwCompute = 512;
-constexpr int kFwGroup = 256;                // threads per compute group
 constexpr int kFwBStages = 2;               // weight TMA ring (one super-chunk per stage)
 constexpr int kFwChunk = 32;                 // pre-conv channels per chunk = UMMA N (gate: 16 of x1 + the matching 16 of x2)
 
@@ -87,14 +94,16 @@ __device__ __forceinline__ float2 h2_to_f2(uint32_t v) {
 // the 64 columns are BANDS = 64 / TW row bands of R rows over a TW-wide tile.
 //   GATE : 4 gated channels per thread (16 gated channels per chunk), fp16 tile = two planes of 32-byte rows
 //   plain: 8 channels per thread       (32 channels per chunk),      fp16 tile = one plane of 64-byte rows
-template <int MT_, int TW_, int R_, bool GATE_, int NA_, int SC_>
+template <int MT_, int TW_, int R_, bool GATE_, int NA_, int SC_, int NG_ = 2>
 struct FwCfg {
   static constexpr int MT = MT_, TW = TW_, R = R_;
+  static constexpr int NG = NG_;                             // compute groups: 2 x 8 warps or 4 x 4 warps, one chunk in flight per group
+  static constexpr int GT = kFwCompute / NG_;                // threads per group = 4 channel groups x GT/4 pixel columns
   static constexpr bool GATE = GATE_;
   static constexpr int NA = NA_;
   static constexpr int SC = SC_;                             // chunks per super-chunk: one tcgen05.mma covers SC * 32 channels
   static constexpr int SCN = SC * kFwChunk;                  // UMMA N of a full super-chunk                             // x-tile buffers: 2 = the next item's tile is loaded and normalised ahead
-  static constexpr int BANDS = 64 / TW;
+  static constexpr int BANDS = GT / 4 / TW;
   static constexpr int TH = R * BANDS;
   static constexpr int SW = TW + 2;
   static constexpr int NPIX = (TH + 2) * SW;
@@ -111,7 +120,8 @@ __global__ void __launch_bounds__(kFwThreads, 1)
 pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const FwArgs g) {
   constexpr int MT = Cfg::MT, TW = Cfg::TW, R = Cfg::R, TH = Cfg::TH, SW = Cfg::SW, NPIX = Cfg::NPIX;
   constexpr bool GATE = Cfg::GATE;
-  constexpr int NA = Cfg::NA, SC = Cfg::SC, SCN = Cfg::SCN;
+  constexpr int NA = Cfg::NA, SC = Cfg::SC, SCN = Cfg::SCN, NG = Cfg::NG, GT = Cfg::GT;
+  static_assert(NG == 2 || (NG == 4 && SC == 4), "four groups take one chunk each of a 4-chunk super-chunk");
   constexpr uint32_t A_KB_BYTES = Cfg::A_KB_BYTES, B_KB_BYTES = Cfg::B_KB_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -269,10 +279,13 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else {
     // ============================ LayerNorm in place, drain, stencil, store =============================
     const int ct = threadIdx.x - 64;                 // 0..511
-    const int grp = ct >> 8;                         // compute group
-    const int gt = ct & 255;                         // thread within the group
+    const int grp = ct / GT;                         // compute group
+    const int gt = ct % GT;                          // thread within the group
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
-    const int slice = ((warp - 2) >> 2) & 1;         // 16-column half of a chunk this warp drains (gate: 0 = x1, 1 = x2)
+    // 16-column halves of a chunk this warp drains (gate: 0 = x1, 1 = x2): 8-warp groups split them over two warps per quarter,
+    // 4-warp groups take both
+    const int slice0 = NG == 2 ? (((warp - 2) >> 2) & 1) : 0;
+    constexpr int kSliceStep = NG == 2 ? 2 : 1;
     // stencil mapping: channel group fastest, then the pixel column, then the row band
     const int cg = gt & 3;
     const int tx = (gt >> 2) % TW;
@@ -288,8 +301,17 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int xh = tx + kx;
       rd_off[kx] = GATE ? (uint32_t)((((cg >> 1) ^ ((xh >> 2) & 1)) << 4) | ((cg & 1) << 3)) : (uint32_t)((cg ^ ((xh >> 1) & 3)) << 4);
     }
+    // per-thread constants of the tile geometry (no divisions inside the item loop): LayerNorm tasks (pixel m = task / 4 -> row, column
+    // in the halo'd tile) and the pixels this thread drains
+    constexpr int LNR = (NPIX * 4 + kFwCompute - 1) / kFwCompute;
+    int ln_yx[LNR];
+#pragma unroll
+    for (int r = 0; r < LNR; ++r) { const int m = (r * kFwCompute + ct) >> 2; ln_yx[r] = ((m / SW) << 8) | (m % SW); }
+    int dr_yx[MT];
+#pragma unroll
+    for (int t = 0; t < MT; ++t) { const int m = t * 128 + quarter * 32 + lane; dr_yx[t] = ((m / SW) << 8) | (m % SW); }
     const int nbar = 1 + grp * 2;                    // named barriers of this group: nbar, nbar + 1
-    auto grp_bar = [](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kFwGroup) : "memory"); };
+    auto grp_bar = [](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GT) : "memory"); };
     // ---- LayerNorm of an item's halo'd tile in place; pixels outside the image stay zero ----
     auto layernorm_tile = [&](int item, uint32_t itn) {
       const int rr = item % per_img;
@@ -297,15 +319,16 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t ab = itn % NA;
       uint8_t* a_tile = base_ptr + (size_t)ab * a_buf_bytes;
       mbar_wait(smem_u32(&bar_afull[ab]), (itn / NA) & 1u);
-      if (g.ln_mode && !(g.dbg & 8)) {
+      if (g.ln_mode && !(FW_DBG(g) & 8)) {
         // four threads per pixel; thread `part` owns the physical 16-byte chunks 2*part + (e ^ (m & 1)), e = 0, 1, of every
         // k-block (the row parity term keeps the quarter-warp's LDS.128 conflict free); statistics meet through shuffles
-        for (int task0 = 0; task0 < NPIX * 4; task0 += kFwCompute) {
-          const int task = task0 + ct;
+#pragma unroll
+        for (int r = 0; r < LNR; ++r) {
+          const int task = r * kFwCompute + ct;
           const int m = task >> 2, part = task & 3;
-          const int py = y0 - 1 + m / SW, px = x0 - 1 + m % SW;
+          const int py = y0 - 1 + (ln_yx[r] >> 8), px = x0 - 1 + (ln_yx[r] & 255);
           const bool act = m < NPIX && py >= 0 && py < g.H && px >= 0 && px < g.W;
-          float s1 = 0.f, s2 = 0.f;
+          float s1 = 0.f, s2 = 0.f, s1b = 0.f, s2b = 0.f;
           for (int kb = 0; kb < g.nkb; ++kb) {
             if (act) {
               const uint8_t* a_row = a_tile + (size_t)kb * A_KB_BYTES + (size_t)m * 128;
@@ -314,15 +337,17 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const uint4 v = *reinterpret_cast<const uint4*>(a_row + ((2 * part + (e ^ (m & 1))) << 4));
                 const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float a = unpack_lo<T>(w4[i]), bb = unpack_hi<T>(w4[i]);
-                  s1 += a + bb;
-                  s2 = fmaf(a, a, s2);
-                  s2 = fmaf(bb, bb, s2);
+                for (int i = 0; i < 4; ++i) {                 // 16-bit x 16-bit + fp32 (FHFMA): no unpack instructions
+                  const unsigned short lo = lo16(w4[i]), hi = hi16(w4[i]);
+                  s1 = fma16<T>(lo, T::kOne, s1);
+                  s1b = fma16<T>(hi, T::kOne, s1b);
+                  s2 = fma16<T>(lo, lo, s2);
+                  s2b = fma16<T>(hi, hi, s2b);
                 }
               }
             }
           }
+          s1 += s1b; s2 += s2b;
           s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
           s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
           const float inv_k = 1.0f / (float)g.C;
@@ -372,29 +397,35 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
         const int m = t * 128 + quarter * 32 + lane;
-        const int py = y0 - 1 + m / SW, px = x0 - 1 + m % SW;
+        const int py = y0 - 1 + (dr_yx[t] >> 8), px = x0 - 1 + (dr_yx[t] & 255);
         inside[t] = m < NPIX && py >= 0 && py < g.H && px >= 0 && px < g.W;
       }
+      // this thread's first output pixel of the item (the chunk loops only add the channel offset)
+      unsigned short* out_item = reinterpret_cast<unsigned short*>(g.out) + (size_t)b * g.out_bstride +
+                                 ((size_t)(y0 + band * R) * g.W + (x0 + tx)) * g.out_pitch;
+      const size_t out_row = (size_t)g.W * g.out_pitch;
 
       for (int sc = 0; sc < n_super; ++sc, ++uses) {
       // the group's chunks of this super-chunk: j = j0, j0 + 2, ... (j0 alternates per item so odd chunk counts balance out)
       const uint32_t sb = uses & 1u;
       mbar_wait(smem_u32(&bar_tfull[sb]), (uses >> 1) & 1u);
       tc_fence_after();
-      for (int j = (grp + (int)it) & 1; j < SC; j += 2) {
+      for (int j = (grp + (int)it) % NG; j < SC; j += NG) {
         const int c = sc * SC + j;
         if (c >= g.n_chunks) break;
         // ---- drain: TMEM -> (+ t[n]) -> fp16 shared-memory tile of this group ----
+#pragma unroll
+        for (int slice = slice0; slice < 2; slice += kSliceStep) {
         const int nb = GATE ? (slice ? g.hp + c * 16 : c * 16) : c * 32 + slice * 16;    // first pre-conv channel of this warp's slice
 #pragma unroll
         for (int t = 0; t < MT; ++t) {
           const int m = t * 128 + quarter * 32 + lane;
           uint32_t acc[16];
-          if (!(g.dbg & 16)) {
+          if (!(FW_DBG(g) & 16)) {
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + sb * (uint32_t)(MT * SCN) + (uint32_t)(t * SCN + j * kFwChunk + slice * 16), acc);
             tmem_ld_wait();
           }
-          if (m < NPIX && !(g.dbg & 2)) {
+          if (m < NPIX && !(FW_DBG(g) & 2)) {
             uint32_t pk[8];
             if (g.has_t && !interior && inside[t]) {
 #pragma unroll
@@ -407,7 +438,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int e = 0; e < 8; ++e) pk[e] = pack_f16_sat(__uint_as_float(acc[2 * e]), __uint_as_float(acc[2 * e + 1]));
             }
-            const int xh = m % SW;
+            const int xh = dr_yx[t] & 255;
             if (GATE) {
               uint8_t* row = conv_buf + (size_t)slice * (MT * 128 * 32) + (size_t)m * 32;
               const int sw = (xh >> 2) & 1;
@@ -421,10 +452,11 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
+        }
         grp_bar(nbar);                                                 // fp16 tile complete
 
         // ---- stencil from shared memory ----
-        if (g.dbg & 1) {
+        if (FW_DBG(g) & 1) {
         } else if (GATE) {
           const int ch = c * 16 + cg * 4;                              // gated channel of this thread
           const uint8_t* wbase = reinterpret_cast<const uint8_t*>(sdw) + (size_t)c * 576 + cg * 8;
@@ -439,9 +471,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t b1[2] = {sd[0], sd[1]}, b2[2] = {sd[8], sd[9]};
           const int x = x0 + tx;
           const bool ok = ch < g.hp && x < g.W;
-          unsigned short* outp = reinterpret_cast<unsigned short*>(g.out) + (size_t)b * g.out_bstride + ch +
-                                 ((size_t)(y0 + band * R) * g.W + x) * g.out_pitch;
-          const size_t out_row = (size_t)g.W * g.out_pitch;
+          unsigned short* outp = out_item + ch;
           const uint8_t* src = conv_buf + (size_t)((band * R) * SW + tx) * 32;
           uint32_t p[3][2], qq[3][2];
 #pragma unroll
@@ -479,7 +509,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 ov.x = pack2<T>(gelu_erf(pa.x) * qa.x, gelu_erf(pa.y) * qa.y);
                 ov.y = pack2<T>(gelu_erf(pb.x) * qb.x, gelu_erf(pb.y) * qb.y);
               }
-              if (ok && y0 + band * R + o < g.H && !(g.dbg & 4)) *reinterpret_cast<uint2*>(outp + o * out_row) = ov;
+              if (ok && y0 + band * R + o < g.H && !(FW_DBG(g) & 4)) *reinterpret_cast<uint2*>(outp + o * out_row) = ov;
             }
           }
         } else {
@@ -492,9 +522,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t bb[4] = {sd[0], sd[1], sd[2], sd[3]};
           const int x = x0 + tx;
           const bool ok = ch < g.n_pre && x < g.W;
-          unsigned short* outp = reinterpret_cast<unsigned short*>(g.out) + (size_t)b * g.out_bstride + ch +
-                                 ((size_t)(y0 + band * R) * g.W + x) * g.out_pitch;
-          const size_t out_row = (size_t)g.W * g.out_pitch;
+          unsigned short* outp = out_item + ch;
           const uint8_t* src = conv_buf + (size_t)((band * R) * SW + tx) * 64;
           uint32_t p[3][4];
 #pragma unroll
@@ -526,7 +554,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const float2 f = h2_to_f2(p[o % 3][e]);
                 op[e] = pack2<T>(f.x, f.y);
               }
-              if (ok && y0 + band * R + o < g.H && !(g.dbg & 4)) *reinterpret_cast<uint4*>(outp + o * out_row) = ov;
+              if (ok && y0 + band * R + o < g.H && !(FW_DBG(g) & 4)) *reinterpret_cast<uint4*>(outp + o * out_row) = ov;
             }
           }
         }
@@ -546,25 +574,26 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // ---------------------------------------------------------------------------------------------------
 struct FwPlan {
-  int mt, tw, na, sc;      // template configuration
+  int mt, tw, na, sc, ng;  // template configuration
   uint32_t smem;
   FwArgs g;
 };
 
 static int tile_h(int mt, int tw) { return mt == 3 ? (tw == 32 ? 8 : 16) : 12; }
 
-static bool plan_fits(const PirPwDw* d, FwPlan* p, int mt, int na, int sc) {
+static bool plan_fits(const PirPwDw* d, FwPlan* p, int mt, int na, int sc, int ng = 2) {
   FwArgs& g = p->g;
   if (2 * mt * sc * kFwChunk > 512) return false;                      // TMEM
+  if (ng == 4 && (sc != 4 || mt != 2)) return false;
   // shared-memory plan: [A: na x nkb x MT x 16 KB] [B ring: 2 x nkb x SC x 4 KB] [fp16 tiles: 2 x MT x 8 KB] [dw taps] [t] [accumulator seeds]
   uint32_t off = (uint32_t)na * g.nkb * mt * 16384u;
   g.off_b = off; off += (uint32_t)kFwBStages * g.nkb * (uint32_t)sc * 4096u;
-  g.off_conv = off; off += 2u * (uint32_t)mt * 128u * 64u;
+  g.off_conv = off; off += (uint32_t)ng * (uint32_t)mt * 128u * 64u;
   g.off_dw = off; off += (uint32_t)g.n_chunks * 576u;
   g.off_vec = off; off += (uint32_t)g.n_vec * 4u;
   g.off_bias = off; off += (uint32_t)g.n_chunks * 128u;
   if (off + 1024u > 227u * 1024u - 1024u) return false;
-  p->mt = mt; p->na = na; p->sc = sc; p->smem = off + 1024u;
+  p->mt = mt; p->na = na; p->sc = sc; p->ng = ng; p->smem = off + 1024u;
   p->tw = (mt == 3 && d->W > 16) ? 32 : 16;
   const int th = tile_h(mt, p->tw);
   g.tiles_x = (d->W + p->tw - 1) / p->tw;
@@ -590,10 +619,11 @@ static int plan_pwdw(const PirPwDw* d, FwPlan* p) {
   // configurations <MT row groups, NA x-tile buffers, SC chunks per MMA>, best first.  PIR_PWDW_CFG="<mt><na><sc>" forces one.
   static const char* force = getenv("PIR_PWDW_CFG");
   if (force && force[0] && force[1] && force[2])
-    return plan_fits(d, p, force[0] - '0', force[1] - '0', force[2] - '0') ? PIR_OK : PIR_ERR_UNSUPPORTED;
-  static const int pref[][3] = {{2, 2, 4}, {2, 1, 4}, {2, 2, 2}, {2, 1, 2}, {3, 1, 2}};
+    return plan_fits(d, p, force[0] - '0', force[1] - '0', force[2] - '0', force[3] ? force[3] - '0' : 2) ? PIR_OK : PIR_ERR_UNSUPPORTED;
+  static const int pref[][4] = {{2, 2, 4, 4}, {2, 1, 4, 4}, {2, 2, 4, 2}, {2, 1, 4, 2}, {2, 2, 2, 2}, {2, 1, 2, 2}, {3, 1, 2, 2}};
+  static const bool no4 = getenv("PIR_PWDW_NG2") != nullptr;            // A/B: never use the four-group variants
   for (const auto& c : pref)
-    if (plan_fits(d, p, c[0], c[1], c[2])) return PIR_OK;
+    if (!(no4 && c[3] == 4) && plan_fits(d, p, c[0], c[1], c[2], c[3])) return PIR_OK;
   return PIR_ERR_UNSUPPORTED;
 }
 
@@ -639,6 +669,8 @@ static int launch_pwdw(const PirPwDw* d, cudaStream_t stream) {
     const uint32_t box[2] = {64, 16};
     if (int e = pir_make_tmap(&tmB, dt, 2, d->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   }
+  if (p.mt == 2 && p.na == 2 && p.sc == 4 && p.ng == 4) return launch_cfg<T, FwCfg<2, 16, 6, GATE, 2, 4, 4>>(p, tmA, tmB, stream);
+  if (p.mt == 2 && p.na == 1 && p.sc == 4 && p.ng == 4) return launch_cfg<T, FwCfg<2, 16, 6, GATE, 1, 4, 4>>(p, tmA, tmB, stream);
   if (p.mt == 2 && p.na == 2 && p.sc == 4) return launch_cfg<T, FwCfg<2, 16, 3, GATE, 2, 4>>(p, tmA, tmB, stream);
   if (p.mt == 2 && p.na == 1 && p.sc == 4) return launch_cfg<T, FwCfg<2, 16, 3, GATE, 1, 4>>(p, tmA, tmB, stream);
   if (p.mt == 2 && p.na == 2 && p.sc == 2) return launch_cfg<T, FwCfg<2, 16, 3, GATE, 2, 2>>(p, tmA, tmB, stream);

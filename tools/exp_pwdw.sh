@@ -1,2 +1,5 @@
-for dbg in 0 7 15 23 31 8; do PIR_PWDW_DBG=$dbg python tools/time_pwdw.py 16 256 256 96 288 0; done
-for dbg in 0 7 15 31 8; do PIR_PWDW_DBG=$dbg python tools/time_pwdw.py 16 256 256 96 256 1; done
+# A/B of the pwdw variants: default (four groups where they fit) vs PIR_PWDW_NG2=1 (two groups)
+for shape in "16 256 256 96 256 1" "16 256 256 96 288 0" "16 256 256 48 128 1" "16 256 256 48 144 0" "16 128 128 96 256 1" "16 128 128 96 288 0" "16 64 64 192 512 1" "16 64 64 192 576 0"; do
+  python tools/time_pwdw.py $shape
+  PIR_PWDW_NG2=1 python tools/time_pwdw.py $shape | sed 's/$/  (NG2)/'
+done
