@@ -51,6 +51,8 @@ struct FwArgs {
   int tiles_x, tiles_y, n_items;
   int has_bias;            // depthwise bias present
   int has_t;               // additive per-channel vector present
+  int scb;                 // chunks per super-chunk (<= SC of the configuration)
+  int rot;                 // rotate the group <-> chunk assignment by the super-chunk index too
   int dbg;                 // diagnostics (PIR_PWDW_DBG): 1 skip the stencil, 2 skip the drain arithmetic, 4 skip the stores, 8 skip LayerNorm, 16 skip TMEM loads
   uint32_t off_b, off_conv, off_dw, off_vec, off_bias;   // byte offsets from the 1024-aligned base
   const void* dw_w;        // [9][n_pre] fp16
@@ -190,7 +192,8 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const int per_img = g.tiles_x * g.tiles_y;
-  const int n_super = (g.n_chunks + SC - 1) / SC;
+  const int n_super = (g.n_chunks + g.scb - 1) / g.scb;
+  const int scb = g.scb;                                                   // chunks per super-chunk
   const uint32_t a_buf_bytes = (uint32_t)g.nkb * A_KB_BYTES;               // one x-tile buffer
 
   if (warp == 0) {
@@ -218,7 +221,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       for (int sc = 0; sc < n_super; ++sc, ++q) {
         const uint32_t st = q % kFwBStages;
-        const int nvalid = min(SC, g.n_chunks - sc * SC);
+        const int nvalid = min(scb, g.n_chunks - sc * scb);
         mbar_wait_sleep(smem_u32(&bar_bempty[st]), ((q / kFwBStages) & 1u) ^ 1u);
         if (elect_one()) {
           const uint32_t full = smem_u32(&bar_bfull[st]);
@@ -226,7 +229,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_expect_tx(full, (uint32_t)g.nkb * (uint32_t)nvalid * 4096u);
           for (int kb = 0; kb < g.nkb; ++kb) {
             for (int j = 0; j < nvalid; ++j) {               // chunk c occupies rows [32 j, 32 j + 32) of the stage
-              const int c = sc * SC + j;
+              const int c = sc * scb + j;
               const int r0 = GATE ? c * 16 : c * 32, r1 = GATE ? g.hp + c * 16 : c * 32 + 16;
               tma_load_2d(dst + (uint32_t)kb * B_KB_BYTES + (uint32_t)j * 4096u, &tmB, full, kb * 64, r0);
               tma_load_2d(dst + (uint32_t)kb * B_KB_BYTES + (uint32_t)j * 4096u + 2048u, &tmB, full, kb * 64, r1);
@@ -249,7 +252,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int sc = 0; sc < n_super; ++sc, ++q) {
         const uint32_t st = q % kFwBStages, ph = (q / kFwBStages) & 1u;
         const uint32_t sb = q & 1u;
-        const int nvalid = min(SC, g.n_chunks - sc * SC);
+        const int nvalid = min(scb, g.n_chunks - sc * scb);
         const uint32_t idesc = make_idesc_f16(T::kFmt, 128, nvalid * kFwChunk, 0, 0);
         mbar_wait(smem_u32(&bar_bfull[st]), ph);
         mbar_wait(smem_u32(&bar_tempty[sb]), ((q >> 1) & 1u) ^ 1u);
@@ -410,9 +413,9 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t sb = uses & 1u;
       mbar_wait(smem_u32(&bar_tfull[sb]), (uses >> 1) & 1u);
       tc_fence_after();
-      for (int j = (grp + (int)it) % NG; j < SC; j += NG) {
-        const int c = sc * SC + j;
-        if (c >= g.n_chunks) break;
+      const int nvalid = min(scb, g.n_chunks - sc * scb);
+      for (int j = (grp + (int)it + (g.rot ? sc : 0)) % NG; j < nvalid; j += NG) {
+        const int c = sc * scb + j;
         // ---- drain: TMEM -> (+ t[n]) -> fp16 shared-memory tile of this group ----
 #pragma unroll
         for (int slice = slice0; slice < 2; slice += kSliceStep) {
@@ -652,6 +655,16 @@ static int launch_pwdw(const PirPwDw* d, cudaStream_t stream) {
   FwPlan p;
   if (plan_pwdw(d, &p) != PIR_OK) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_pwdw: C = %d, N = %d does not fit the shared-memory plan", d->C, d->N);
   p.g.dw_w = d->dw_w; p.g.dw_bias = d->dw_bias; p.g.vec_t = d->vec_t;
+  {
+    // equal-sized super-chunks (9 chunks run as 3 + 3 + 3, not 4 + 4 + 1) with the group <-> chunk assignment rotated by the
+    // super-chunk index, so the idle group moves around: 440 -> 420 us on the C = 96 qkv kernel (same-box A/B).  PIR_PWDW_BAL=0 restores
+    // the plain split (bit 0: equal sizes, bit 1: rotation).
+    static const char* bal = getenv("PIR_PWDW_BAL");
+    const int mode = bal ? atoi(bal) : 3;
+    const int n_super = (p.g.n_chunks + p.sc - 1) / p.sc;
+    p.g.scb = (mode & 1) ? (p.g.n_chunks + n_super - 1) / n_super : p.sc;
+    p.g.rot = (mode & 2) ? 1 : 0;
+  }
   p.g.out = d->out; p.g.out_pitch = d->out_pitch; p.g.out_bstride = d->out_bstride;
   const CUtensorMapDataType dt = T::kFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap tmA, tmB;
