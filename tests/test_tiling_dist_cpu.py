@@ -59,7 +59,7 @@ def _worker(rank, world, port, q):
     x = torch.rand(1, 3, 72, 56)
     out = tiling.tile_eval(fake_model, x, 32, 8, batch=4, blend=cpu_blend)
     if rank == 0:
-        q.put(out)
+        q.put(out.numpy())              # by value: a tensor travels as a shared-memory handle that dies with this process
     dist.barrier()
     dist.destroy_process_group()
 
@@ -73,7 +73,7 @@ def test_tile_eval_sharded_over_two_gloo_ranks():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out = q.get(timeout=120)
+    out = torch.from_numpy(q.get(timeout=120))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
