@@ -287,6 +287,7 @@ typedef struct PirPromptBwd {
   float* scratch;
   float* demb;
   float* dst_prompt; float* dst_lin_w; float* dst_lin_b;
+  int32_t align_corners;    /* bilinear rule of the forward (see PirPrompt)                                                  */
 } PirPromptBwd;
 int64_t pir_prompt_bwd_ws_floats(int32_t B, int32_t L, int32_t D, int32_t S);
 int pir_prompt_bwd(const PirPromptBwd* d, void* stream);
@@ -338,6 +339,26 @@ int pir_mirror_pad(const float* in, float* out, int32_t planes, int32_t H, int32
 int64_t pir_psnr_ssim_ws_bytes(int32_t B, int32_t C, int32_t H, int32_t W);
 int pir_psnr_ssim(const float* restored, const float* clean, int32_t B, int32_t C, int32_t H, int32_t W, void* ws, double* out, void* stream);
 int pir_add_noise(const float* clean255, float* out, int64_t n, float sigma, uint64_t seed, void* stream);
+
+/* ---- OCAB backward (autograd of prompt_xrestormer.py:215-232 + RelPosEmb :25-73) ----------------------------------------------
+ * Given qkv (as for pir_ocab) and dout = dL/d(out) [B,H,W,inner], recomputes the attention of every (window, head) and writes
+ *   dqkv [B,H,W,3*inner] 16-bit: dq directly (query windows do not overlap); dk, dv of a pixel are the sum over the (up to four)
+ *        overlapping key windows that contain it, gathered deterministically from per-window partials in `ws`,
+ *   dst_rel_h, dst_rel_w: fp32 [2*ows-1][dim_head] parameter gradients (* inv_scale), reduced over all windows / images / heads.
+ * ws: pir_ocab_bwd_ws_floats() floats of scratch.                                                                              */
+typedef struct PirOcabBwd {
+  int32_t dtype;
+  int32_t B, H, W;
+  int32_t heads, dim_head, ws_, ows;
+  const void* qkv; int64_t qkv_pitch, qkv_bstride;
+  const void* dout; int64_t dout_pitch, dout_bstride;
+  const float* rel_h; const float* rel_w;
+  void* dqkv; int64_t dqkv_pitch, dqkv_bstride;
+  float* ws; float inv_scale;
+  float* dst_rel_h; float* dst_rel_w;
+} PirOcabBwd;
+int64_t pir_ocab_bwd_ws_floats(int32_t B, int32_t H, int32_t W, int32_t heads);
+int pir_ocab_bwd(const PirOcabBwd* d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,16 @@ class PirOcab(C.Structure):
                 ("out", vp), ("out_pitch", i64), ("out_bstride", i64)]
 
 
+class PirOcabBwd(C.Structure):
+    _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("heads", i32), ("dim_head", i32), ("ws_", i32), ("ows", i32),
+                ("qkv", vp), ("qkv_pitch", i64), ("qkv_bstride", i64),
+                ("dout", vp), ("dout_pitch", i64), ("dout_bstride", i64),
+                ("rel_h", vp), ("rel_w", vp),
+                ("dqkv", vp), ("dqkv_pitch", i64), ("dqkv_bstride", i64),
+                ("ws", vp), ("inv_scale", C.c_float),
+                ("dst_rel_h", vp), ("dst_rel_w", vp)]
+
+
 class PirPatchEmbed(C.Structure):
     _fields_ = [("dtype", i32), ("B", i32), ("H", i32), ("W", i32), ("Cin", i32), ("Cout", i32),
                 ("img", vp), ("w", vp), ("bias", vp),
@@ -129,7 +139,7 @@ class PirPromptBwd(C.Structure):
                 ("dup", vp), ("dup_pitch", i64), ("dup_bstride", i64),
                 ("prompt", vp), ("weights", vp), ("pool_ws", vp), ("lin_w", vp),
                 ("inv_scale", f32), ("scratch", vp), ("demb", vp),
-                ("dst_prompt", vp), ("dst_lin_w", vp), ("dst_lin_b", vp)]
+                ("dst_prompt", vp), ("dst_lin_w", vp), ("dst_lin_b", vp), ("align_corners", i32)]
 
 
 class PirBcastAdd(C.Structure):
@@ -175,6 +185,8 @@ SYMBOLS = {
     "pir_bcast_add": (i32, [C.POINTER(PirBcastAdd), vp]),
     "pir_nchw32_to_nhwc16": (i32, [C.POINTER(PirToNhwc16), vp]),
     "pir_ocab": (i32, [C.POINTER(PirOcab), vp]),
+    "pir_ocab_bwd_ws_floats": (i64, [i32, i32, i32, i32]),
+    "pir_ocab_bwd": (i32, [C.POINTER(PirOcabBwd), vp]),
     "pir_mirror_pad": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "pir_psnr_ssim_ws_bytes": (i64, [i32, i32, i32, i32]),
     "pir_psnr_ssim": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),

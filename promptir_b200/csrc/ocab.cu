@@ -300,6 +300,271 @@ ocab_kernel(const OcArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Backward.  One CTA of 256 threads per (window, head); thread = (query i, part s) as in the SIMT forward.
+//   recompute p = softmax(logits);  dP = dO V^T;  dS = p (dP - <p, dP>);
+//   dQs_i = sum_j dS_ij (k_j + rel_w[kc - y + 11] + rel_h[kr - x + 11]),  dq = dQs / 4                  -> global (queries do not overlap)
+//   dK_j = sum_i dS_ij qs_i,  dV_j = sum_i p_ij dO_i     (dS, p staged in shared memory, one thread per (key, half))
+//        -> per-window partial in the workspace: overlapping windows share key pixels, a gather kernel adds the <= 4 contributions
+//   d rel_w[r] = sum_i sum_{kc - y_i + 11 = r} (sum_kr dS_i[kr, kc]) qs_i   (and rel_h alike) -> per-CTA partial, reduced in fixed order
+// fp32 throughout; deterministic (no atomics).
+// ------------------------------------------------------------------------------------------------------
+constexpr int kObKV = kOcKeys * 32;          // floats of dK|dV per (window, head): [144][16 dk | 16 dv]
+constexpr int kObRel = 2 * kOcRel * kOcDh;   // floats of d rel_w | d rel_h per (window, head)
+
+struct ObArgs {
+  int H, W, heads, inner;
+  const unsigned short* qkv; long long qpitch, qbs;
+  const unsigned short* dout; long long dpitch, dbs;
+  const float* rel_h; const float* rel_w;
+  unsigned short* dqkv; long long gpitch, gbs;
+  float* ws_kv;            // [B][windows][heads][144][32]
+  float* ws_rel;           // [B][windows][heads][2][23][16]
+};
+
+template <class T>
+__global__ void __launch_bounds__(256)
+ocab_bwd_kernel(const ObArgs a) {
+  extern __shared__ __align__(16) float ob_smem[];
+  float (*sK)[kOcRow] = reinterpret_cast<float (*)[kOcRow]>(ob_smem);                      // [144][20]
+  float (*sV)[kOcRow] = reinterpret_cast<float (*)[kOcRow]>(ob_smem + kOcKeys * kOcRow);
+  float (*sRw)[kOcDh] = reinterpret_cast<float (*)[kOcDh]>(ob_smem + 2 * kOcKeys * kOcRow);
+  float (*sRh)[kOcDh] = sRw + kOcRel;
+  float (*sQ)[kOcDh] = sRh + kOcRel;                                                       // [64][16] scaled queries
+  float (*sdO)[kOcDh] = sQ + 64;                                                           // [64][16]
+  float (*sP)[kOcKeys + 1] = reinterpret_cast<float (*)[kOcKeys + 1]>(&sdO[64][0]);        // [64][145]
+  float (*sdS)[kOcKeys + 1] = sP + 64;                                                     // [64][145]
+  float (*sC)[kOcOws] = reinterpret_cast<float (*)[kOcOws]>(&sdS[64][0]);                  // [64][12] column sums of dS (per kc)
+  float (*sR)[kOcOws] = sC + 64;                                                           // [64][12] row sums of dS (per kr)
+  float (*sTw)[kOcOws] = sR + 64;                                                          // [64][12] qs . rel_w[kc - y + 11]
+  float (*sTh)[kOcOws] = sTw + 64;                                                         // [64][12] qs . rel_h[kr - x + 11]
+  const int tid = threadIdx.x;
+  const int nw = a.W / kOcWs, nwin = (a.H / kOcWs) * nw;
+  const int wy = blockIdx.x / nw, wx = blockIdx.x % nw;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const unsigned short* base = a.qkv + (size_t)b * a.qbs;
+
+  for (int e = tid; e < kOcKeys * 4; e += 256) {
+    const int j = e >> 2, which = (e >> 1) & 1, half = e & 1;
+    const int py = wy * kOcWs - (kOcOws - kOcWs) / 2 + j / kOcOws, px = wx * kOcWs - (kOcOws - kOcWs) / 2 + j % kOcOws;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (py >= 0 && py < a.H && px >= 0 && px < a.W)
+      v = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)py * a.W + px) * a.qpitch + (size_t)(1 + which) * a.inner + h * kOcDh + half * 8));
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    float* dst = (which ? sV[j] : sK[j]) + half * 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { dst[2 * q] = unpack_lo<T>(w4[q]); dst[2 * q + 1] = unpack_hi<T>(w4[q]); }
+  }
+  for (int e = tid; e < kOcRel * kOcDh; e += 256) {
+    sRw[e / kOcDh][e % kOcDh] = __ldg(a.rel_w + e);
+    sRh[e / kOcDh][e % kOcDh] = __ldg(a.rel_h + e);
+  }
+  const int i = tid >> 2, s = tid & 3;
+  const int x = i >> 3, y = i & 7;
+  const size_t qpix = (size_t)(wy * kOcWs + x) * a.W + wx * kOcWs + y;
+  float qs[16], dO[16];
+  load16<T>(base + qpix * a.qpitch + h * kOcDh, qs);
+  load16<T>(a.dout + (size_t)b * a.dbs + qpix * a.dpitch + h * kOcDh, dO);
+#pragma unroll
+  for (int d = 0; d < 16; ++d) qs[d] *= 0.25f;
+  if (s == 0) {
+#pragma unroll
+    for (int d = 0; d < 16; ++d) { sQ[i][d] = qs[d]; sdO[i][d] = dO[d]; }
+  }
+  __syncthreads();
+
+  auto dot16 = [](const float (&u)[16], const float* r) {
+    const float4 r0 = *reinterpret_cast<const float4*>(r), r1 = *reinterpret_cast<const float4*>(r + 4);
+    const float4 r2 = *reinterpret_cast<const float4*>(r + 8), r3 = *reinterpret_cast<const float4*>(r + 12);
+    float t0 = u[0] * r0.x, t1 = u[1] * r0.y, t2 = u[2] * r0.z, t3 = u[3] * r0.w;
+    t0 = fmaf(u[4], r1.x, t0); t1 = fmaf(u[5], r1.y, t1); t2 = fmaf(u[6], r1.z, t2); t3 = fmaf(u[7], r1.w, t3);
+    t0 = fmaf(u[8], r2.x, t0); t1 = fmaf(u[9], r2.y, t1); t2 = fmaf(u[10], r2.z, t2); t3 = fmaf(u[11], r2.w, t3);
+    t0 = fmaf(u[12], r3.x, t0); t1 = fmaf(u[13], r3.y, t1); t2 = fmaf(u[14], r3.z, t2); t3 = fmaf(u[15], r3.w, t3);
+    return (t0 + t1) + (t2 + t3);
+  };
+  // ---- bias tables of this query: part s computes the 3 key columns kc = s + 4 b and the 3 key rows a = s, s + 4, s + 8 ----
+#pragma unroll
+  for (int bb = 0; bb < 3; ++bb) {
+    sTw[i][s + 4 * bb] = dot16(qs, sRw[s + 4 * bb - y + kOcOws - 1]);
+    sTh[i][s + 4 * bb] = dot16(qs, sRh[s + 4 * bb - x + kOcOws - 1]);
+    sC[i][s + 4 * bb] = 0.f;
+  }
+  __syncwarp();                                         // the four parts of a query share a warp
+  // ---- recompute the softmax; logits / probabilities live in this thread's own slots of sP (runtime loops: registers stay small) ----
+  float mx = -INFINITY;
+#pragma unroll 2
+  for (int t = 0; t < 36; ++t) {
+    const int ka = t / 3, j = s + 4 * t;
+    const float l = dot16(qs, sK[j]) + sTw[i][j - ka * kOcOws] + sTh[i][ka];
+    sP[i][j] = l;
+    mx = fmaxf(mx, l);
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  float sum = 0.f;
+#pragma unroll 4
+  for (int t = 0; t < 36; ++t) { const float e = exp2f((sP[i][s + 4 * t] - mx) * 1.4426950408889634f); sP[i][s + 4 * t] = e; sum += e; }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  const float inv = 1.0f / sum;
+  // ---- dP = dO . v_j (parked in sdS), <p, dP> ----
+  float rowdot = 0.f;
+#pragma unroll 2
+  for (int t = 0; t < 36; ++t) {
+    const int j = s + 4 * t;
+    const float pj = sP[i][j] * inv;
+    const float dPt = dot16(dO, sV[j]);
+    sP[i][j] = pj;
+    sdS[i][j] = dPt;
+    rowdot = fmaf(pj, dPt, rowdot);
+  }
+  rowdot += __shfl_xor_sync(0xffffffffu, rowdot, 1);
+  rowdot += __shfl_xor_sync(0xffffffffu, rowdot, 2);
+  // ---- dS, dQs += dS k_j, column sums of dS per key column ----
+  float dq[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) dq[d] = 0.f;
+#pragma unroll 2
+  for (int t = 0; t < 36; ++t) {
+    const int ka = t / 3, j = s + 4 * t;
+    const float dS = sP[i][j] * (sdS[i][j] - rowdot);
+    sdS[i][j] = dS;
+    sC[i][j - ka * kOcOws] += dS;                       // key column kc = j - 12 ka is owned by this part alone
+    const float* kr = sK[j];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const float4 kv = *reinterpret_cast<const float4*>(kr + 4 * q4);
+      dq[4 * q4] = fmaf(dS, kv.x, dq[4 * q4]); dq[4 * q4 + 1] = fmaf(dS, kv.y, dq[4 * q4 + 1]);
+      dq[4 * q4 + 2] = fmaf(dS, kv.z, dq[4 * q4 + 2]); dq[4 * q4 + 3] = fmaf(dS, kv.w, dq[4 * q4 + 3]);
+    }
+  }
+  __syncwarp();
+  // relative-position part of dQs: this part's 3 key columns and 3 key rows (row sums over all 12 columns of the query)
+#pragma unroll
+  for (int bb = 0; bb < 3; ++bb) {
+    const int kk = s + 4 * bb;
+    const float cbv = sC[i][kk];
+    float rav = 0.f;
+#pragma unroll
+    for (int kc = 0; kc < kOcOws; ++kc) rav += sdS[i][kk * kOcOws + kc];
+    sR[i][kk] = rav;
+    const float* rw = sRw[kk - y + kOcOws - 1];
+    const float* rh = sRh[kk - x + kOcOws - 1];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) dq[d] = fmaf(cbv, rw[d], fmaf(rav, rh[d], dq[d]));
+  }
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    dq[d] += __shfl_xor_sync(0xffffffffu, dq[d], 1);
+    dq[d] += __shfl_xor_sync(0xffffffffu, dq[d], 2);
+    dq[d] *= 0.25f;                                      // qs = q / 4
+  }
+  {
+    float c4[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) c4[d] = s == 0 ? dq[d] : (s == 1 ? dq[4 + d] : (s == 2 ? dq[8 + d] : dq[12 + d]));
+    uint2 pk;
+    pk.x = pack2<T>(c4[0], c4[1]);
+    pk.y = pack2<T>(c4[2], c4[3]);
+    *reinterpret_cast<uint2*>(a.dqkv + (size_t)b * a.gbs + qpix * a.gpitch + h * kOcDh + 4 * s) = pk;
+  }
+  __syncthreads();
+  // ---- dK_j = sum_i dS_ij qs_i,  dV_j = sum_i p_ij dO_i: task = (key j, dk | dv, half of the 16 channels) ----
+  const size_t cta = ((size_t)b * nwin + blockIdx.x) * a.heads + h;
+  float* okv = a.ws_kv + cta * kObKV;
+  for (int task = tid; task < kOcKeys * 4; task += 256) {
+    const int j = task % kOcKeys, sel = task / kOcKeys;   // sel: 0 dk lo, 1 dk hi, 2 dv lo, 3 dv hi
+    const float (*coef)[kOcKeys + 1] = sel < 2 ? sdS : sP;
+    const float (*vec)[kOcDh] = sel < 2 ? sQ : sdO;
+    const int d0 = (sel & 1) * 8;
+    float acc[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+    for (int ii = 0; ii < 64; ++ii) {
+      const float cf = coef[ii][j];
+      const float4 v0 = *reinterpret_cast<const float4*>(&vec[ii][d0]), v1 = *reinterpret_cast<const float4*>(&vec[ii][d0 + 4]);
+      acc[0] = fmaf(cf, v0.x, acc[0]); acc[1] = fmaf(cf, v0.y, acc[1]); acc[2] = fmaf(cf, v0.z, acc[2]); acc[3] = fmaf(cf, v0.w, acc[3]);
+      acc[4] = fmaf(cf, v1.x, acc[4]); acc[5] = fmaf(cf, v1.y, acc[5]); acc[6] = fmaf(cf, v1.z, acc[6]); acc[7] = fmaf(cf, v1.w, acc[7]);
+    }
+    float* o = okv + (size_t)j * 32 + (sel >> 1) * 16 + d0;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  // ---- table gradients of this (window, head): task = (table, r, d) ----
+  float* orel = a.ws_rel + cta * kObRel;
+  for (int task = tid; task < kObRel; task += 256) {
+    const int d = task % kOcDh, r = (task / kOcDh) % kOcRel, tbl = task / (kOcDh * kOcRel);   // tbl 0: rel_w (columns), 1: rel_h (rows)
+    float acc = 0.f;
+    for (int ii = 0; ii < 64; ++ii) {
+      const int pos = tbl == 0 ? (ii & 7) : (ii >> 3);    // query column y / row x
+      const int kk = r + pos - (kOcOws - 1);              // key column / row with kk - pos + 11 == r
+      if (kk >= 0 && kk < kOcOws) acc = fmaf(tbl == 0 ? sC[ii][kk] : sR[ii][kk], sQ[ii][d], acc);
+    }
+    orel[task] = acc;
+  }
+}
+
+// gather: dk, dv of pixel (y, x), head h = sum over the key windows containing it.  one thread per (pixel, head, dk|dv)
+template <class T>
+__global__ void __launch_bounds__(256)
+ocab_bwd_gather_kernel(const ObArgs a, long long total) {
+  const int nw = a.W / kOcWs, nh = a.H / kOcWs, nwin = nh * nw;
+  constexpr int pad = (kOcOws - kOcWs) / 2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int sel = (int)(e & 1);
+    long long r = e >> 1;
+    const int h = (int)(r % a.heads); r /= a.heads;
+    const int x = (int)(r % a.W); r /= a.W;
+    const int y = (int)(r % a.H);
+    const int b = (int)(r / a.H);
+    float acc[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) acc[d] = 0.f;
+    // windows wy with wy*8 - pad <= y <= wy*8 - pad + 11
+    const int wy1 = min((y + pad) / kOcWs, nh - 1), wx1 = min((x + pad) / kOcWs, nw - 1);
+    for (int wy = max(wy1 - 1, 0); wy <= wy1; ++wy) {
+      const int kr = y - (wy * kOcWs - pad);
+      if (kr < 0 || kr >= kOcOws) continue;
+      for (int wx = max(wx1 - 1, 0); wx <= wx1; ++wx) {
+        const int kc = x - (wx * kOcWs - pad);
+        if (kc < 0 || kc >= kOcOws) continue;
+        const float* p = a.ws_kv + ((((size_t)b * nwin + wy * nw + wx) * a.heads + h) * kOcKeys + kr * kOcOws + kc) * 32 + sel * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(p + 4 * q);
+          acc[4 * q] += v.x; acc[4 * q + 1] += v.y; acc[4 * q + 2] += v.z; acc[4 * q + 3] += v.w;
+        }
+      }
+    }
+    unsigned short* o = a.dqkv + (size_t)b * a.gbs + ((size_t)y * a.W + x) * a.gpitch + (size_t)(1 + sel) * a.inner + h * kOcDh;
+    uint4 o0, o1;
+    o0.x = pack2<T>(acc[0], acc[1]); o0.y = pack2<T>(acc[2], acc[3]); o0.z = pack2<T>(acc[4], acc[5]); o0.w = pack2<T>(acc[6], acc[7]);
+    o1.x = pack2<T>(acc[8], acc[9]); o1.y = pack2<T>(acc[10], acc[11]); o1.z = pack2<T>(acc[12], acc[13]); o1.w = pack2<T>(acc[14], acc[15]);
+    *reinterpret_cast<uint4*>(o) = o0;
+    *reinterpret_cast<uint4*>(o + 8) = o1;
+  }
+}
+
+// reduce the per-(window, head) table partials in a fixed order: one block per table entry group
+__global__ void __launch_bounds__(256)
+ocab_bwd_rel_kernel(const float* __restrict__ ws_rel, long long nparts, float inv_scale, float* __restrict__ dst_w, float* __restrict__ dst_h) {
+  __shared__ double red[256];
+  const int e = blockIdx.x;                               // 0 .. kObRel - 1
+  double s = 0.0;
+  for (long long p = threadIdx.x; p < nparts; p += 256) s += (double)ws_rel[p * kObRel + e];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float v = (float)red[0] * inv_scale;
+    if (e < kOcRel * kOcDh) dst_w[e] = v; else dst_h[e - kOcRel * kOcDh] = v;
+  }
+}
+
 }  // namespace pir
 
 extern "C" int pir_ocab(const PirOcab* d, void* stream) {
@@ -329,4 +594,53 @@ extern "C" int pir_ocab(const PirOcab* d, void* stream) {
     else ocab_kernel<FP16><<<grid, 128, 0, s>>>(a);
   }
   return pir_check_launch("pir_ocab");
+}
+
+extern "C" int64_t pir_ocab_bwd_ws_floats(int32_t B, int32_t H, int32_t W, int32_t heads) {
+  if (B <= 0 || H <= 0 || W <= 0 || heads <= 0) return 0;
+  return (int64_t)B * (H / pir::kOcWs) * (W / pir::kOcWs) * heads * (pir::kObKV + pir::kObRel);
+}
+
+extern "C" int pir_ocab_bwd(const PirOcabBwd* d, void* stream) {
+  using namespace pir;
+  if (!d) return pir_fail(PIR_ERR_ARG, "pir_ocab_bwd: null descriptor");
+  if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->heads <= 0) return pir_fail(PIR_ERR_ARG, "pir_ocab_bwd: empty problem");
+  if (d->ws_ != kOcWs || d->ows != kOcOws || d->dim_head != kOcDh)
+    return pir_fail(PIR_ERR_UNSUPPORTED, "pir_ocab_bwd: built for window 8, overlapping window 12, head dim 16");
+  if ((d->H % kOcWs) || (d->W % kOcWs)) return pir_fail(PIR_ERR_ARG, "pir_ocab_bwd: H and W must be multiples of the window size");
+  if ((d->qkv_pitch % 8) || (d->qkv_bstride % 8) || (d->dout_pitch % 8) || (d->dout_bstride % 8) || (d->dqkv_pitch % 8) || (d->dqkv_bstride % 8) ||
+      ((uintptr_t)d->qkv & 15) || ((uintptr_t)d->dout & 15) || ((uintptr_t)d->dqkv & 15) || ((uintptr_t)d->ws & 15) || !d->qkv || !d->dout || !d->dqkv ||
+      !d->ws || !d->rel_h || !d->rel_w || !d->dst_rel_h || !d->dst_rel_w)
+    return pir_fail(PIR_ERR_ARG, "pir_ocab_bwd: tensors missing or not 16-byte aligned");
+  if (d->heads > 65535 || d->B > 65535) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_ocab_bwd: grid too large");
+  const int nwin = (d->H / kOcWs) * (d->W / kOcWs);
+  ObArgs a{};
+  a.H = d->H; a.W = d->W; a.heads = d->heads; a.inner = d->heads * kOcDh;
+  a.qkv = reinterpret_cast<const unsigned short*>(d->qkv); a.qpitch = d->qkv_pitch; a.qbs = d->qkv_bstride;
+  a.dout = reinterpret_cast<const unsigned short*>(d->dout); a.dpitch = d->dout_pitch; a.dbs = d->dout_bstride;
+  a.rel_h = d->rel_h; a.rel_w = d->rel_w;
+  a.dqkv = reinterpret_cast<unsigned short*>(d->dqkv); a.gpitch = d->dqkv_pitch; a.gbs = d->dqkv_bstride;
+  const long long nparts = (long long)d->B * nwin * d->heads;
+  a.ws_kv = d->ws;
+  a.ws_rel = d->ws + (size_t)nparts * kObKV;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const size_t smem = sizeof(float) * (2 * kOcKeys * kOcRow + 2 * kOcRel * kOcDh + 2 * 64 * kOcDh + 2 * 64 * (kOcKeys + 1) + 4 * 64 * kOcOws);
+  static bool set[2] = {false, false};
+  const int fi = d->dtype == PIR_DTYPE_BF16 ? 1 : 0;
+  if (!set[fi]) {
+    cudaError_t e = fi ? cudaFuncSetAttribute(ocab_bwd_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                       : cudaFuncSetAttribute(ocab_bwd_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return pir_fail(PIR_ERR_CUDA, "pir_ocab_bwd: cannot raise dynamic shared memory limit");
+    set[fi] = true;
+  }
+  dim3 grid((unsigned)nwin, (unsigned)d->heads, (unsigned)d->B);
+  if (fi) ocab_bwd_kernel<BF16><<<grid, 256, smem, s>>>(a); else ocab_bwd_kernel<FP16><<<grid, 256, smem, s>>>(a);
+  if (int e = pir_check_launch("pir_ocab_bwd")) return e;
+  const long long total = (long long)d->B * d->H * d->W * d->heads * 2;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (fi) ocab_bwd_gather_kernel<BF16><<<(unsigned)blocks, 256, 0, s>>>(a, total); else ocab_bwd_gather_kernel<FP16><<<(unsigned)blocks, 256, 0, s>>>(a, total);
+  if (int e = pir_check_launch("pir_ocab_bwd(gather)")) return e;
+  ocab_bwd_rel_kernel<<<kObRel, 256, 0, s>>>(a.ws_rel, nparts, d->inv_scale, d->dst_rel_w, d->dst_rel_h);
+  return pir_check_launch("pir_ocab_bwd(tables)");
 }

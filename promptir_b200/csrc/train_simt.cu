@@ -524,7 +524,8 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const SgArgs g) {
   }
 }
 
-// k2: one warp per attention row (b, r = h*c + i): softmax backward of dA (in place -> dcos), cos, rq, temperature partial.  c <= 256
+// k2: one warp per attention row (b, r = h*c + i): softmax backward of dA (in place -> dcos), cos, rq, temperature partial.  c <= 32 NT
+template <int NT>
 __global__ void __launch_bounds__(256) mdta_bwd_rows_kernel(const MbArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
@@ -534,15 +535,15 @@ __global__ void __launch_bounds__(256) mdta_bwd_rows_kernel(const MbArgs a) {
   const int h = r / c, i = r - h * c;
   const float qn = a.nrm[(size_t)b * 2 * C + r];
   const float T = a.temperature[h];
-  float dA[8], A[8], cs[8];
+  float dA[NT], A[NT], cs[NT];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {                       // dA = Wo_h^T dWf_h was left in the dcos buffer by the SGEMM
+  for (int t = 0; t < NT; ++t) {                       // dA = Wo_h^T dWf_h was left in the dcos buffer by the SGEMM
     const int j = lane + t * 32;
     dA[t] = j < c ? a.dcos[((size_t)b * C + r) * c + j] : 0.f;
   }
   float dot = 0.f;
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
+  for (int t = 0; t < NT; ++t) {
     const int j = lane + t * 32;
     A[t] = 0.f; cs[t] = 0.f;
     if (j < c) {
@@ -556,7 +557,7 @@ __global__ void __launch_bounds__(256) mdta_bwd_rows_kernel(const MbArgs a) {
   for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
   float dT = 0.f, rq = 0.f;
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
+  for (int t = 0; t < NT; ++t) {
     const int j = lane + t * 32;
     if (j < c) {
       const float dS = A[t] * (dA[t] - dot);
@@ -641,8 +642,8 @@ __global__ void __launch_bounds__(256) mdta_bwd_small_kernel(const MbArgs a) {
 // ------------------------------------------------------------------------------------------------------
 // PromptGenBlock backward.  scratch: dmix [B][S][S][D] | dw [B][L] | emb [B][C]
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bilinear_src(int y, float scale, int S, int* y0, int* y1, float* ly) {
-  const float fy = fmaxf(scale * ((float)y + 0.5f) - 0.5f, 0.f);
+__device__ __forceinline__ void bilinear_src(int y, float scale, int S, int align, int* y0, int* y1, float* ly) {
+  const float fy = align ? scale * (float)y : fmaxf(scale * ((float)y + 0.5f) - 0.5f, 0.f);
   *y0 = min((int)fy, S - 1);
   *y1 = *y0 + (*y0 < S - 1 ? 1 : 0);
   *ly = fminf(fmaxf(fy - (float)*y0, 0.f), 1.f);
@@ -652,10 +653,12 @@ __device__ __forceinline__ void bilinear_src(int y, float scale, int S, int* y0,
 template <class T>
 __global__ void __launch_bounds__(256)
 prompt_bwd_dmix_kernel(const unsigned short* __restrict__ dup, long long pitch, long long bs, int H, int W, int D, int S, float* __restrict__ dmix,
-                       long long total) {
+                       long long total, int align) {
   const int chunks = D >> 3;
-  const float sh = (float)S / (float)H, sw = (float)S / (float)W;
-  const int ry = (int)ceilf(1.0f / sh) + 1, rx = (int)ceilf(1.0f / sw) + 1;
+  const float sh = align ? (H > 1 ? (float)(S - 1) / (float)(H - 1) : 0.f) : (float)S / (float)H;
+  const float sw = align ? (W > 1 ? (float)(S - 1) / (float)(W - 1) : 0.f) : (float)S / (float)W;
+  // destination pixels whose footprint can contain a source index: within ~1/scale of its centre (the whole axis if scale is 0)
+  const int ry = sh > 0.f ? (int)ceilf(1.0f / sh) + 1 : H, rx = sw > 0.f ? (int)ceilf(1.0f / sw) + 1 : W;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int ch = (int)(e % chunks);
     long long p = e / chunks;
@@ -665,15 +668,15 @@ prompt_bwd_dmix_kernel(const unsigned short* __restrict__ dup, long long pitch, 
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const int yc = (int)(((float)s + 0.5f) / sh), xc = (int)(((float)t + 0.5f) / sw);
+    const int yc = sh > 0.f ? (int)(((float)s + (align ? 0.f : 0.5f)) / sh) : 0, xc = sw > 0.f ? (int)(((float)t + (align ? 0.f : 0.5f)) / sw) : 0;
     for (int y = max(yc - 2 * ry, 0); y <= min(yc + 2 * ry, H - 1); ++y) {
       int y0, y1; float ly;
-      bilinear_src(y, sh, S, &y0, &y1, &ly);
+      bilinear_src(y, sh, S, align, &y0, &y1, &ly);
       const float wy = (y0 == s ? 1.f - ly : 0.f) + (y1 == s ? ly : 0.f);
       if (wy == 0.f) continue;
       for (int x = max(xc - 2 * rx, 0); x <= min(xc + 2 * rx, W - 1); ++x) {
         int x0, x1; float lx;
-        bilinear_src(x, sw, S, &x0, &x1, &lx);
+        bilinear_src(x, sw, S, align, &x0, &x1, &lx);
         const float wx = (x0 == t ? 1.f - lx : 0.f) + (x1 == t ? lx : 0.f);
         if (wx == 0.f) continue;
         float f[8];
@@ -921,7 +924,7 @@ extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
   if (!d) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: null descriptor");
   if (d->B <= 0 || d->C <= 0 || d->heads <= 0 || d->splits_f <= 0 || d->splits_b <= 0) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: empty problem");
   if (d->C % d->heads) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: C must be divisible by heads");
-  if (d->C / d->heads > 256 || d->heads > 8) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_mdta_bwd: head dim > 256 or heads > 8");
+  if (d->C / d->heads > 768 || d->heads > 8) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_mdta_bwd: head dim > 768 or heads > 8");
   if (!d->ws_f || !d->ws_b || !d->temperature || !d->wo || !d->scratch || !d->wft || !d->wqk || !d->dst_wo || !d->dst_temp)
     return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: missing pointers");
   if (d->dst_bias && !d->colsum_b) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: bias gradient needs the column sums");
@@ -961,7 +964,8 @@ extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
     sgemm(g);
     if (int e = pir_check_launch("pir_mdta_bwd(dA)")) return e;
   }
-  mdta_bwd_rows_kernel<<<dim3((C + 7) / 8, B), 256, 0, s>>>(a);
+  if (c <= 256) mdta_bwd_rows_kernel<8><<<dim3((C + 7) / 8, B), 256, 0, s>>>(a);
+  else mdta_bwd_rows_kernel<24><<<dim3((C + 7) / 8, B), 256, 0, s>>>(a);
   if (int e = pir_check_launch("pir_mdta_bwd(rows)")) return e;
   mdta_bwd_cols_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(a);
   if (int e = pir_check_launch("pir_mdta_bwd(cols)")) return e;
@@ -1013,8 +1017,8 @@ extern "C" int pir_prompt_bwd(const PirPromptBwd* d, void* stream) {
   float* dlog = dw + (size_t)d->B * d->L;
   const long long total = (long long)d->B * d->S * d->S * (d->D / 8);
   auto* dup = reinterpret_cast<const unsigned short*>(d->dup);
-  PIR_BY_DTYPE(d->dtype, (prompt_bwd_dmix_kernel<BF16><<<grid_for(total), 256, 0, s>>>(dup, d->dup_pitch, d->dup_bstride, d->H, d->W, d->D, d->S, dmix, total)),
-               (prompt_bwd_dmix_kernel<FP16><<<grid_for(total), 256, 0, s>>>(dup, d->dup_pitch, d->dup_bstride, d->H, d->W, d->D, d->S, dmix, total)));
+  PIR_BY_DTYPE(d->dtype, (prompt_bwd_dmix_kernel<BF16><<<grid_for(total), 256, 0, s>>>(dup, d->dup_pitch, d->dup_bstride, d->H, d->W, d->D, d->S, dmix, total, d->align_corners)),
+               (prompt_bwd_dmix_kernel<FP16><<<grid_for(total), 256, 0, s>>>(dup, d->dup_pitch, d->dup_bstride, d->H, d->W, d->D, d->S, dmix, total, d->align_corners)));
   if (int e = pir_check_launch("pir_prompt_bwd(dmix)")) return e;
   prompt_bwd_dot_kernel<<<dim3(d->L, d->B), 256, 0, s>>>(dmix, d->prompt, n, d->L, dw);
   if (int e = pir_check_launch("pir_prompt_bwd(dot)")) return e;

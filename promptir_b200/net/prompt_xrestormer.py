@@ -2,8 +2,8 @@
 
 Same constructor arguments, parameter names / shapes / registration order (so seeded construction and `state_dict` round-trips
 are identical to the reference, prompt_xrestormer.py:366-425) and the same `forward(inp_img)` (prompt_xrestormer.py:428-478).
-The sub-modules only HOLD parameters; `forward` hands the image to `promptir_b200.xengine.XEngine`.  Inference only (the
-reference has no training script for this variant); there is no PyTorch/CPU fallback.
+The sub-modules only HOLD parameters; `forward` hands the image to `promptir_b200.xengine.XEngine` (no grad) or, with autograd
+enabled, to `promptir_b200.xtrain_engine.XTrainEngine` through one autograd node; there is no PyTorch/CPU fallback.
 """
 from __future__ import annotations
 
@@ -13,7 +13,7 @@ from typing import Dict, Tuple
 import torch
 import torch.nn as nn
 
-from .model import Downsample, FeedForward, LayerNorm, OverlapPatchEmbed, Upsample
+from .model import Downsample, FeedForward, LayerNorm, OverlapPatchEmbed, Upsample, _PromptIRFunction
 
 
 class RelPosEmb(nn.Module):                                 # prompt_xrestormer.py:48-73
@@ -117,6 +117,17 @@ class PromptXRestormer(nn.Module):
         self.compute_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[os.environ.get("PROMPTIR_B200_DTYPE", "bf16")]
         self.use_cuda_graph = os.environ.get("PROMPTIR_B200_GRAPH", "1") != "0"
         self._engines: Dict[Tuple, object] = {}
+        self._train_engine = None
+        self.grad_scale = None                              # static loss scale of the 16-bit backward (None: 1 for bf16, 65536 for fp16)
+
+    def train_engine_for(self, batch: int, height: int, width: int, device: torch.device, input_grad: bool = False):
+        from ..xtrain_engine import XTrainEngine
+        key = (batch, height, width, str(device), self.compute_dtype, input_grad, self.grad_scale)
+        if self._train_engine is None or self._train_engine[0] != key:
+            self._train_engine = None
+            self._train_engine = (key, XTrainEngine(self, batch, height, width, device, self.compute_dtype, grad_scale=self.grad_scale,
+                                                    input_grad=input_grad))
+        return self._train_engine[1]
 
     def engine_for(self, batch: int, height: int, width: int, device: torch.device):
         from ..xengine import XEngine
@@ -131,6 +142,7 @@ class PromptXRestormer(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._engines = {}
+        self._train_engine = None
         return super()._apply(fn, *a, **k)
 
     def forward(self, inp_img: torch.Tensor) -> torch.Tensor:              # prompt_xrestormer.py:428
@@ -147,9 +159,11 @@ class PromptXRestormer(nn.Module):
         if h % m or w % m:
             raise RuntimeError(f"height and width must be multiples of {m} (three 2x downsamples and {self.window_size}x{self.window_size} "
                                f"attention windows at every level), got {h}x{w}; the reference fails in rearrange for such sizes too")
-        if torch.is_grad_enabled() and (inp_img.requires_grad or any(p.requires_grad for p in self.parameters())) and self.training:
-            raise NotImplementedError("promptir_b200.PromptXRestormer: the backward is not built; run under torch.no_grad() / eval()")
-        eng = self.engine_for(b, h, w, inp_img.device)
         x = inp_img if (inp_img.dtype == torch.float32 and inp_img.is_contiguous()) else inp_img.float().contiguous()
+        if torch.is_grad_enabled() and (inp_img.requires_grad or any(p.requires_grad for p in self.parameters())):
+            eng = self.train_engine_for(b, h, w, inp_img.device, input_grad=inp_img.requires_grad)
+            out = _PromptIRFunction.apply(self, eng, x, *[p for _, p in self.named_parameters()])
+            return out if inp_img.dtype == torch.float32 else out.to(inp_img.dtype)
+        eng = self.engine_for(b, h, w, inp_img.device)
         out = eng.run(x, use_graph=self.use_cuda_graph)
         return out if inp_img.dtype == torch.float32 else out.to(inp_img.dtype)

@@ -387,6 +387,7 @@ def prompt_bwd(ws: torch.Tensor, rec: dict) -> Launch:
     d.prompt, d.weights = _f32ptr(prm, "prompt"), _f32ptr(rec["weights"], "weights")
     d.pool_ws, d.lin_w = _f32ptr(rec["pool_ws"], "pool_ws"), _f32ptr(rec["lin_w"], "lin_w")
     d.inv_scale = rec["inv_scale"]
+    d.align_corners = int(bool(rec.get("align_corners", False)))
     d.scratch, d.demb = ws.data_ptr(), _f32ptr(rec["demb"], "demb")
     d.dst_prompt, d.dst_lin_w, d.dst_lin_b = (_f32ptr(rec[k], k) for k in ("dst_prompt", "dst_lin_w", "dst_lin_b"))
     keep = (ws, dup, prm, rec["weights"], rec["pool_ws"], rec["lin_w"], rec["demb"], rec["dst_prompt"], rec["dst_lin_w"], rec["dst_lin_b"])
@@ -433,3 +434,28 @@ def ocab(qkv: torch.Tensor, rel_h: torch.Tensor, rel_w: torch.Tensor, out: torch
     d.rel_h, d.rel_w = _f32ptr(rel_h, "ocab.rel_h"), _f32ptr(rel_w, "ocab.rel_w")
     d.out, d.out_pitch, d.out_bstride = po, op, obs
     return _prepared("pir_ocab", d, (qkv, rel_h, rel_w, out))
+
+
+def ocab_bwd_ws_floats(B: int, H: int, W: int, heads: int) -> int:
+    return int(_lib.load().pir_ocab_bwd_ws_floats(B, H, W, heads))
+
+
+def ocab_bwd(ws: torch.Tensor, rec: dict) -> Launch:
+    """OCAB backward (pir_ocab_bwd): rec holds qkv, dout, rel_h, rel_w, dqkv, dst_rel_h, dst_rel_w, heads, inv_scale."""
+    qkv, dout, dqkv = rec["qkv"], rec["dout"], rec["dqkv"]
+    pq, B, H, W, C3, qp, qbs = _nhwc(qkv, "ocab_bwd.qkv")
+    pd, dB, dH, dW, inner, dp, dbs = _nhwc(dout, "ocab_bwd.dout")
+    pg, gB, gH, gW, gC, gp, gbs = _nhwc(dqkv, "ocab_bwd.dqkv")
+    heads = rec["heads"]
+    assert inner == 16 * heads and C3 == 3 * inner and (dB, dH, dW) == (B, H, W) and (gB, gH, gW, gC) == (B, H, W, C3)
+    assert ws.numel() >= ocab_bwd_ws_floats(B, H, W, heads)
+    d = _lib.PirOcabBwd()
+    d.dtype = dtype_code(qkv.dtype)
+    d.B, d.H, d.W, d.heads, d.dim_head, d.ws_, d.ows = B, H, W, heads, 16, 8, 12
+    d.qkv, d.qkv_pitch, d.qkv_bstride = pq, qp, qbs
+    d.dout, d.dout_pitch, d.dout_bstride = pd, dp, dbs
+    d.rel_h, d.rel_w = _f32ptr(rec["rel_h"], "rel_h"), _f32ptr(rec["rel_w"], "rel_w")
+    d.dqkv, d.dqkv_pitch, d.dqkv_bstride = pg, gp, gbs
+    d.ws, d.inv_scale = ws.data_ptr(), rec["inv_scale"]
+    d.dst_rel_h, d.dst_rel_w = _f32ptr(rec["dst_rel_h"], "dst_rel_h"), _f32ptr(rec["dst_rel_w"], "dst_rel_w")
+    return _prepared("pir_ocab_bwd", d, (ws, qkv, dout, dqkv, rec["rel_h"], rec["rel_w"], rec["dst_rel_h"], rec["dst_rel_w"]), kernels=3)

@@ -281,45 +281,33 @@ class TrainEngine(Engine):
 
     def _tblock(self, blk, x: Tensor, g: Tensor, x_out: Optional[Tensor] = None) -> None:
         """One TransformerBlock, forward now and its backward pushed on the stack.  net/model.py:192-196."""
+        xo = x if x_out is None else x_out
+        self._t_mdta(blk.attn, blk.norm1, x, g, xo)
+        self._t_gdfn(blk.ffn, blk.norm2, xo, g)
+
+    def _t_mdta(self, at, norm, x: Tensor, g: Tensor, xo: Tensor) -> None:
+        """xo = x + MDTA(LN(x)) (net/model.py:117-138, 193) and its backward on g (in place)."""
         dt = self.dtype
         B, h, w, c = x.shape
-        xo = x if x_out is None else x_out
-        heads = blk.attn.num_heads
-        hid = blk.ffn.project_out.in_channels
-        hp, gmap = packing.gdfn_maps(hid, self.device)
-        n1, n2, at, ff = blk.norm1.body, blk.norm2.body, blk.attn, blk.ffn
-        beta = lambda n: getattr(n, "bias", None)
+        heads = at.num_heads
+        n1 = norm.body
+        beta1 = getattr(n1, "bias", None)
         flip = lambda wt: wt.detach().flip(2, 3)
-
-        # ---- packed weights: forward and transposed (dgrad) ----
-        qkv_w, _, qkv_t = self._cached(lambda: list(packing.pack_pointwise(at.qkv.weight, dt, gamma=n1.weight, beta=beta(n1), bias=at.qkv.bias)))
+        qkv_w, _, qkv_t = self._cached(lambda: list(packing.pack_pointwise(at.qkv.weight, dt, gamma=n1.weight, beta=beta1, bias=at.qkv.bias)))
         (qkv_wT,) = self._cached(lambda: [packing.pack_pointwise((at.qkv.weight.detach().reshape(3 * c, c) * n1.weight.detach().view(1, -1)).t(), dt)[0]])
         dwq_w, dwq_f, dwq_b = self._cached(lambda: [packing.pack_depthwise(at.qkv_dwconv.weight, dt), packing.pack_depthwise(flip(at.qkv_dwconv.weight), dt),
                                                     None if at.qkv_dwconv.bias is None else at.qkv_dwconv.bias.detach().float().contiguous()])
         temp, wo, wo_b = self._cached(lambda: [at.temperature.detach().float().reshape(-1).contiguous(),
                                                at.project_out.weight.detach().float().reshape(c, c).contiguous(),
                                                None if at.project_out.bias is None else at.project_out.bias.detach().float().contiguous()])
-        pin_w, _, pin_t = self._cached(lambda: list(packing.pack_pointwise(ff.project_in.weight, dt, gamma=n2.weight, beta=beta(n2),
-                                                                           bias=ff.project_in.bias, row_map=gmap, n_total=2 * hp)))
-        (pin_wT,) = self._cached(lambda: [packing.pack_pointwise((ff.project_in.weight.detach().reshape(2 * hid, c) * n2.weight.detach().view(1, -1)).t(),
-                                                                  dt, col_map=gmap, k_total=2 * hp)[0]])
-        dwf_w, dwf_f, dwf_b = self._cached(lambda: [packing.pack_depthwise(ff.dwconv.weight, dt, chan_map=gmap, c_total=2 * hp),
-                                                    packing.pack_depthwise(flip(ff.dwconv.weight), dt, chan_map=gmap, c_total=2 * hp),
-                                                    packing.scatter_vec(ff.dwconv.bias, gmap, 2 * hp)])
-        pout_w, _, pout_t = self._cached(lambda: list(packing.pack_pointwise(ff.project_out.weight, dt, bias=ff.project_out.bias, k_total=hp)))
-        (pout_wT,) = self._cached(lambda: [packing.pack_pointwise(ff.project_out.weight.detach().reshape(c, hid).t(), dt, n_total=hp,
-                                                                   row_map=torch.arange(hid, device=self.device))[0]])
-
-        # ---- kept activations ----
         keep = lambda ch: self._zeros(B, h, w, ch)
-        xh1, xh2, qkv_pre, qkv, hid_pre, gated = keep(c), keep(c), keep(3 * c), keep(3 * c), keep(2 * hp), keep(hp)
-        rstd1, rstd2 = self._f32(B * h * w), self._f32(B * h * w)
+        xh1, qkv_pre, qkv = keep(c), keep(3 * c), keep(3 * c)
+        rstd1 = self._f32(B * h * w)
         splits = ops.mdta_splits(B, h * w, c)
         ws = self._f32(ops.mdta_ws_floats(B, c, splits))
-        self.saved_bytes += sum(t.numel() * t.element_size() for t in (xh1, xh2, qkv_pre, qkv, hid_pre, gated, rstd1, rstd2, ws))
+        self.saved_bytes += sum(t.numel() * t.element_size() for t in (xh1, qkv_pre, qkv, rstd1, ws))
         wfold = self.wfold[c]
 
-        # ---- forward ----
         self._ln_fwd(x, xh1, rstd1, "LN1")
         self._gemm(xh1, qkv_w, qkv_pre, n=3 * c, vec_t=qkv_t, tag="K1")
         self._dw(qkv_pre, dwq_w, qkv, gate=False, bias=dwq_b, tag="K2")
@@ -328,34 +316,12 @@ class TrainEngine(Engine):
         self._emit("mdta_finalize", (lambda: gram_fin[1]), qkv=qkv, heads=heads, ws=ws, splits=splits, temperature=temp, wo=wo,
                    wfold=wfold, tag="K3b")
         self._gemm(qkv[..., 2 * c:], wfold, xo, n=c, res=x, vec_t=wo_b, w_batched=True, tag="K4")
-        self._ln_fwd(xo, xh2, rstd2, "LN2")
-        self._gemm(xh2, pin_w, hid_pre, n=2 * hp, vec_t=pin_t, tag="K5")
-        self._dw(hid_pre, dwf_w, gated, gate=True, bias=dwf_b, tag="K6")
-        self._gemm(gated, pout_w, xo, n=c, res=xo, vec_t=pout_t, tag="K7")
 
-        # ---- backward ----
         def bwd():
             G = self._grad_of
-            dgt = self._scratch(self.Ta, h, w, hp)
-            y = self._scratch(self.Tb, h, w, 2 * hp)
-            dhp = self._scratch(self.Tc, h, w, 2 * hp)
             dxh = self._scratch(self.Td, h, w, c)
             dqkv = self._scratch(self.Tb, h, w, 3 * c)
             dqkv_pre = self._scratch(self.Tc, h, w, 3 * c)
-            # -- GDFN (net/model.py:94-99) --
-            self._gemm(g, pout_wT, dgt, n=hp, tag="B7d")
-            wg = self._wgrad(g, gated, colsum=ff.project_out.bias is not None, tag="B7w")
-            self._wgrad_fin(wg, dst_w=G(ff.project_out.weight).view(c, hid), dst_bias=G(ff.project_out.bias), tag="B7f")
-            self._dw(hid_pre, dwf_w, y, gate=2, bias=dwf_b, dg=dgt, tag="B6g")      # y = dw(hid_pre) recomputed, gate backward fused
-            self._dw_wgrad(hid_pre, y, dst_w=G(ff.dwconv.weight), dst_bias=G(ff.dwconv.bias), half=hid, half_pad=hp, tag="B6w")
-            self._dw(y, dwf_f, dhp, gate=False, bias=None, tag="B6d")
-            self._gemm(dhp, pin_wT, dxh, n=c, tag="B5d")
-            wg = self._wgrad(dhp, xh2, colsum=True, tag="B5w")
-            self._wgrad_fin(wg, dst_w=G(ff.project_in.weight).view(2 * hid, c), half=hid, half_pad=hp, gamma=self._raw(n2.weight),
-                            beta=self._raw(beta(n2)), w=self._raw(ff.project_in.weight), dst_gamma=G(n2.weight), dst_beta=G(beta(n2)),
-                            dst_bias=G(ff.project_in.bias), tag="B5f")
-            self._ln_bwd(dxh, xh2, rstd2, g, "BLN2")
-            # -- MDTA (net/model.py:117-138) --
             v = qkv[..., 2 * c:]
             wgv = self._wgrad(g, v, per_image=True, colsum=at.project_out.bias is not None, tag="B4w")
             wft, wqk = self.wft[c], self.wqk[c]
@@ -370,9 +336,58 @@ class TrainEngine(Engine):
             self._dw(dqkv, dwq_f, dqkv_pre, gate=False, bias=None, tag="B2d")
             self._gemm(dqkv_pre, qkv_wT, dxh, n=c, tag="B1d")
             wg = self._wgrad(dqkv_pre, xh1, colsum=True, tag="B1w")
-            self._wgrad_fin(wg, dst_w=G(at.qkv.weight).view(3 * c, c), gamma=self._raw(n1.weight), beta=self._raw(beta(n1)),
-                            w=self._raw(at.qkv.weight), dst_gamma=G(n1.weight), dst_beta=G(beta(n1)), dst_bias=G(at.qkv.bias), tag="B1f")
+            self._wgrad_fin(wg, dst_w=G(at.qkv.weight).view(3 * c, c), gamma=self._raw(n1.weight), beta=self._raw(beta1),
+                            w=self._raw(at.qkv.weight), dst_gamma=G(n1.weight), dst_beta=G(beta1), dst_bias=G(at.qkv.bias), tag="B1f")
             self._ln_bwd(dxh, xh1, rstd1, g, "BLN1")
+        self._later(bwd)
+
+    def _t_gdfn(self, ff, norm, x: Tensor, g: Tensor) -> None:
+        """x += GDFN(LN(x)) in place (net/model.py:94-99, 194) and its backward on g (in place)."""
+        dt = self.dtype
+        B, h, w, c = x.shape
+        hid = ff.project_out.in_channels
+        hp, gmap = packing.gdfn_maps(hid, self.device)
+        n2 = norm.body
+        beta2 = getattr(n2, "bias", None)
+        flip = lambda wt: wt.detach().flip(2, 3)
+        pin_w, _, pin_t = self._cached(lambda: list(packing.pack_pointwise(ff.project_in.weight, dt, gamma=n2.weight, beta=beta2,
+                                                                           bias=ff.project_in.bias, row_map=gmap, n_total=2 * hp)))
+        (pin_wT,) = self._cached(lambda: [packing.pack_pointwise((ff.project_in.weight.detach().reshape(2 * hid, c) * n2.weight.detach().view(1, -1)).t(),
+                                                                  dt, col_map=gmap, k_total=2 * hp)[0]])
+        dwf_w, dwf_f, dwf_b = self._cached(lambda: [packing.pack_depthwise(ff.dwconv.weight, dt, chan_map=gmap, c_total=2 * hp),
+                                                    packing.pack_depthwise(flip(ff.dwconv.weight), dt, chan_map=gmap, c_total=2 * hp),
+                                                    packing.scatter_vec(ff.dwconv.bias, gmap, 2 * hp)])
+        pout_w, _, pout_t = self._cached(lambda: list(packing.pack_pointwise(ff.project_out.weight, dt, bias=ff.project_out.bias, k_total=hp)))
+        (pout_wT,) = self._cached(lambda: [packing.pack_pointwise(ff.project_out.weight.detach().reshape(c, hid).t(), dt, n_total=hp,
+                                                                   row_map=torch.arange(hid, device=self.device))[0]])
+        keep = lambda ch: self._zeros(B, h, w, ch)
+        xh2, hid_pre, gated = keep(c), keep(2 * hp), keep(hp)
+        rstd2 = self._f32(B * h * w)
+        self.saved_bytes += sum(t.numel() * t.element_size() for t in (xh2, hid_pre, gated, rstd2))
+
+        self._ln_fwd(x, xh2, rstd2, "LN2")
+        self._gemm(xh2, pin_w, hid_pre, n=2 * hp, vec_t=pin_t, tag="K5")
+        self._dw(hid_pre, dwf_w, gated, gate=True, bias=dwf_b, tag="K6")
+        self._gemm(gated, pout_w, x, n=c, res=x, vec_t=pout_t, tag="K7")
+
+        def bwd():
+            G = self._grad_of
+            dgt = self._scratch(self.Ta, h, w, hp)
+            y = self._scratch(self.Tb, h, w, 2 * hp)
+            dhp = self._scratch(self.Tc, h, w, 2 * hp)
+            dxh = self._scratch(self.Td, h, w, c)
+            self._gemm(g, pout_wT, dgt, n=hp, tag="B7d")
+            wg = self._wgrad(g, gated, colsum=ff.project_out.bias is not None, tag="B7w")
+            self._wgrad_fin(wg, dst_w=G(ff.project_out.weight).view(c, hid), dst_bias=G(ff.project_out.bias), tag="B7f")
+            self._dw(hid_pre, dwf_w, y, gate=2, bias=dwf_b, dg=dgt, tag="B6g")      # y = dw(hid_pre) recomputed, gate backward fused
+            self._dw_wgrad(hid_pre, y, dst_w=G(ff.dwconv.weight), dst_bias=G(ff.dwconv.bias), half=hid, half_pad=hp, tag="B6w")
+            self._dw(y, dwf_f, dhp, gate=False, bias=None, tag="B6d")
+            self._gemm(dhp, pin_wT, dxh, n=c, tag="B5d")
+            wg = self._wgrad(dhp, xh2, colsum=True, tag="B5w")
+            self._wgrad_fin(wg, dst_w=G(ff.project_in.weight).view(2 * hid, c), half=hid, half_pad=hp, gamma=self._raw(n2.weight),
+                            beta=self._raw(beta2), w=self._raw(ff.project_in.weight), dst_gamma=G(n2.weight), dst_beta=G(beta2),
+                            dst_bias=G(ff.project_in.bias), tag="B5f")
+            self._ln_bwd(dxh, xh2, rstd2, g, "BLN2")
         self._later(bwd)
 
     # ---- down / up / reduce / prompt / ends --------------------------------------------------------------------
@@ -408,6 +423,19 @@ class TrainEngine(Engine):
             self._gemm(dconv, wT, g_x, n=conv.in_channels, taps=9, tag="Bud")
         self._later(bwd)
 
+    def _tconv3(self, conv, x, out, g_x, g_out, tag="conv3") -> None:
+        """out = conv3x3(x) (no bias), g_x = conv3x3^T(g_out) (assigned)."""
+        dt = self.dtype
+        (w, wT) = self._cached(lambda: [packing.pack_conv3x3(conv.weight, dt),
+                                        packing.pack_conv3x3(conv.weight.detach().transpose(0, 1).flip(2, 3), dt)])
+        self._gemm(x, w, out, n=conv.out_channels, taps=9, tag=tag)
+
+        def bwd():
+            wg = self._wgrad(g_out, x, taps=9, tag="B" + tag + "w")
+            self._wgrad_fin(wg, dst_w=self._grad_of(conv.weight), tag="B" + tag + "f")
+            self._gemm(g_out, wT, g_x, n=conv.in_channels, taps=9, tag="B" + tag + "d")
+        self._later(bwd)
+
     def _treduce(self, conv, x, out, g_x, g_out) -> None:
         dt = self.dtype
         w, _, t = self._cached(lambda: list(packing.pack_pointwise(conv.weight, dt, bias=conv.bias)))
@@ -421,7 +449,7 @@ class TrainEngine(Engine):
             self._gemm(g_out, wT, g_x, n=conv.in_channels, tag="Brd")
         self._later(bwd)
 
-    def _tprompt(self, pg, x, out, g_x, g_out) -> None:
+    def _tprompt(self, pg, x, out, g_x, g_out, align_corners: bool = False) -> None:
         """PromptGenBlock (model.py:226-235).  g_x receives (+=) the gradient through the global-average-pool branch."""
         dt = self.dtype
         B, h, w, cx = x.shape
@@ -434,8 +462,8 @@ class TrainEngine(Engine):
         up = self._zeros(B, h, w, d)                          # kept: resized prompt (operand of the conv's weight gradient)
         pws = self._f32(ops.prompt_ws_floats(B, h * w, cx))   # kept: pooled partial sums
         wts = self._f32(B, L)                                 # kept: softmax weights
-        self._emit("prompt", lambda: ops.prompt_gen(x, prm, lw, lb, up, pws, wts), x=x, prompt=prm, lin_w=lw, lin_b=lb, out=up, ws=pws,
-                   weights_out=wts, tag="K10")
+        self._emit("prompt", lambda: ops.prompt_gen(x, prm, lw, lb, up, pws, wts, align_corners=align_corners), x=x, prompt=prm, lin_w=lw,
+                   lin_b=lb, out=up, ws=pws, weights_out=wts, align_corners=align_corners, tag="K10")
         self._gemm(up, cw, out, n=d, taps=9, tag="prompt_conv")
 
         def bwd():
@@ -444,7 +472,8 @@ class TrainEngine(Engine):
             self._wgrad_fin(wg, dst_w=self._grad_of(pg.conv3x3.weight), tag="Bpf")
             self._gemm(g_out, cwT, dup, n=d, taps=9, tag="Bpd")
             demb = self._f32(B, cx)
-            rec = dict(dup=dup, prompt=prm, weights=wts, pool_ws=pws, lin_w=lw, HW=h * w, C=cx, demb=demb, dst_prompt=self._grad_of(pg.prompt_param),
+            rec = dict(dup=dup, prompt=prm, weights=wts, pool_ws=pws, lin_w=lw, HW=h * w, C=cx, demb=demb, align_corners=align_corners,
+                       dst_prompt=self._grad_of(pg.prompt_param),
                        dst_lin_w=self._grad_of(pg.linear_layer.weight), dst_lin_b=self._grad_of(pg.linear_layer.bias),
                        inv_scale=1.0 / self.grad_scale, tag="Bpp")
             self._wg_need = max(self._wg_need, ops.prompt_bwd_ws_floats(B, L, d, prm.shape[1]))

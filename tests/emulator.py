@@ -310,7 +310,7 @@ def emu_prompt_bwd(r):
     emb = r["pool_ws"].view(B, -1, r["C"]).sum(1) / r["HW"]
     with torch.enable_grad():
         mix = torch.zeros(B, D, S, S, device=dup.device, requires_grad=True)
-        up = F.interpolate(mix, (H, W), mode="bilinear")
+        up = F.interpolate(mix, (H, W), mode="bilinear", align_corners=bool(r.get("align_corners", False)))
         (dmix,) = torch.autograd.grad(up, mix, dup.permute(0, 3, 1, 2))
     r["dst_prompt"].copy_(torch.einsum("bl,bdst->ldst", wts, dmix).unsqueeze(0) * inv)
     dw = torch.einsum("bdst,lstd->bl", dmix, prm)
@@ -359,3 +359,21 @@ def emu_ocab(r):
 
 
 DISPATCH["ocab"] = emu_ocab
+
+
+def emu_ocab_bwd(r):
+    """pir_ocab_bwd == autograd of the attention core (oracle.xrestormer_oracle.ocab_core) w.r.t. q, k, v and the two tables."""
+    from oracle.xrestormer_oracle import ocab_core
+    qkv, dout, dqkv = r["qkv"], r["dout"], r["dqkv"]
+    with torch.enable_grad():
+        x = _nchw(qkv).detach().clone().requires_grad_(True)
+        rh, rw = r["rel_h"].detach().clone().requires_grad_(True), r["rel_w"].detach().clone().requires_grad_(True)
+        q, k, v = x.chunk(3, dim=1)
+        o = ocab_core(q, k, v, rh, rw, r["heads"])
+        gx, grh, grw = torch.autograd.grad(o, (x, rh, rw), _nchw(dout))
+    dqkv.copy_(_nhwc(gx).to(dqkv.dtype))
+    r["dst_rel_h"].copy_(grh * r["inv_scale"])
+    r["dst_rel_w"].copy_(grw * r["inv_scale"])
+
+
+DISPATCH["ocab_bwd"] = emu_ocab_bwd

@@ -111,3 +111,68 @@ def test_forward_matches_reference_golden(model, golden_dir, dt, case, seed):
 def test_errors_are_loud(model):
     with pytest.raises(RuntimeError):
         model(torch.rand(1, 3, 96, 64, device=DEV))           # not a multiple of 64
+
+
+def _small_x_model(seed=0):
+    torch.manual_seed(seed)
+    m = PromptXRestormer(num_blocks=[1, 1, 1, 2], num_refinement_blocks=1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("temperature"):
+                p.copy_(torch.rand_like(p) + 0.5)
+            elif "norm" in n and n.endswith("weight"):
+                p.copy_(torch.rand_like(p) + 0.5)
+            elif "norm" in n and n.endswith("bias"):
+                p.copy_(torch.randn_like(p) * 0.2)
+    return m
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_xtrain_engine_op_by_op(dt):
+    """Every launch of the PromptXRestormer training programs (incl. pir_ocab_bwd) against its torch restatement."""
+    from test_gpu_train import _run_ops
+    from promptir_b200.xtrain_engine import XTrainEngine
+    m = _small_x_model().to(DEV)
+    B, H, W = 2, 64, 128
+    x, _ = O.synthetic_batch(B, H, W, seed=3)
+    eng = XTrainEngine(m, B, H, W, DEV, dt, grad_scale=1.0 if dt == torch.bfloat16 else 64.0, input_grad=dt == torch.bfloat16)
+    eng.img_in.copy_(x.to(DEV))
+    s = torch.cuda.current_stream().cuda_stream
+    failures = []
+    _run_ops(eng.fwd_ops, s, failures, dt)
+    assert not failures, "forward:\n" + "\n".join(failures)
+    torch.manual_seed(5)
+    eng.d_out.copy_(torch.randn(B, 3, H, W, device=DEV) / 64)
+    _run_ops(eng.bwd_ops, s, failures, dt)
+    assert not failures, "backward:\n" + "\n".join(failures)
+
+
+@pytest.mark.parametrize("dt,per_lim,cos_lim", [(torch.bfloat16, 1e-1, 0.998), (torch.float16, 3e-2, 0.9999)])
+def test_x_loss_backward_matches_oracle_autograd(dt, per_lim, cos_lim):
+    """loss.backward() through the drop-in PromptXRestormer vs fp32 autograd of the CPU oracle (stated limits: per-tensor relative
+    L2 error 10 % / 3 %, flat-gradient cosine 0.998 / 0.9999 for bf16 / fp16)."""
+    from oracle import xrestormer_oracle as XO
+    m = _small_x_model(seed=1).to(DEV).train()
+    m.compute_dtype = dt
+    B, H, W = 1, 64, 64
+    x, clean = O.synthetic_batch(B, H, W, seed=7)
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    ref_loss = torch.nn.functional.l1_loss(XO.xrestormer_forward(sd, x, num_blocks=(1, 1, 1, 2), num_refinement_blocks=1), clean)
+    ref_loss.backward()
+    loss = torch.nn.functional.l1_loss(m(x.to(DEV)), clean.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 2e-2 * abs(ref_loss.item()) + 1e-4
+    fg, fr, worst = [], [], (0.0, "")
+    gmax = max(v.grad.norm().item() for v in sd.values())
+    for n, p in m.named_parameters():
+        g, r = p.grad.detach().cpu().float(), sd[n].grad
+        assert torch.isfinite(g).all(), n
+        if r.norm().item() > 1e-3 * gmax:
+            worst = max(worst, (((g - r).norm() / r.norm()).item(), n))
+        fg.append(g.reshape(-1))
+        fr.append(r.reshape(-1))
+    fg, fr = torch.cat(fg), torch.cat(fr)
+    cos = torch.nn.functional.cosine_similarity(fg, fr, dim=0).item()
+    print(f"[x train parity] {dt}: loss {loss.item():.5f} (oracle {ref_loss.item():.5f}) flat-grad cos {cos:.6f} "
+          f"rel-L2 {((fg - fr).norm() / fr.norm()).item():.4f} worst tensor {worst[1]} {worst[0]:.4f}")
+    assert cos >= cos_lim and worst[0] <= per_lim, (cos, worst)

@@ -54,3 +54,34 @@ def test_errors_are_loud(model):
         model(torch.rand(1, 3, 64, 64))                       # CPU tensor: no fallback
     with pytest.raises(ValueError):
         XEngine(model, 1, 96, 64, "cpu", torch.float32)       # not a multiple of 64
+
+
+def test_backward_program_matches_autograd():
+    """XTrainEngine (forward + hand-derived backward, incl. the OCAB backward and the PromptBlock wiring) emulated in fp32 vs autograd."""
+    from promptir_b200.xtrain_engine import XTrainEngine
+    from oracle import promptir_oracle as O
+    torch.manual_seed(0)
+    m = PromptXRestormer(num_blocks=[1, 1, 1, 2], num_refinement_blocks=1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("temperature"):
+                p.copy_(torch.rand_like(p) + 0.5)
+            elif "norm" in n and n.endswith("weight"):
+                p.copy_(torch.rand_like(p) + 0.5)
+            elif "norm" in n and n.endswith("bias"):
+                p.copy_(torch.randn_like(p) * 0.2)
+    B, H, W = 1, 64, 128
+    x, _ = O.synthetic_batch(B, H, W, seed=3)
+    torch.manual_seed(5)
+    d_out = torch.randn(B, 3, H, W) / (3 * H * W)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    xin = x.clone().requires_grad_(True)
+    ref_out = XO.xrestormer_forward(sd, xin, num_blocks=(1, 1, 1, 2), num_refinement_blocks=1)
+    ref_out.backward(d_out)
+    eng = XTrainEngine(m, B, H, W, "cpu", torch.float32, input_grad=True)
+    out, grads = emulator.run_train(eng, x, d_out)
+    assert (out - ref_out.detach()).abs().max().item() < 3e-5
+    assert all(v.grad is not None for v in sd.values())               # no dead parameters in this network
+    worst = max((((grads[n] - v.grad).norm() / v.grad.norm().clamp_min(1e-30)).item(), n) for n, v in sd.items())
+    assert worst[0] < 3e-4, worst
+    assert ((eng.d_img - xin.grad).norm() / xin.grad.norm()).item() < 3e-4
