@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--adamw", action="store_true", help="include torch.optim.AdamW(fused=True).step() in the timed step")
     ap.add_argument("--cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
+    ap.add_argument("--model", default="promptir", choices=["promptir", "xrestormer"], help="xrestormer: the PromptXRestormer variant (side % 64 == 0)")
     ap.add_argument("--ops-file", default="", help="write the per-launch timing list (tag, kind, shape, ms) here")
     args = ap.parse_args()
     real_stdout = os.dup(1)          # libraries (NCCL banner) print to fd 1: keep stdout for the one JSON line
@@ -57,7 +58,12 @@ def main():
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[args.dtype]
     B, S = args.batch, args.side
     torch.manual_seed(0)
-    net = PromptIR(decoder=True).to(dev).train()
+    if args.model == "xrestormer":
+        from promptir_b200 import PromptXRestormer
+        from promptir_b200.xtrain_engine import XTrainEngine as TrainEngine      # noqa: F811
+        net = PromptXRestormer().to(dev).train()
+    else:
+        net = PromptIR(decoder=True).to(dev).train()
     net.compute_dtype = dt
     x, y = synth.synthetic_batch(B, S, S, seed=1 + rank)
     x, y = x.to(dev), y.to(dev)
@@ -168,10 +174,15 @@ def main():
         torch.set_num_threads(cores)
         sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
         xc, yc = x[:1].cpu(), y[:1].cpu()
+        if args.model == "xrestormer":
+            from oracle import xrestormer_oracle as XO
+            fwd = XO.xrestormer_forward
+        else:
+            fwd = O.promptir_forward
         times = []
         for i in range(3):
             t0 = time.perf_counter()
-            F.l1_loss(O.promptir_forward(sd, xc), yc).backward()
+            F.l1_loss(fwd(sd, xc), yc).backward()
             times.append(time.perf_counter() - t0)
         sec = statistics.median(times[1:])
         cpu = {"value": S * S / 1e6 / sec, "unit": "MP/s", "cores": cores, "kind": "port",
@@ -180,10 +191,10 @@ def main():
     if rank == 0:
         mp = world * B * S * S / 1e6
         os.write(real_stdout, (json.dumps({
-            "metric": "promptir_train_step_megapixels_per_sec", "value": mp / (ms_eng / 1e3), "unit": "MP/s", "n_gpus": world,
+            "metric": ("prompt_xrestormer" if args.model == "xrestormer" else "promptir") + "_train_step_megapixels_per_sec", "value": mp / (ms_eng / 1e3), "unit": "MP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_eng, "higher_is_better": True, "scaling": "weak",
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"PromptIR training step (forward + L1 loss + backward{' + AdamW' if args.adamw else ''}), "
+            "config": {"workload": f"{'PromptXRestormer' if args.model == 'xrestormer' else 'PromptIR'} training step (forward + L1 loss + backward{' + AdamW' if args.adamw else ''}), "
                                    f"{S}x{S} patches, batch {B} per GPU (BASELINE.json configs[3])",
                        "parallelism": f"data parallel over {world} GPU(s), one NCCL all-reduce of the flat fp32 gradient buffer per step"},
             "images_per_sec": world * B / (ms_eng / 1e3), "ms_forward": ms_fwd, "ms_backward": ms_bwd,
