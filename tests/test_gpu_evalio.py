@@ -40,3 +40,23 @@ def test_add_gaussian_noise_statistics():
         assert not torch.equal(out, evalio.add_gaussian_noise(clean, sigma, seed=sigma + 1))
     dark = evalio.add_gaussian_noise(torch.zeros(1, 3, 64, 64, device=DEV), 25, seed=1)
     assert 0.4 < (dark == 0).float().mean().item() < 0.6                                                      # clip at 0
+
+
+def test_eval_loop_matches_host_scoring():
+    """The on-device evaluation step (noise -> pad -> forward -> crop -> score) against the same images scored by the oracle on the host."""
+    from promptir_b200 import PromptIR, synth
+    torch.manual_seed(0)
+    net = PromptIR(decoder=True).eval().to(DEV)
+    net.compute_dtype = torch.float16
+    _, clean = synth.synthetic_batch(2, 70, 100, seed=5)
+    clean = clean.to(DEV)
+    with torch.no_grad():
+        degrad = evalio.add_gaussian_noise(clean * 255.0, 25.0, seed=3)
+        padded, h, w = evalio.pad_to_64(degrad)
+        assert padded.shape[-2:] == (128, 128) and (h, w) == (70, 100)
+        restored = net(padded)[:, :, :h, :w]
+        p, s, n = evalio.compute_psnr_ssim(restored, clean)
+    pr, sr, nr = EO.compute_psnr_ssim(restored.cpu(), clean.cpu())
+    assert n == nr == 2 and abs(p - pr) <= 1e-4 and abs(s - sr) <= 2e-5
+    pd, sd_, _ = evalio.compute_psnr_ssim(degrad, clean)
+    assert 19.5 < pd < 21.5                                   # sigma 25 on [0, 255] is ~20.2 dB before clipping effects
