@@ -58,9 +58,6 @@ class TrainEngine(Engine):
     # ------------------------------------------------------------------------------------------------
     # helpers
     # ------------------------------------------------------------------------------------------------
-    def _empty(self, *shape, dtype=None) -> Tensor:
-        return torch.zeros(*shape, dtype=dtype or self.dtype, device=self.device)
-
     def _f32(self, *shape) -> Tensor:
         return torch.zeros(*shape, dtype=torch.float32, device=self.device)
 
@@ -242,8 +239,11 @@ class TrainEngine(Engine):
         self._gemm(self.dec1, ow, self.out, n=oc.out_channels, taps=9, out_mode=OUT_FINAL_NCHW32, vec_t=ob, img=self.img_in, tag="output")
         self._later(lambda: self._output_bwd(oc))
 
-        # ================================ backward program ===============================================
-        # pass 1 (dry): size the shared workspace; pass 2: emit the records and prepare the launches against it
+        self._finish_build()
+
+    def _finish_build(self) -> None:
+        """Emit the backward program from the closures the forward construction left on the stack (in reverse), after a dry pass that
+        sizes the shared fp32 workspace of the weight-gradient kernels."""
         npk = len(self._packers)
         self.ops, self._dry = [], True
         for fn in reversed(self._bwd_stack):

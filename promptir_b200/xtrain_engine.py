@@ -10,7 +10,7 @@ gradients and the flat gradient buffer are shared); this file adds the X block's
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List
+from typing import Callable, Dict, List  # noqa: F401
 
 import torch
 
@@ -131,32 +131,6 @@ class XTrainEngine(TrainEngine):
         self._gemm(self.dec1, ow, self.out, n=oc.out_channels, taps=9, out_mode=OUT_FINAL_NCHW32, vec_t=ob, img=self.img_in, tag="output")
         self._later(lambda: self._output_bwd(oc))
         self._finish_build()
-
-    def _finish_build(self) -> None:
-        """Size the shared workspace with a dry pass over the backward closures, then emit the backward program."""
-        npk = len(self._packers)
-        self.ops, self._dry = [], True
-        for fn in reversed(self._bwd_stack):
-            fn()
-        del self._packers[npk:]
-        self.wg_ws = self._f32(max(self._wg_need, 1))
-        self.ops, self._dry = [], False
-        self.bwd_ops = self.ops
-        for fn in reversed(self._bwd_stack):
-            fn()
-        self._bwd_stack = []
-        self.ops = self.fwd_ops + self.bwd_ops
-        written = set()
-        for r in self.bwd_ops:
-            for k, v in r.items():
-                if k.startswith("dst_") and v is not None:
-                    written.add(v.data_ptr())
-        self.live_params = {n for n, gview in self.grads.items() if gview.data_ptr() in written}
-        self.generation = 0
-        self._param_version = self._current_version()
-        self.fwd_launches = [r["launch"] for r in self.fwd_ops]
-        self.bwd_launches = [r["launch"] for r in self.bwd_ops]
-        self.launches = self.fwd_launches
 
     # ---- X blocks --------------------------------------------------------------------------------------------------------
     def _txstage(self, mod, x: Tensor, g: Tensor, first_out=None) -> None:
