@@ -611,7 +611,8 @@ __global__ void __launch_bounds__(256) mdta_bwd_weights_kernel(const MbArgs a, u
       if (k < C) { if (k / c == jg / c) v = a.dcos[((size_t)b * C + k) * c + jg % c] / (nrm[k] * nrm[C + jg]); }
       else if (k == n) v = -a.rk[(size_t)b * C + jg];
     }
-    wqk[((size_t)b * 2 * C + n) * kpad2 + k] = to16<T>(v);
+    // fp16 storage: 1 / (|q| |k|) factors of degenerate (single-pixel) levels times the loss scale can leave the fp16 range -> saturate
+    wqk[((size_t)b * 2 * C + n) * kpad2 + k] = to16<T>(T::kFmt ? v : fminf(fmaxf(v, -65504.f), 65504.f));
   }
 }
 

@@ -242,3 +242,23 @@ def test_gate_bwd_kernel(dt):
     failures = []
     _compare("gate_bwd", y, ref, failures)
     assert not failures, failures
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 8), (3, 16, 40), (1, 8, 136)])
+def test_training_extreme_shapes(shape):
+    """Smallest legal images (latent = one pixel), thin strips, odd batches: gradients vs fp32 autograd of the oracle."""
+    B, H, W = shape
+    m = perturbed_model(seed=3).to(DEV).train()
+    # 8 x 8: the level-4 attention normalises over ONE pixel, so 1 / (|q| |k|) is unbounded; with fp16's loss scale that leaves the fp16
+    # range (saturated, i.e. clipped gradients) -- bf16, the training default, has the range
+    m.compute_dtype = torch.bfloat16 if H * W == 64 else torch.float16
+    x, clean = O.synthetic_batch(B, H, W, seed=H * W)
+    ref_loss, ref = _oracle_grads(m, x, clean)
+    loss = torch.nn.functional.l1_loss(m(x.to(DEV)), clean.to(DEV))
+    loss.backward()
+    fg = torch.cat([p.grad.reshape(-1).cpu() for n, p in m.named_parameters() if ref[n] is not None])
+    fr = torch.cat([ref[n].reshape(-1) for n, p in m.named_parameters() if ref[n] is not None])
+    assert torch.isfinite(fg).all()
+    rel = ((fg - fr).norm() / fr.norm()).item()
+    print(f"[train extreme] {shape}: loss {loss.item():.5f} vs {ref_loss:.5f}, flat-gradient rel-L2 {rel:.4f}")
+    assert abs(loss.item() - ref_loss) <= 2e-2 * abs(ref_loss) + 1e-4 and rel <= (8e-2 if H * W == 64 else 2e-2)
