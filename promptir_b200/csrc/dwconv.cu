@@ -57,10 +57,12 @@ dwconv_plain_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
     mbar_expect_tx(bar_a[buf], TILE_BYTES);
     tma_load_4d(smem_u32(dw_smem) + buf * TILE_BYTES, &tmIn, bar_a[buf], c0, (r % a.tiles_x) * kDwTW - 1, (r / a.tiles_x) * TH - 1, b);
   };
+  pdl_launch_dependents();
   if (tid == 0) {
     mbar_init(bar_a[0], 1);
     mbar_init(bar_a[1], 1);
     fence_barrier_init();
+    pdl_wait();
     if ((int)blockIdx.x < a.n_sp) issue(blockIdx.x, 0);
   }
   // taps for this thread's 8 channels, kept as packed 16-bit pairs (9 x 4 registers)
@@ -83,6 +85,7 @@ dwconv_plain_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
     for (int t = 0; t < 9; ++t) wt[t] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();                 // barrier init visible to all waiters
+  pdl_wait();
 
   int it = 0;
   for (int sp = blockIdx.x; sp < a.n_sp; sp += gridDim.x, ++it) {
@@ -174,10 +177,12 @@ dwconv_gate_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
     tma_load_4d(dst, &tmIn, bar_a[buf], c0, xx, yy, b);
     tma_load_4d(dst + HALF_BYTES, &tmIn, bar_a[buf], a.C + c0, xx, yy, b);
   };
+  pdl_launch_dependents();
   if (tid == 0) {
     mbar_init(bar_a[0], 1);
     mbar_init(bar_a[1], 1);
     fence_barrier_init();
+    pdl_wait();
     if ((int)blockIdx.x < a.n_sp) issue(blockIdx.x, 0);
   }
   const int c = c0 + cg * 4;
@@ -201,6 +206,7 @@ dwconv_gate_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
     for (int t = 0; t < 9; ++t) { w1[t] = make_uint2(0, 0); w2[t] = make_uint2(0, 0); }
   }
   __syncthreads();
+  pdl_wait();
 
   int it = 0;
   for (int sp = blockIdx.x; sp < a.n_sp; sp += gridDim.x, ++it) {
@@ -329,8 +335,8 @@ static int launch_dwconv(const PirDwConv* d, cudaStream_t stream) {
     }
     const int chunks = (d->C + 31) / 32;
     dim3 grid((unsigned)workers_for(chunks, 2), (unsigned)chunks, 1);
-    if (bw) dwconv_gate_kernel<T, TH, true><<<grid, 256, smem, stream>>>(tm, a);
-    else dwconv_gate_kernel<T, TH, false><<<grid, 256, smem, stream>>>(tm, a);
+    if (bw) pir_launch(dwconv_gate_kernel<T, TH, true>, grid, dim3(256), smem, stream, tm, a);
+    else pir_launch(dwconv_gate_kernel<T, TH, false>, grid, dim3(256), smem, stream, tm, a);
   } else {
     const bool use48 = (d->C % 64 != 0) && (d->C % 48 == 0);
     const int cc = use48 ? 48 : 64;
@@ -342,10 +348,10 @@ static int launch_dwconv(const PirDwConv* d, cudaStream_t stream) {
     static bool set[2][2] = {{false, false}, {false, false}};
     if (use48) {
       if (!set[T::kFmt][0]) { cudaFuncSetAttribute(dwconv_plain_kernel<T, 6, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set[T::kFmt][0] = true; }
-      dwconv_plain_kernel<T, 6, TH><<<grid, 6 * 32, smem, stream>>>(tm, a);
+      pir_launch(dwconv_plain_kernel<T, 6, TH>, grid, dim3(6 * 32), smem, stream, tm, a);
     } else {
       if (!set[T::kFmt][1]) { cudaFuncSetAttribute(dwconv_plain_kernel<T, 8, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set[T::kFmt][1] = true; }
-      dwconv_plain_kernel<T, 8, TH><<<grid, 8 * 32, smem, stream>>>(tm, a);
+      pir_launch(dwconv_plain_kernel<T, 8, TH>, grid, dim3(8 * 32), smem, stream, tm, a);
     }
   }
   return pir_check_launch("pir_dwconv3x3");

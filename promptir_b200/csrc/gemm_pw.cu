@@ -96,10 +96,12 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     svec[i] = (g.ln_s && i < g.N) ? g.ln_s[i] : 0.f;
     svec[g.n_alloc + i] = (g.vec_t && i < g.N) ? g.vec_t[i] : 0.f;
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();                                    // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ========================================= TMA producer ==========================================
@@ -419,7 +421,7 @@ static int launch_pw(const PirGemm* d, cudaStream_t stream) {
   }
   const int total_tiles = d->B * g.m_tiles;
   const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
-  gemm_pw_kernel<T><<<grid, kPwThreads, smem, stream>>>(tmA, tmB, tmO, tmR, g);
+  if (pir_launch(gemm_pw_kernel<T>, dim3(grid), dim3(kPwThreads), smem, stream, tmA, tmB, tmO, tmR, g) != cudaSuccess) {}
   return pir_check_launch("pir_gemm(pw)");
 }
 

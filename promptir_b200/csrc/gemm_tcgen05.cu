@@ -93,10 +93,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)g.tmem_cols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();                                    // the prologue above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================================== TMA producer ==========================================
@@ -376,7 +378,7 @@ static int launch_gemm(const PirGemm* d, cudaStream_t stream) {
     attr_set[T::kFmt] = true;
   }
   dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)d->B);
-  gemm_kernel<T><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, g);
+  pir_launch(gemm_kernel<T>, grid, dim3(kGemmThreads), smem, stream, tmA, tmB, g);
   return pir_check_launch("pir_gemm");
 }
 

@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -62,6 +63,11 @@ int pir_make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void
                     (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
                     rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
   return PIR_OK;
+}
+
+bool pir_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("PIR_PDL"); return e && e[0] == '1'; }();
+  return on;
 }
 
 extern "C" int pir_abi_version(void) { return PIR_ABI_VERSION; }

@@ -78,10 +78,12 @@ mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
     tmem_alloc(smem_u32(&tmem_base_smem), tmem_cols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
 
   if (warp == 0) {
     int stage = 0;
@@ -273,6 +275,8 @@ template <int NT>
 __global__ void __launch_bounds__(256)
 mdta_softmax_kernel(const float* __restrict__ ws_gram, const float* __restrict__ ws_norm, const float* __restrict__ temperature,
                     float* __restrict__ attn, int C, int heads, int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;         // global q channel
   const int b = blockIdx.y;
@@ -326,6 +330,8 @@ mdta_fold_kernel(const float* __restrict__ wo, const float* __restrict__ attn, u
                  int heads, int kpad) {
   __shared__ float sW[32][33];
   __shared__ float sA[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = C / heads;
   const int jt_per_head = (c + 31) / 32;
   const int h = blockIdx.y / jt_per_head;
@@ -394,7 +400,7 @@ static int launch_gram(const PirMdta* d, cudaStream_t stream) {
     set[T::kFmt] = true;
   }
   dim3 grid((unsigned)(gram_nblocks_m(d->C) * g.nblocks_n), (unsigned)d->splits, (unsigned)d->B);
-  mdta_gram_kernel<T><<<grid, kGramThreads, smem, stream>>>(tm, g);
+  pir_launch(mdta_gram_kernel<T>, grid, dim3(kGramThreads), smem, stream, tm, g);
   return pir_check_launch("pir_mdta_gram");
 }
 
@@ -446,14 +452,14 @@ extern "C" int pir_mdta_finalize(const PirMdta* d, void* stream) {
   const float* ws_gram = d->ws;
   const float* ws_norm = d->ws + (size_t)d->B * d->splits * d->C * c;
   float* attn = d->ws + (size_t)d->B * d->splits * ((size_t)d->C * c + 2 * d->C);
-  if (c <= 256) pir::mdta_softmax_kernel<8><<<dim3((d->C + 7) / 8, d->B), 256, 0, s>>>(ws_gram, ws_norm, d->temperature, attn, d->C, d->heads, d->splits);
-  else pir::mdta_softmax_kernel<24><<<dim3((d->C + 7) / 8, d->B), 256, 0, s>>>(ws_gram, ws_norm, d->temperature, attn, d->C, d->heads, d->splits);
+  if (c <= 256) pir_launch(pir::mdta_softmax_kernel<8>, dim3((d->C + 7) / 8, d->B), dim3(256), 0, s, ws_gram, ws_norm, d->temperature, attn, d->C, d->heads, d->splits);
+  else pir_launch(pir::mdta_softmax_kernel<24>, dim3((d->C + 7) / 8, d->B), dim3(256), 0, s, ws_gram, ws_norm, d->temperature, attn, d->C, d->heads, d->splits);
   if (int e = pir_check_launch("pir_mdta_finalize(softmax)")) return e;
   const int kpad = (d->C + 63) / 64 * 64;
   dim3 grid((d->C + 31) / 32, d->heads * ((c + 31) / 32), d->B);
   if (d->dtype == PIR_DTYPE_BF16)
-    pir::mdta_fold_kernel<pir::BF16><<<grid, dim3(32, 8), 0, s>>>(d->wo, attn, reinterpret_cast<unsigned short*>(d->wfold), d->C, d->heads, kpad);
+    pir_launch(pir::mdta_fold_kernel<pir::BF16>, grid, dim3(32, 8), 0, s, d->wo, attn, reinterpret_cast<unsigned short*>(d->wfold), d->C, d->heads, kpad);
   else
-    pir::mdta_fold_kernel<pir::FP16><<<grid, dim3(32, 8), 0, s>>>(d->wo, attn, reinterpret_cast<unsigned short*>(d->wfold), d->C, d->heads, kpad);
+    pir_launch(pir::mdta_fold_kernel<pir::FP16>, grid, dim3(32, 8), 0, s, d->wo, attn, reinterpret_cast<unsigned short*>(d->wfold), d->C, d->heads, kpad);
   return pir_check_launch("pir_mdta_finalize(fold)");
 }

@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256)
 pool_partial_kernel(const unsigned short* __restrict__ x, long long pitch, long long bstride, int HW, int C, int chunk,
                     float* __restrict__ partial) {
   extern __shared__ float sred[];            // [PL][C]
+  pdl_launch_dependents();
+  pdl_wait();
   const int groups = C >> 3;
   const int PL = blockDim.x / groups;
   const int cg = threadIdx.x % groups;
@@ -55,6 +57,8 @@ prompt_mix_kernel(const float* __restrict__ partial, int nchunks, int HW, int C,
                   unsigned short* __restrict__ out, long long pitch, long long bstride, float* __restrict__ weights_out, int align) {
   extern __shared__ float semb[];            // [C]
   __shared__ float slog[kMaxL];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   // pooled mean: every block re-derives it from the per-chunk partials (up to 64 of them): spread the chain over 4 threads per channel
   // with two accumulators each -- it is pure L2 latency, and every block of the grid pays it
@@ -147,15 +151,15 @@ static int launch_prompt(const PirPrompt* d, cudaStream_t s) {
   if (groups > 256) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_prompt_gen: C > 2048");
   const int PL = 256 / groups;
   const int threads = PL * groups;
-  pool_partial_kernel<T><<<dim3(nchunks, d->B), threads, (size_t)PL * d->C * sizeof(float), s>>>(
-      reinterpret_cast<const unsigned short*>(d->x), d->x_pitch, d->x_bstride, HW, d->C, chunk, d->ws);
+  pir_launch(pool_partial_kernel<T>, dim3(nchunks, d->B), dim3(threads), (size_t)PL * d->C * sizeof(float), s,
+             reinterpret_cast<const unsigned short*>(d->x), d->x_pitch, d->x_bstride, HW, d->C, chunk, d->ws);
   if (int e = pir_check_launch("pir_prompt_gen(pool)")) return e;
   const long long total = (long long)HW * (d->D / 8);
   // every block re-derives the component weights from the pooled partials, so keep the grid to a few blocks per SM in total
   int blocks = (int)((total + 255) / 256);
   const int cap = (148 * 4 + d->B - 1) / d->B;
   if (blocks > cap) blocks = cap;
-  prompt_mix_kernel<T><<<dim3(blocks, d->B), 256, 5 * d->C * sizeof(float), s>>>(
+  pir_launch(prompt_mix_kernel<T>, dim3(blocks, d->B), dim3(256), 5 * d->C * sizeof(float), s,
       d->ws, nchunks, HW, d->C, d->lin_w, d->lin_b, d->L, d->prompt, d->D, d->S, d->H, d->W,
       reinterpret_cast<unsigned short*>(d->out), d->out_pitch, d->out_bstride, d->weights_out, d->align_corners);
   return pir_check_launch("pir_prompt_gen(mix)");
@@ -218,7 +222,9 @@ patch_embed_px_kernel(const float* __restrict__ img, const float* __restrict__ w
     const int co = e % COUT, k = e / COUT;
     sw[k][co] = w[(size_t)co * CIN * 9 + k];
   }
+  pdl_launch_dependents();
   __syncthreads();
+  pdl_wait();                                   // (the output buffer may still be read by the previous forward's tail)
   const int b = blockIdx.y;
   const float* ib = img + (size_t)b * CIN * H * W;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < (long long)H * W; p += (long long)gridDim.x * blockDim.x) {
@@ -262,8 +268,8 @@ static int launch_patch_embed(const PirPatchEmbed* d, cudaStream_t s) {
     long long gx = (hw + 127) / 128;
     const long long cap = (148 * 12 + d->B - 1) / d->B;
     if (gx > cap) gx = cap;
-    patch_embed_px_kernel<T, 3, 48><<<dim3((unsigned)gx, d->B), 128, 0, s>>>(d->img, d->w, d->bias, d->H, d->W,
-                                                                          reinterpret_cast<unsigned short*>(d->out), d->out_pitch, d->out_bstride);
+    pir_launch(patch_embed_px_kernel<T, 3, 48>, dim3((unsigned)gx, d->B), dim3(128), 0, s, d->img, d->w, d->bias, d->H, d->W,
+               reinterpret_cast<unsigned short*>(d->out), d->out_pitch, d->out_bstride);
     return pir_check_launch("pir_patch_embed");
   }
   const int groups = d->Cout / 8;

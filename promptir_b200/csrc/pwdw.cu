@@ -187,10 +187,13 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       seed[g.n_chunks * 32 + i] = __half_as_ushort(__float2half_rn(bias + tsum));
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();                                    // barrier init, TMEM allocation and the staging of the (static) depthwise taps / seeds above
+                                                 // overlapped the previous kernel's tail; x itself is only read from here on
   const int per_img = g.tiles_x * g.tiles_y;
   const int n_super = (g.n_chunks + g.scb - 1) / g.scb;
   const int scb = g.scb;                                                   // chunks per super-chunk
@@ -646,7 +649,7 @@ static int launch_cfg(const FwPlan& p, const CUtensorMap& tmA, const CUtensorMap
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = p.g.n_items < num_sms ? p.g.n_items : num_sms;
-  pwdw_kernel<T, Cfg><<<grid, kFwThreads, p.smem, stream>>>(tmA, tmB, p.g);
+  pir_launch(pwdw_kernel<T, Cfg>, dim3(grid), dim3(kFwThreads), p.smem, stream, tmA, tmB, p.g);
   return pir_check_launch("pir_pwdw");
 }
 
