@@ -414,18 +414,33 @@ dw_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
+// 32 consecutive (tap, channel) elements x 8 partial lanes per block: the serial chain over the per-CTA partials is parts / 8 long
 __global__ void __launch_bounds__(256)
 dw_wgrad_fin_kernel(const float* __restrict__ ws, int parts, int C, int R, int half, int half_pad, float inv_scale, float* __restrict__ dst_w,
                     float* __restrict__ dst_bias) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= R * 10) return;
-  const int r = e / 10, t = e % 10;
+  __shared__ float red[8][33];
+  const int le = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + le;                  // element = t * R + r  (rows fastest: consecutive channels -> coalesced)
+  const bool ok = e < R * 10;
+  const int t = ok ? e / R : 0, r = ok ? e % R : 0;
   const int pr = r < half ? r : r - half + half_pad;
-  float s = 0.f;
-  for (int p = 0; p < parts; ++p) s += ws[((size_t)p * 10 + t) * C + pr];
-  s *= inv_scale;
-  if (t < 9) dst_w[(size_t)r * 9 + t] = s;
-  else if (dst_bias) dst_bias[r] = s;
+  float s0 = 0.f, s1 = 0.f;
+  if (ok) {
+    const float* p0 = ws + (size_t)t * C + pr;
+    int p = sl;
+    for (; p + 8 < parts; p += 16) { s0 += p0[(size_t)p * 10 * C]; s1 += p0[(size_t)(p + 8) * 10 * C]; }
+    if (p < parts) s0 += p0[(size_t)p * 10 * C];
+  }
+  red[sl][le] = s0 + s1;
+  __syncthreads();
+  if (sl == 0 && ok) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][le];
+    s *= inv_scale;
+    if (t < 9) dst_w[(size_t)r * 9 + t] = s;
+    else if (dst_bias) dst_bias[r] = s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -910,7 +925,7 @@ extern "C" int pir_dw_wgrad(const PirDwWgrad* d, void* stream) {
   if ((d->R > d->half ? d->R - d->half + d->half_pad : d->R) > d->C) return pir_fail(PIR_ERR_ARG, "pir_dw_wgrad: parameter larger than the tensor");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (int e = d->dtype == PIR_DTYPE_BF16 ? launch_dw_wgrad<BF16>(d, s) : launch_dw_wgrad<FP16>(d, s)) return e;
-  dw_wgrad_fin_kernel<<<(unsigned)((d->R * 10 + 255) / 256), 256, 0, s>>>(d->ws, d->parts, d->C, d->R, d->half, d->half_pad, d->inv_scale, d->dst_w,
+  dw_wgrad_fin_kernel<<<(unsigned)((d->R * 10 + 31) / 32), 256, 0, s>>>(d->ws, d->parts, d->C, d->R, d->half, d->half_pad, d->inv_scale, d->dst_w,
                                                                          d->dst_bias);
   return pir_check_launch("pir_dw_wgrad(finalize)");
 }

@@ -273,45 +273,75 @@ __device__ __forceinline__ float sum_parts(const float* p, size_t stride, int P)
   return (s0 + s1) + (s2 + s3);
 }
 
-// one thread per (r, k): all taps.  grid.x covers R*Cc.
+// plain weights: 32 consecutive (r, k) elements x 8 split lanes per block, all taps
 __global__ void __launch_bounds__(256)
 wgrad_fin_kernel(const PirWgradFin f) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)f.R * f.Cc) return;
-  const int r = (int)(e / f.Cc), k = (int)(e % f.Cc);
+  __shared__ float red[8][33];
+  const int le = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const long long e = (long long)blockIdx.x * 32 + le;
+  const bool ok = e < (long long)f.R * f.Cc;
+  const int r = ok ? (int)(e / f.Cc) : 0, k = ok ? (int)(e % f.Cc) : 0;
   const int pr = prow_of(r, f.half, f.half_pad);
   const size_t pstride = (size_t)f.taps * f.M * f.N;
   for (int t = 0; t < f.taps; ++t) {
-    const float G = sum_parts(f.ws + ((size_t)t * f.M + pr) * f.N + k, pstride, f.P) * f.inv_scale;
-    f.dst_w[((size_t)r * f.Cc + k) * f.taps + t] = G;
+    const float* p0 = f.ws + ((size_t)t * f.M + pr) * f.N + k;
+    float s0 = 0.f, s1 = 0.f;
+    if (ok) {
+      int p = sl;
+      for (; p + 8 < f.P; p += 16) { s0 += p0[(size_t)p * pstride]; s1 += p0[(size_t)(p + 8) * pstride]; }
+      if (p < f.P) s0 += p0[(size_t)p * pstride];
+    }
+    red[sl][le] = s0 + s1;
+    __syncthreads();
+    if (sl == 0 && ok) {
+      float g = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) g += red[q][le];
+      f.dst_w[((size_t)r * f.Cc + k) * f.taps + t] = g * f.inv_scale;
+    }
+    __syncthreads();
   }
 }
 
-// LayerNorm-folded weights, step 1: reduce the P partials IN PLACE into partial 0 (and colsum 0).  Blocks [0, nmain) take the
+// LayerNorm-folded weights, step 1: reduce the P partials IN PLACE into partial 0 (and colsum 0).  A block takes 32 consecutive
+// elements x 8 split lanes (coalesced 128-byte rows per split; the serial chain is P / 8 loads, not P); blocks [0, nmain) take the
 // matrix, the rest the column sums.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_inplace_kernel(float* __restrict__ ws, float* __restrict__ colsum, int P, long long MN, int M, int nmain) {
-  if ((int)blockIdx.x < nmain) {
-    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (e < MN) ws[e] = sum_parts(ws + e, (size_t)MN, P);
-  } else if (colsum) {
-    const int m = ((int)blockIdx.x - nmain) * 256 + threadIdx.x;
-    if (m < M) colsum[m] = sum_parts(colsum + m, (size_t)M, P);
+  __shared__ float red[8][33];
+  const int le = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  float* base;
+  long long e, n;
+  if ((int)blockIdx.x < nmain) { base = ws; n = MN; e = (long long)blockIdx.x * 32 + le; }
+  else { base = colsum; n = M; e = (long long)((int)blockIdx.x - nmain) * 32 + le; }
+  float s0 = 0.f, s1 = 0.f;
+  if (e < n) {
+    int p = sl;
+    for (; p + 8 < P; p += 16) { s0 += base[(size_t)p * n + e]; s1 += base[(size_t)(p + 8) * n + e]; }
+    if (p < P) s0 += base[(size_t)p * n + e];
+  }
+  red[sl][le] = s0 + s1;
+  __syncthreads();
+  if (sl == 0 && e < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][le];
+    base[e] = t;
   }
 }
 
-// step 2: dW = gamma G + beta s, and the column reductions dgamma[k] = sum_r W G, dbeta[k] = sum_r W s.  One block per 32 input
-// channels (lane = channel: coalesced), 8 warps stride over the rows; block 0 also writes dbias.
+// step 2: dW = gamma G + beta s, and the column reductions dgamma[k] = sum_r W G, dbeta[k] = sum_r W s.  One block per 8 input channels
+// x 32 row lanes (32-byte segments stay whole; the row loop is R / 32 long); block 0 also writes dbias.
 __global__ void __launch_bounds__(256)
 wgrad_ln_apply_kernel(const PirWgradFin f) {
-  __shared__ float sg[8][32], sb[8][32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k = blockIdx.x * 32 + lane;
+  __shared__ float sg[32][9], sb[32][9];
+  const int kc = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int k = blockIdx.x * 8 + kc;
   float dg = 0.f, db = 0.f;
   if (k < f.Cc) {
     const float gam = f.gamma[k], bet = f.beta ? f.beta[k] : 0.f;
 #pragma unroll 4
-    for (int r = warp; r < f.R; r += 8) {
+    for (int r = rl; r < f.R; r += 32) {
       const int pr = prow_of(r, f.half, f.half_pad);
       const float G = f.ws[(size_t)pr * f.N + k] * f.inv_scale;
       const float s = f.colsum ? f.colsum[pr] * f.inv_scale : 0.f;
@@ -321,13 +351,13 @@ wgrad_ln_apply_kernel(const PirWgradFin f) {
       db = fmaf(w, s, db);
     }
   }
-  sg[warp][lane] = dg;
-  sb[warp][lane] = db;
+  sg[rl][kc] = dg;
+  sb[rl][kc] = db;
   __syncthreads();
-  if (warp == 0 && k < f.Cc) {
+  if (rl == 0 && k < f.Cc) {
     float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { a += sg[w][lane]; b += sb[w][lane]; }
+    for (int w = 0; w < 32; ++w) { a += sg[w][kc]; b += sb[w][kc]; }
     f.dst_gamma[k] = a;
     if (f.dst_beta) f.dst_beta[k] = b;
   }
@@ -465,14 +495,14 @@ extern "C" int pir_wgrad_finalize(const PirWgradFin* d, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (d->gamma) {                                         // LayerNorm-folded 1x1 conv: reduce in place, then apply + column sums
     const long long MN = (long long)d->M * d->N;
-    const int nmain = (int)((MN + 255) / 256), ncs = d->colsum ? (d->M + 255) / 256 : 0;
+    const int nmain = (int)((MN + 31) / 32), ncs = d->colsum ? (d->M + 31) / 32 : 0;
     pir::wgrad_reduce_inplace_kernel<<<(unsigned)(nmain + ncs), 256, 0, s>>>(d->ws, d->colsum, d->P, MN, d->M, nmain);
     if (int e = pir_check_launch("pir_wgrad_finalize(reduce)")) return e;
-    pir::wgrad_ln_apply_kernel<<<(unsigned)((d->Cc + 31) / 32), 256, 0, s>>>(*d);
+    pir::wgrad_ln_apply_kernel<<<(unsigned)((d->Cc + 7) / 8), 256, 0, s>>>(*d);
     return pir_check_launch("pir_wgrad_finalize(ln)");
   }
   const long long total = (long long)d->R * d->Cc;
-  pir::wgrad_fin_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*d);
+  pir::wgrad_fin_kernel<<<(unsigned)((total + 31) / 32), 256, 0, s>>>(*d);
   if (int e = pir_check_launch("pir_wgrad_finalize")) return e;
   if (d->dst_bias) {
     pir::wgrad_fin_bias_kernel<<<(unsigned)((d->R + 255) / 256), 256, 0, s>>>(*d);
