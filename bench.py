@@ -217,14 +217,30 @@ def run_ours(args):
         table[tag] = {"launches": d["n"], "ms": round(d["ms"], 4), "share": round(d["ms"] / total_ms, 4), "GBps": round(gbs, 1),
                       "TFLOPs": round(tfs, 2), "bound": "hbm" if t_h >= t_t else "tensor",
                       "frac": round(max(t_h, t_t) / d["ms"], 4)}
-    top = max(tags, key=lambda t: tags[t]["ms"])
-    td = tags[top]
+    # dominant kernel = the (tag, input shape) class with the most time; its per-launch numbers go into `roofline`
+    classes = {}
+    for i, r in enumerate(eng.ops):
+        tag = r.get("tag") or r["kind"]
+        src = r.get("a") if r.get("a") is not None else (r.get("x") if r.get("x") is not None else r.get("qkv"))
+        shape = tuple(src.shape) if src is not None else ()
+        t_ms = statistics.mean(evs[rep][i][0].elapsed_time(evs[rep][i][1]) for rep in range(nrep))
+        by, fl = op_cost(r)
+        d = classes.setdefault((tag, shape), {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "n": 0})
+        d["ms"] += t_ms
+        d["bytes"] += by
+        d["flops"] += fl
+        d["n"] += 1
+    (top, top_shape), td = max(classes.items(), key=lambda kv: kv[1]["ms"])
     hbm_bound = td["bytes"] / pk["hbm"] / 1e6 >= td["flops"] / pk["tc"] / 1e9
     ach = td["bytes"] / td["ms"] / 1e6 if hbm_bound else td["flops"] / td["ms"] / 1e9
-    roofline = {"kernel": top, "bound": "hbm" if hbm_bound else "tensor", "achieved": round(ach, 1),
+    # DRAM bytes (read + write) of ONE launch of that class from the committed `ncu --set full` capture, when there is one
+    ncu_traffic = {("K56", (BATCH, SIDE, SIDE, 96)): (202.1e6 + 483.7e6, "profiles/r1_pwdw_ncu_v7.md")}
+    traffic, traffic_src = ncu_traffic.get((top, top_shape), (None, None))
+    roofline = {"kernel": f"{top} on {list(top_shape)}", "bound": "hbm" if hbm_bound else "tensor", "achieved": round(ach, 1),
                 "peak": pk["hbm"] if hbm_bound else pk["tc"], "unit": "GB/s" if hbm_bound else "TFLOP/s",
-                "frac": round(ach / (pk["hbm"] if hbm_bound else pk["tc"]), 4), "traffic": None,
-                "launches_per_step": td["n"], "avg_launch_ms": round(td["ms"] / td["n"], 4), "peak_source": pk["src"],
+                "frac": round(ach / (pk["hbm"] if hbm_bound else pk["tc"]), 4), "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": round(td["bytes"] / td["n"]), "launches_per_step": td["n"],
+                "avg_launch_ms": round(td["ms"] / td["n"], 4), "share_of_step": round(td["ms"] / total_ms, 4), "peak_source": pk["src"],
                 "note": ("K56/K12 are the fused LN+1x1+dw3x3(+gate) kernels: their binding resource is CUDA-core issue (fp16x2 FMA, "
                          "MUFU), not HBM or the tensor pipe -- see DESIGN.md 3.2 and profiles/ for issue-slot utilisation") if top in ("K56", "K12") else "",
                 "how": "CUDA events around each launch, eager pass, mean of %d steps; achieved = algorithmic bytes / time" % nrep}
