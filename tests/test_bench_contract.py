@@ -1,0 +1,50 @@
+"""bench.py's line contract, as far as it can be checked without a GPU: the reference arm prints exactly one JSON line on
+stdout with the driver's keys, and the product arm refuses to run (non-zero exit, no JSON) when there is no CUDA device."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], cwd=ROOT, env=env, capture_output=True,
+                          text=True, timeout=600)
+
+
+def test_reference_arm_line():
+    p = _run("--impl", "reference", "--steps", "1", "--warmup", "1")
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines                      # one JSON line, nothing else on stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "promptir_fwd_megapixels_per_sec" and d["unit"] == "MP/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["n_gpus"] == 1 and d["gpu_launches"] == 0
+    assert d["value"] > 0 and abs(d["value"] - 256 * 256 / 1e6 / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"] + 1e-9
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "256x256" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_do_nothing():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_product_arm_has_no_cpu_fallback():
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present: the product arm runs for real (covered by the -m gpu suite and the driver)")
+    p = _run("--steps", "1", "--warmup", "1")
+    assert p.returncode != 0
+    assert p.stdout.strip() == ""                      # no JSON line is produced by a run that did not measure anything
+    assert "no CPU fallback" in p.stderr or "no CUDA device" in p.stderr
