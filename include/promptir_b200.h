@@ -129,6 +129,8 @@ int pir_mdta_splits(int32_t B, int32_t HW, int32_t C);
 int64_t pir_mdta_ws_floats(int32_t B, int32_t C, int32_t splits);
 int pir_mdta_gram(const PirMdta* d, void* stream);
 int pir_mdta_finalize(const PirMdta* d, void* stream);
+/* kernels pir_mdta_finalize enqueues for this shape: 1 (fused softmax + fold, head dim <= 192) or 2 */
+int pir_mdta_finalize_kernels(int32_t C, int32_t heads);
 
 /* ---- PromptGenBlock (model.py:226-232): pool -> linear -> softmax -> weighted prompt sum -> bilinear --
  * x: NHWC 16-bit [B,H,W,C] feature; prompt: fp32 [L][S][S][D] (repacked prompt_param); lin_w fp32 [L][C],

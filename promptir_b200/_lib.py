@@ -163,6 +163,7 @@ SYMBOLS = {
     "pir_pwdw": (i32, [C.POINTER(PirPwDw), vp]),
     "pir_mdta_splits": (i32, [i32, i32, i32]),
     "pir_mdta_ws_floats": (i64, [i32, i32, i32]),
+    "pir_mdta_finalize_kernels": (i32, [i32, i32]),
     "pir_mdta_gram": (i32, [C.POINTER(PirMdta), vp]),
     "pir_mdta_finalize": (i32, [C.POINTER(PirMdta), vp]),
     "pir_prompt_ws_floats": (i64, [i32, i32, i32]),

@@ -11,6 +11,7 @@
 //                           then fold into project_out:  Wf[b][o][hc+j] = sum_i Wo[o][hc+i] A[b,h][i][j]
 //                           so that (attn @ v) and project_out become ONE pointwise GEMM on v (pir_gemm with
 //                           per-image weights) -- the attention output is never materialised.
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "host.h"
 
@@ -367,6 +368,273 @@ mdta_fold_kernel(const float* __restrict__ wo, const float* __restrict__ attn, u
 }
 
 // ------------------------------------------------------------------------------------------------------
+// finalize, fused (head dim <= 192): one CTA per (o-chunk, head, image) reduces the head's c x c Gram block and
+// norms into shared memory, runs the softmax there (one warp per row; same arithmetic and summation order as
+// mdta_softmax_kernel, so the two paths agree bit for bit), writes the attention matrix for the backward pass and
+// folds it into Wo:  Wf[b][o][h*c + j] = sum_i Wo[o][h*c + i] * A[i][j]  for its o rows.  One launch instead of two and
+// no 32x32-tile round trips through L2: lanes run over j, each warp keeps 8 o rows in registers, Wo tiles are staged
+// transposed so the 8 weights of a k step are two broadcast float4 reads.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kFinThreads = 512;
+constexpr int kFinRows = (kFinThreads / 32) * 8;   // o rows per pass
+constexpr int kFinIC = 64;                         // k (= i) chunk staged per pass
+constexpr int kFinWPitch = kFinRows + 4;
+
+// Sums the split-K partials of four items at a time, eight loads in flight each (32 independent loads per thread and
+// round); per item the additions happen in sum_splits() order (four accumulators over the multiple-of-4 prefix, the
+// remainder onto the first), so both finalize paths produce the same bits.
+struct FinItem { const float* p; size_t stride; float* dst; };
+
+__device__ __forceinline__ void sum_splits_x4(const FinItem (&it)[4], int splits) {
+  float acc[4][4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x) acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.f;
+  const int tail = splits & ~3;
+  for (int sp = 0; sp < splits; sp += 8) {
+    float l[4][8];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) l[x][u] = (it[x].p != nullptr && sp + u < splits) ? it[x].p[(size_t)(sp + u) * it[x].stride] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool main = sp + u < tail;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        if (main) acc[x][u & 3] += l[x][u];
+        else acc[x][0] += l[x][u];
+      }
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+    if (it[x].p != nullptr) *it[x].dst = (acc[x][0] + acc[x][1]) + (acc[x][2] + acc[x][3]);
+}
+
+template <class T, int NT>
+__global__ void __launch_bounds__(kFinThreads)
+mdta_finalize_fused_kernel(const float* __restrict__ ws_gram, const float* __restrict__ ws_norm,
+                           const float* __restrict__ temperature, const float* __restrict__ wo, float* __restrict__ attn,
+                           unsigned short* __restrict__ wfold, int C, int heads, int splits, int kpad, int o_per_cta) {
+  extern __shared__ __align__(16) float fin_smem[];
+  constexpr int kPre = kFinRows * kFinIC / kFinThreads;              // Wo values each thread stages per chunk
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int nrank = (int)gridDim.x, rank = (int)blockIdx.x;          // the cluster spans grid.x: one CTA per o-chunk
+  const int c = C / heads;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  float* sG = fin_smem;                                              // [c][c] Gram sums, then probabilities
+  float* sN = sG + c * c;                                            // [2c]: ||q_i||^2, ||k_j||^2; then 32 * NT floats of slack (masked lanes)
+  float* sW = sG + ((c * c + 2 * c + 32 * NT + 3) & ~3);             // [kFinIC][kFinWPitch], 16-byte aligned
+  const int o_begin = rank * o_per_cta;
+  const int o_end = o_begin + o_per_cta < C ? o_begin + o_per_cta : C;
+
+  // Wo tile (rows ob.., k chunk i0..) -> registers; it only depends on weights, so the first one is fetched before
+  // anything else and each next one while the current chunk is being multiplied.
+  float pre[kPre];
+  auto fetch_w = [&](int ob, int i0) {
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int e = tid + u * kFinThreads;
+      const int oo = e / kFinIC, ii = e % kFinIC;
+      const int o = ob + oo, i = i0 + ii;
+      pre[u] = (o < o_end && i < c) ? wo[(size_t)o * C + h * c + i] : 0.f;
+    }
+  };
+  fetch_w(o_begin, 0);
+  pdl_launch_dependents();
+  pdl_wait();
+
+  // ---- 1a: split-K partials of this head's Gram block and norms -> shared memory.  One SM pulls only ~40 GB/s out of
+  // L2 with this access pattern, so the c*c + 2c sums are divided over the CTAs of the cluster (item e lives at sG[e] in
+  // its owner) and exchanged through distributed shared memory. ----
+  const int ng = c * c, n = ng + 2 * c;
+  const int per = (n + nrank - 1) / nrank;
+  {
+    const size_t gstride = (size_t)C * c;
+    const float* gb = ws_gram + ((size_t)b * splits * C + (size_t)h * c) * c;
+    const float* nb = ws_norm + (size_t)b * splits * 2 * C;
+    const int lo = rank * per, hi = lo + per < n ? lo + per : n;
+    for (int e0 = lo + tid; e0 < hi; e0 += 4 * kFinThreads) {
+      FinItem it[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int e = e0 + x * kFinThreads;
+        if (e < hi && e < ng) it[x] = FinItem{gb + e, gstride, sG + e};
+        else if (e < hi) {
+          const int t = e - ng;
+          it[x] = FinItem{nb + (t < c ? h * c + t : C + h * c + (t - c)), (size_t)2 * C, sG + e};
+        } else it[x] = FinItem{nullptr, 0, nullptr};
+      }
+      sum_splits_x4(it, splits);
+    }
+  }
+  if (nrank > 1) {
+    cluster.sync();
+    const int lo = rank * per, hi = lo + per;
+    for (int e0 = tid; e0 < n; e0 += 4 * kFinThreads) {               // four independent remote loads in flight per thread
+      float v[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int e = e0 + x * kFinThreads;
+        v[x] = (e < n && (e < lo || e >= hi)) ? cluster.map_shared_rank(sG, e / per)[e] : 0.f;
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int e = e0 + x * kFinThreads;
+        if (e < n && (e < lo || e >= hi)) sG[e] = v[x];
+      }
+    }
+    cluster.sync();                                                   // nobody overwrites (1b) or leaves before all peers have read
+  } else {
+    __syncthreads();
+  }
+  // ---- 1b: softmax rows, in place ----
+  {
+    const float temp = temperature[h];
+    for (int i = warp; i < c; i += kFinThreads / 32) {
+      const float qn = fmaxf(sqrtf(sN[i]), 1e-12f);                  // F.normalize: x / max(||x||, eps)
+      float v[NT];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int j = lane + t * 32;
+        v[t] = -INFINITY;
+        if (j < c) {
+          const float kn = fmaxf(sqrtf(sN[c + j]), 1e-12f);
+          v[t] = sG[i * c + j] / (qn * kn) * temp;
+          mx = fmaxf(mx, v[t]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int j = lane + t * 32;
+        if (j < c) { v[t] = expf(v[t] - mx); sum += v[t]; }
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.0f / sum;
+      float* arow = attn + ((size_t)(b * heads + h) * c + i) * c;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int j = lane + t * 32;
+        if (j < c) {
+          const float p = v[t] * inv;
+          sG[i * c + j] = p;
+          if (blockIdx.x == 0) arow[j] = p;          // kept for pir_mdta_bwd
+        }
+      }
+    }
+  }
+  // ---- 2: fold into Wo ----
+  for (int ob = o_begin; ob < o_end; ob += kFinRows) {
+    float acc[8][NT];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int t = 0; t < NT; ++t) acc[r][t] = 0.f;
+    for (int i0 = 0; i0 < c; i0 += kFinIC) {
+      __syncthreads();                              // sG complete (first pass) / previous sW tile consumed
+#pragma unroll
+      for (int u = 0; u < kPre; ++u) {
+        const int e = tid + u * kFinThreads;
+        sW[(e % kFinIC) * kFinWPitch + e / kFinIC] = pre[u];
+      }
+      __syncthreads();
+      if (i0 + kFinIC < c) fetch_w(ob, i0 + kFinIC);
+      else if (ob + kFinRows < o_end) fetch_w(ob + kFinRows, 0);
+      if (ob + warp * 8 < o_end) {
+        const int imax = c - i0 < kFinIC ? c - i0 : kFinIC;
+#pragma unroll 4
+        for (int ii = 0; ii < imax; ++ii) {
+          const float4 w0 = *reinterpret_cast<const float4*>(sW + ii * kFinWPitch + warp * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(sW + ii * kFinWPitch + warp * 8 + 4);
+          const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          float a[NT];
+#pragma unroll
+          for (int t = 0; t < NT; ++t) a[t] = sG[(i0 + ii) * c + lane + t * 32];       // lanes with j >= c read slack: never stored
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[r][t] = fmaf(w[r], a[t], acc[r][t]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int o = ob + warp * 8 + r;
+      if (o < o_end) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int j = lane + t * 32;
+          if (j < c) wfold[((size_t)b * C + o) * kpad + h * c + j] = to16<T>(acc[r][t]);
+        }
+      }
+    }
+  }
+}
+
+static size_t fin_smem_bytes(int c, int nt) {
+  return ((size_t)((c * c + 2 * c + 32 * nt + 3) & ~3) + (size_t)kFinIC * kFinWPitch) * sizeof(float);
+}
+
+static bool fin_fused_ok(int C, int heads) {
+  static const bool off = [] { const char* e = getenv("PIR_MDTA_FUSED"); return e && e[0] == '0'; }();   // A/B: softmax + fold kernels
+  return !off && heads > 0 && C % heads == 0 && C / heads <= 192;
+}
+
+template <class T, int NT>
+static int launch_fin_fused(const PirMdta* d, cudaStream_t s, const float* ws_gram, const float* ws_norm, float* attn) {
+  const int c = d->C / d->heads;
+  const size_t smem = fin_smem_bytes(c, NT);
+  static size_t raised = 0;
+  if (smem > 48 * 1024 && smem > raised) {
+    if (cudaFuncSetAttribute(mdta_finalize_fused_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return pir_fail(PIR_ERR_CUDA, "pir_mdta_finalize: cannot raise dynamic shared memory limit");
+    raised = smem;
+  }
+  // one cluster per (head, image); its CTAs share the split-K reduction and take C / size output rows each
+  // (a multiple of 8 = one warp's rows).  Enough CTAs to cover the SMs when B * heads alone does not.
+  const int pairs = d->B * d->heads;
+  // Clusters of 8 only when a handful of them exist (not every GPC can place two at a time: 16 clusters of 8 ran in two
+  // waves, 20 us instead of 14); otherwise up to 4 CTAs per cluster while the grid stays within one wave.
+  int cl = 1;
+  while (cl < 4 && pairs * cl * 2 <= 148) cl *= 2;
+  if (pairs <= 8) cl = 8;
+  const int o_per_cta = ((d->C + cl - 1) / cl + 7) / 8 * 8;
+  const int kpad = (d->C + 63) / 64 * 64;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cl, (unsigned)d->heads, (unsigned)d->B);
+  cfg.blockDim = dim3(kFinThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pir_pdl_enabled() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, mdta_finalize_fused_kernel<T, NT>, ws_gram, ws_norm, d->temperature, d->wo, attn,
+                     reinterpret_cast<unsigned short*>(d->wfold), (int)d->C, (int)d->heads, (int)d->splits, kpad, o_per_cta);
+  return pir_check_launch("pir_mdta_finalize(fused)");
+}
+
+template <class T>
+static int launch_fin_fused_t(const PirMdta* d, cudaStream_t s, const float* ws_gram, const float* ws_norm, float* attn) {
+  const int c = d->C / d->heads;
+  if (c <= 64) return launch_fin_fused<T, 2>(d, s, ws_gram, ws_norm, attn);
+  if (c <= 96) return launch_fin_fused<T, 3>(d, s, ws_gram, ws_norm, attn);
+  return launch_fin_fused<T, 6>(d, s, ws_gram, ws_norm, attn);
+}
+
+// ------------------------------------------------------------------------------------------------------
 static int gram_nblocks_n(int C) { return (C + 255) / 256; }
 static int gram_nblocks_m(int C) { return (C + 127) / 128; }
 
@@ -444,6 +712,8 @@ extern "C" int pir_mdta_gram(const PirMdta* d, void* stream) {
   return d->dtype == PIR_DTYPE_BF16 ? pir::launch_gram<pir::BF16>(d, s) : pir::launch_gram<pir::FP16>(d, s);
 }
 
+extern "C" int pir_mdta_finalize_kernels(int32_t C, int32_t heads) { return pir::fin_fused_ok(C, heads) ? 1 : 2; }
+
 extern "C" int pir_mdta_finalize(const PirMdta* d, void* stream) {
   if (int e = pir::check_mdta(d, "pir_mdta_finalize")) return e;
   if (!d->temperature || !d->wo || !d->wfold) return pir_fail(PIR_ERR_ARG, "pir_mdta_finalize: missing pointers");
@@ -452,6 +722,9 @@ extern "C" int pir_mdta_finalize(const PirMdta* d, void* stream) {
   const float* ws_gram = d->ws;
   const float* ws_norm = d->ws + (size_t)d->B * d->splits * d->C * c;
   float* attn = d->ws + (size_t)d->B * d->splits * ((size_t)d->C * c + 2 * d->C);
+  if (pir::fin_fused_ok(d->C, d->heads))
+    return d->dtype == PIR_DTYPE_BF16 ? pir::launch_fin_fused_t<pir::BF16>(d, s, ws_gram, ws_norm, attn)
+                                      : pir::launch_fin_fused_t<pir::FP16>(d, s, ws_gram, ws_norm, attn);
   if (c <= 256) pir_launch(pir::mdta_softmax_kernel<8>, dim3((d->C + 7) / 8, d->B), dim3(256), 0, s, ws_gram, ws_norm, d->temperature, attn, d->C, d->heads, d->splits);
   else pir_launch(pir::mdta_softmax_kernel<24>, dim3((d->C + 7) / 8, d->B), dim3(256), 0, s, ws_gram, ws_norm, d->temperature, attn, d->C, d->heads, d->splits);
   if (int e = pir_check_launch("pir_mdta_finalize(softmax)")) return e;

@@ -333,7 +333,7 @@ class Engine:
     # bookkeeping for bench.py -------------------------------------------------------------------------
     def kernels_per_forward(self) -> int:
         per = {"mdta_finalize": 2, "prompt": 2}
-        return sum(per.get(r["kind"], 1) for r in self.ops)
+        return sum(getattr(r.get("launch"), "kernels", per.get(r["kind"], 1)) for r in self.ops)
 
 
 class SplitEngine:

@@ -52,6 +52,7 @@ def _prepared(fn_name: str, desc, keep, kernels: int = 1) -> Launch:
         _lib.launch_count += _k                  # kernels this entry point enqueues
 
     launch.desc = desc
+    launch.kernels = kernels
     return launch
 
 
@@ -159,7 +160,8 @@ def mdta(qkv: torch.Tensor, heads: int, ws: torch.Tensor, temperature: torch.Ten
     d.qkv, d.qkv_pitch, d.qkv_bstride = pq, qp, qbs
     d.ws, d.temperature, d.wo, d.wfold = ws.data_ptr(), temperature.data_ptr(), wo.data_ptr(), wfold.data_ptr()
     keep = (qkv, ws, temperature, wo, wfold)
-    return _prepared("pir_mdta_gram", d, keep), _prepared("pir_mdta_finalize", d, keep, kernels=2)
+    return (_prepared("pir_mdta_gram", d, keep),
+            _prepared("pir_mdta_finalize", d, keep, kernels=int(_lib.load().pir_mdta_finalize_kernels(Cdim, heads))))
 
 
 def prompt_ws_floats(B: int, HW: int, Cdim: int) -> int:

@@ -210,7 +210,7 @@ class XEngine(Engine):
 
     def kernels_per_forward(self) -> int:
         per = {"mdta_finalize": 2, "prompt": 2}
-        return sum(per.get(r["kind"], 1) for r in self.ops)
+        return sum(getattr(r.get("launch"), "kernels", per.get(r["kind"], 1)) for r in self.ops)
 
 
 def x_op_cost(rec: dict):

@@ -202,4 +202,4 @@ class XTrainEngine(TrainEngine):
 
     def kernels_per_step(self) -> int:
         per = {"mdta_finalize": 2, "prompt": 2, "wgrad_fin": 2, "dw_wgrad": 2, "mdta_bwd": 10, "prompt_bwd": 4, "ocab_bwd": 3}
-        return sum(per.get(r["kind"], 1) for r in self.ops)
+        return sum(getattr(r.get("launch"), "kernels", per.get(r["kind"], 1)) for r in self.ops)

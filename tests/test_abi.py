@@ -34,6 +34,7 @@ def test_host_only_entry_points(lib):
     assert lib.pir_abi_version() == 1
     assert 1 <= lib.pir_mdta_splits(16, 65536, 96) <= 64 and lib.pir_mdta_splits(1, 64, 384) == 1
     assert lib.pir_mdta_ws_floats(2, 48, 3) == 2 * 3 * (48 * 48 + 96) + 2 * 48 * 48
+    assert lib.pir_mdta_finalize_kernels(384, 8) in (1, 2) and lib.pir_mdta_finalize_kernels(704, 1) == 2
     assert lib.pir_prompt_ws_floats(2, 1024, 384) == 2 * 4 * 384
     # argument validation happens before any CUDA call: a null descriptor is rejected with a message
     assert lib.pir_gemm(None, None) == -1 and b"null" in lib.pir_last_error()

@@ -277,7 +277,8 @@ def test_pwdw(case, dt):
 # MDTA gram + finalize
 # --------------------------------------------------------------------------------------------------
 MDTA_CASES = [(2, 16, 16, 48, 1), (1, 32, 32, 96, 2), (2, 24, 24, 96, 1), (1, 16, 16, 192, 4), (2, 8, 8, 384, 8), (1, 8, 8, 704, 4),
-              (1, 16, 16, 320, 4), (1, 24, 40, 160, 4), (1, 128, 128, 48, 1)]
+              (1, 16, 16, 320, 4), (1, 24, 40, 160, 4), (1, 128, 128, 48, 1), (16, 32, 32, 192, 4), (3, 16, 16, 384, 8),
+              (1, 64, 64, 384, 2), (1, 256, 256, 48, 1)]
 
 
 @pytest.mark.parametrize("dt", DTYPES)
@@ -312,6 +313,53 @@ def test_mdta(case, dt):
     nref = torch.stack([q.pow(2).sum(1), k.pow(2).sum(1)], dim=1)
     assert torch.allclose(nrm, nref, rtol=1e-4, atol=1e-3), f"norm mismatch {(nrm - nref).abs().max().item()}"
     report_mismatch("mdta_wfold", wfold.view(B, 1, Cc, kp), ref.view(B, 1, Cc, kp), *tol(dt))
+    # the attention matrices kept in the workspace for pir_mdta_bwd: [B][heads][c][c] after the partials
+    attn = ws[B * splits * (Cc * c + 2 * Cc):][: B * Cc * c].view(B, heads, c, c)
+    qn = torch.nn.functional.normalize(q.transpose(1, 2).reshape(B, heads, c, -1), dim=-1)
+    kn = torch.nn.functional.normalize(k.transpose(1, 2).reshape(B, heads, c, -1), dim=-1)
+    aref = ((qn @ kn.transpose(-1, -2)) * temp.view(1, heads, 1, 1)).softmax(-1)
+    assert (attn - aref).abs().max().item() <= 2e-5, f"attention mismatch {(attn - aref).abs().max().item()}"
+
+
+_FIN_AB = """
+import sys, torch
+sys.path.insert(0, %r)
+from promptir_b200 import ops, packing
+torch.manual_seed(5)
+out = []
+for (B, H, W, Cc, heads) in [(2, 16, 16, 48, 1), (1, 24, 40, 160, 4), (2, 8, 8, 704, 4), (3, 16, 16, 384, 8)]:
+    qkv = torch.randn(B, H, W, 3 * Cc, device="cuda").to(torch.bfloat16)
+    temp = torch.rand(heads, device="cuda") * 4 + 0.5
+    wo = (torch.randn(Cc, Cc, device="cuda") / Cc ** 0.5).contiguous()
+    wfold = torch.zeros(B, Cc, packing.kpad_of(Cc), device="cuda", dtype=torch.bfloat16)
+    splits = ops.mdta_splits(B, H * W, Cc)
+    ws = torch.zeros(ops.mdta_ws_floats(B, Cc, splits), device="cuda")
+    gram, fin = ops.mdta(qkv, heads, ws, temp, wo, wfold, splits)
+    s = torch.cuda.current_stream().cuda_stream
+    gram(s); fin(s)
+    torch.cuda.synchronize()
+    out += [wfold.float().cpu(), ws.cpu(), torch.tensor([float(fin.kernels)])]
+torch.save(out, sys.argv[1])
+"""
+
+
+def test_mdta_finalize_fused_equals_two_kernel_path(tmp_path):
+    """PIR_MDTA_FUSED=0 selects the softmax + fold kernels; the fused kernel keeps their arithmetic and summation order,
+    so folded weights and saved attention must agree bit for bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = []
+    for flag in ("1", "0"):
+        f = str(tmp_path / f"fin{flag}.pt")
+        env = dict(os.environ, PIR_MDTA_FUSED=flag)
+        subprocess.run([sys.executable, "-c", _FIN_AB % root, f], check=True, env=env, timeout=300)
+        res.append(torch.load(f))
+    assert [int(t.item()) for t in res[0][2::3]] == [1, 1, 1, 1] and [int(t.item()) for t in res[1][2::3]] == [2, 2, 2, 2]
+    for i, (a, b) in enumerate(zip(res[0], res[1])):
+        if i % 3 != 2:
+            assert torch.equal(a, b), f"case {i // 3}: {'wfold' if i % 3 == 0 else 'workspace'} differs"
 
 
 # --------------------------------------------------------------------------------------------------
