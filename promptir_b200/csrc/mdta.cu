@@ -272,6 +272,34 @@ __device__ __forceinline__ float sum_splits(const float* p, size_t stride, int s
   return (s0 + s1) + (s2 + s3);
 }
 
+// Sums the split-K partials of four items at a time, eight loads in flight each (32 independent loads per thread and
+// round); per item the additions happen in sum_splits() order (four accumulators over the multiple-of-4 prefix, the
+// remainder onto the first), so every finalize path produces the same bits.  A null pointer skips the item.
+__device__ __forceinline__ void sum_splits_x4(const float* const (&p)[4], const size_t (&stride)[4], int splits, float (&out)[4]) {
+  float acc[4][4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x) acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.f;
+  const int tail = splits & ~3;
+  for (int sp = 0; sp < splits; sp += 8) {
+    float l[4][8];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) l[x][u] = (p[x] != nullptr && sp + u < splits) ? p[x][(size_t)(sp + u) * stride[x]] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool main = sp + u < tail;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        if (main) acc[x][u & 3] += l[x][u];
+        else acc[x][0] += l[x][u];
+      }
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x) out[x] = (acc[x][0] + acc[x][1]) + (acc[x][2] + acc[x][3]);
+}
+
 template <int NT>
 __global__ void __launch_bounds__(256)
 mdta_softmax_kernel(const float* __restrict__ ws_gram, const float* __restrict__ ws_norm, const float* __restrict__ temperature,
@@ -286,20 +314,37 @@ mdta_softmax_kernel(const float* __restrict__ ws_gram, const float* __restrict__
   const int h = r / c, i = r - h * c;
   const float* gbase = ws_gram + ((size_t)b * splits * C + r) * c;             // + sp * C * c
   const float* nbase = ws_norm + (size_t)b * splits * 2 * C;                   // + sp * 2 * C
-  const float qn = fmaxf(sqrtf(sum_splits(nbase + r, (size_t)2 * C, splits)), 1e-12f);   // F.normalize: x / max(||x||, eps)
   const float temp = temperature[h];
-  // c <= 32 * NT: up to NT columns per lane (NT = 8 for the usual 48-wide heads, 24 for the single-head prompt blocks)
+  // c <= 32 * NT: up to NT columns per lane (NT = 8 for the usual 48-wide heads, 24 for the single-head prompt blocks).
+  // Two columns (their k norm and Gram sums) per batch of loads.
   float v[NT];
   float mx = -INFINITY;
+  float qn = 1.f;
 #pragma unroll
-  for (int t = 0; t < NT; ++t) {
-    const int j = lane + t * 32;
+  for (int t = 0; t < NT; t += 2) {
+    const int j0 = lane + t * 32, j1 = lane + (t + 1) * 32;
+    const bool ok0 = j0 < c, ok1 = t + 1 < NT && j1 < c;
+    if (t * 32 >= c) {                                                  // whole warp past the head dimension
+      v[t] = -INFINITY;
+      if (t + 1 < NT) v[t + 1] = -INFINITY;
+      continue;
+    }
+    const float* p[4] = {ok0 ? nbase + C + h * c + j0 : nullptr, ok0 ? gbase + j0 : nullptr,
+                         ok1 ? nbase + C + h * c + j1 : nullptr, ok1 ? gbase + j1 : nullptr};
+    const size_t st[4] = {(size_t)2 * C, (size_t)C * c, (size_t)2 * C, (size_t)C * c};
+    float out[4];
+    if (t == 0) {                                                     // q norm: every lane of the row needs it
+      const float* pq[4] = {nbase + r, nullptr, nullptr, nullptr};
+      float oq[4];
+      sum_splits_x4(pq, st, splits, oq);
+      qn = fmaxf(sqrtf(oq[0]), 1e-12f);                               // F.normalize: x / max(||x||, eps)
+    }
+    sum_splits_x4(p, st, splits, out);
     v[t] = -INFINITY;
-    if (j < c) {
-      const float kn = fmaxf(sqrtf(sum_splits(nbase + C + h * c + j, (size_t)2 * C, splits)), 1e-12f);
-      const float s = sum_splits(gbase + j, (size_t)C * c, splits);
-      v[t] = s / (qn * kn) * temp;
-      mx = fmaxf(mx, v[t]);
+    if (ok0) { v[t] = out[1] / (qn * fmaxf(sqrtf(out[0]), 1e-12f)) * temp; mx = fmaxf(mx, v[t]); }
+    if (t + 1 < NT) {
+      v[t + 1] = -INFINITY;
+      if (ok1) { v[t + 1] = out[3] / (qn * fmaxf(sqrtf(out[2]), 1e-12f)) * temp; mx = fmaxf(mx, v[t + 1]); }
     }
   }
 #pragma unroll
@@ -380,37 +425,6 @@ constexpr int kFinRows = (kFinThreads / 32) * 8;   // o rows per pass
 constexpr int kFinIC = 64;                         // k (= i) chunk staged per pass
 constexpr int kFinWPitch = kFinRows + 4;
 
-// Sums the split-K partials of four items at a time, eight loads in flight each (32 independent loads per thread and
-// round); per item the additions happen in sum_splits() order (four accumulators over the multiple-of-4 prefix, the
-// remainder onto the first), so both finalize paths produce the same bits.
-struct FinItem { const float* p; size_t stride; float* dst; };
-
-__device__ __forceinline__ void sum_splits_x4(const FinItem (&it)[4], int splits) {
-  float acc[4][4];
-#pragma unroll
-  for (int x = 0; x < 4; ++x) acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.f;
-  const int tail = splits & ~3;
-  for (int sp = 0; sp < splits; sp += 8) {
-    float l[4][8];
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-      for (int u = 0; u < 8; ++u) l[x][u] = (it[x].p != nullptr && sp + u < splits) ? it[x].p[(size_t)(sp + u) * it[x].stride] : 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const bool main = sp + u < tail;
-#pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        if (main) acc[x][u & 3] += l[x][u];
-        else acc[x][0] += l[x][u];
-      }
-    }
-  }
-#pragma unroll
-  for (int x = 0; x < 4; ++x)
-    if (it[x].p != nullptr) *it[x].dst = (acc[x][0] + acc[x][1]) + (acc[x][2] + acc[x][3]);
-}
-
 template <class T, int NT>
 __global__ void __launch_bounds__(kFinThreads)
 mdta_finalize_fused_kernel(const float* __restrict__ ws_gram, const float* __restrict__ ws_norm,
@@ -457,17 +471,23 @@ mdta_finalize_fused_kernel(const float* __restrict__ ws_gram, const float* __res
     const float* nb = ws_norm + (size_t)b * splits * 2 * C;
     const int lo = rank * per, hi = lo + per < n ? lo + per : n;
     for (int e0 = lo + tid; e0 < hi; e0 += 4 * kFinThreads) {
-      FinItem it[4];
+      const float* p[4];
+      size_t st[4];
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         const int e = e0 + x * kFinThreads;
-        if (e < hi && e < ng) it[x] = FinItem{gb + e, gstride, sG + e};
+        p[x] = nullptr; st[x] = 0;
+        if (e < hi && e < ng) { p[x] = gb + e; st[x] = gstride; }
         else if (e < hi) {
           const int t = e - ng;
-          it[x] = FinItem{nb + (t < c ? h * c + t : C + h * c + (t - c)), (size_t)2 * C, sG + e};
-        } else it[x] = FinItem{nullptr, 0, nullptr};
+          p[x] = nb + (t < c ? h * c + t : C + h * c + (t - c)); st[x] = (size_t)2 * C;
+        }
       }
-      sum_splits_x4(it, splits);
+      float out[4];
+      sum_splits_x4(p, st, splits, out);
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+        if (p[x] != nullptr) sG[e0 + x * kFinThreads] = out[x];
     }
   }
   if (nrank > 1) {

@@ -460,19 +460,24 @@ struct MbArgs {
   float *dst_wo, *dst_temp, *dst_bias;
 };
 
+// eight loads in flight per round; even terms onto s0, odd terms onto s1, in order
 __device__ __forceinline__ float sum_strided(const float* p, size_t stride, int n) {
   float s0 = 0.f, s1 = 0.f;
-  int i = 0;
-  for (; i + 2 <= n; i += 2) { s0 += p[(size_t)i * stride]; s1 += p[(size_t)(i + 1) * stride]; }
-  if (i < n) s0 += p[(size_t)i * stride];
+  for (int i = 0; i < n; i += 8) {
+    float l[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) l[u] = i + u < n ? p[(size_t)(i + u) * stride] : 0.f;
+    s0 += l[0]; s1 += l[1]; s0 += l[2]; s1 += l[3]; s0 += l[4]; s1 += l[5]; s0 += l[6]; s1 += l[7];
+  }
   return s0 + s1;
 }
 
-// k1: norms and the per-image dWfold.  grid (ceil(C*C/256), B)
+// k1: norms, the per-image dWfold and the forward Gram sums (raw, into the cos buffer; k2 normalises them).  grid (ceil(C*C/256), B)
 __global__ void __launch_bounds__(256) mdta_bwd_reduce_kernel(const MbArgs a) {
   const int b = blockIdx.y;
   const int e = blockIdx.x * 256 + threadIdx.x;
   if (e < a.C * a.C) a.dWf[(size_t)b * a.C * a.C + e] = sum_strided(a.ws_b + (size_t)b * a.sb * a.C * a.C + e, (size_t)a.C * a.C, a.sb);
+  if (e < a.C * a.c) a.cosm[(size_t)b * a.C * a.c + e] = sum_strided(a.gram + (size_t)b * a.sf * a.C * a.c + e, (size_t)a.C * a.c, a.sf);
   if (e < 2 * a.C)
     a.nrm[(size_t)b * 2 * a.C + e] = fmaxf(sqrtf(sum_strided(a.norm + (size_t)b * a.sf * 2 * a.C + e, (size_t)2 * a.C, a.sf)), 1e-12f);
 }
@@ -501,17 +506,27 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const SgArgs g) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < g.K; k0 += 16) {
+  // tile coordinates of the four A and four B elements this thread stages per K chunk (fixed for the whole loop)
+  int am[4], ak[4], bn[4], bk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (g.a_sm == 1) { am[i] = t & 63; ak[i] = (t >> 6) + 4 * i; } else { ak[i] = t & 15; am[i] = (t >> 4) + 16 * i; }
+    if (g.b_sn == 1) { bn[i] = t & 63; bk[i] = (t >> 6) + 4 * i; } else { bk[i] = t & 15; bn[i] = (t >> 4) + 16 * i; }
+  }
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      int m, k;
-      if (g.a_sm == 1) { m = t & 63; k = (t >> 6) + 4 * i; } else { k = t & 15; m = (t >> 4) + 16 * i; }
-      As[k][m] = (m0 + m < g.M && k0 + k < g.K) ? A[(size_t)(m0 + m) * g.a_sm + (size_t)(k0 + k) * g.a_sk] : 0.f;
-      int n, kb;
-      if (g.b_sn == 1) { n = t & 63; kb = (t >> 6) + 4 * i; } else { kb = t & 15; n = (t >> 4) + 16 * i; }
-      Bs[kb][n] = (n0 + n < g.N && k0 + kb < g.K) ? Bm[(size_t)(k0 + kb) * g.b_sk + (size_t)(n0 + n) * g.b_sn] : 0.f;
+      ra[i] = (m0 + am[i] < g.M && k0 + ak[i] < g.K) ? A[(size_t)(m0 + am[i]) * g.a_sm + (size_t)(k0 + ak[i]) * g.a_sk] : 0.f;
+      rb[i] = (n0 + bn[i] < g.N && k0 + bk[i] < g.K) ? Bm[(size_t)(k0 + bk[i]) * g.b_sk + (size_t)(n0 + bn[i]) * g.b_sn] : 0.f;
     }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < g.K; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { As[ak[i]][am[i]] = ra[i]; Bs[bk[i]][bn[i]] = rb[i]; }
     __syncthreads();
+    if (k0 + 16 < g.K) fetch(k0 + 16);              // next chunk's loads fly while this one is multiplied
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
@@ -564,7 +579,7 @@ __global__ void __launch_bounds__(256) mdta_bwd_rows_kernel(const MbArgs a) {
     if (j < c) {
       A[t] = a.attn[((size_t)(b * a.heads + h) * c + i) * c + j];
       const float kn = a.nrm[(size_t)b * 2 * C + C + h * c + j];
-      cs[t] = sum_strided(a.gram + ((size_t)b * a.sf * C + r) * c + j, (size_t)C * c, a.sf) / (qn * kn);
+      cs[t] = a.cosm[((size_t)b * C + r) * c + j] / (qn * kn);
       dot = fmaf(dA[t], A[t], dot);
     }
   }
@@ -591,67 +606,81 @@ __global__ void __launch_bounds__(256) mdta_bwd_rows_kernel(const MbArgs a) {
   }
 }
 
-// k3: rk[b][h*c + j] = sum_i dcos[i][j] cos[i][j] / kn_j^2.  one thread per (b, channel)
+// k3: rk[b][h*c + j] = sum_i dcos[i][j] cos[i][j] / kn_j^2.  one warp per (b, channel): lanes over i, fixed-order butterfly
 __global__ void __launch_bounds__(256) mdta_bwd_cols_kernel(const MbArgs a) {
-  const int e = blockIdx.x * 256 + threadIdx.x;
+  const int e = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (e >= a.B * a.C) return;
   const int b = e / a.C, ch = e % a.C;
   const int h = ch / a.c, j = ch - h * a.c;
   const size_t base = ((size_t)b * a.C + h * a.c) * a.c + j;
   float s = 0.f;
-  for (int i = 0; i < a.c; ++i) s = fmaf(a.dcos[base + (size_t)i * a.c], a.cosm[base + (size_t)i * a.c], s);
-  const float kn = a.nrm[(size_t)b * 2 * a.C + a.C + ch];
-  a.rk[e] = s / (kn * kn);
+  for (int i = lane; i < a.c; i += 32) s = fmaf(a.dcos[base + (size_t)i * a.c], a.cosm[base + (size_t)i * a.c], s);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    const float kn = a.nrm[(size_t)b * 2 * a.C + a.C + ch];
+    a.rk[e] = s / (kn * kn);
+  }
 }
 
-// k4: wqk[b] (softmax / cosine / normalisation backward as a 2C x 2C matrix).  grid (ceil(2C*2C/256), B)
+// k4: wqk[b] (softmax / cosine / normalisation backward as a 2C x 2C matrix).  grid (ceil(2C * 2C / 8 / 256), B): eight consecutive k
+// per thread (2C % 8 == 0), one 16-byte store; most groups lie outside the head blocks and are plain zeros.
 template <class T>
 __global__ void __launch_bounds__(256) mdta_bwd_weights_kernel(const MbArgs a, unsigned short* __restrict__ wqk, int kpad2) {
   const int b = blockIdx.y;
   const int C = a.C, c = a.c;
   const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int groups = 2 * C / 8;
+  if (e >= (long long)2 * C * groups) return;
   const float* nrm = a.nrm + (size_t)b * 2 * C;
-  {
-    if (e >= (long long)4 * C * C) return;
-    const int n = (int)(e / (2 * C)), k = (int)(e % (2 * C));
-    float v = 0.f;
+  const int n = (int)(e / groups), k0 = (int)(e % groups) * 8;
+  float v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int k = k0 + u;
+    float x = 0.f;
     if (n < C) {
-      if (k < C) { if (k == n) v = -a.rq[(size_t)b * C + n]; }
+      if (k < C) { if (k == n) x = -a.rq[(size_t)b * C + n]; }
       else {
         const int kk = k - C;
-        if (kk / c == n / c) v = a.dcos[((size_t)b * C + n) * c + kk % c] / (nrm[n] * nrm[C + kk]);
+        if (kk / c == n / c) x = a.dcos[((size_t)b * C + n) * c + kk % c] / (nrm[n] * nrm[C + kk]);
       }
     } else {
       const int jg = n - C;
-      if (k < C) { if (k / c == jg / c) v = a.dcos[((size_t)b * C + k) * c + jg % c] / (nrm[k] * nrm[C + jg]); }
-      else if (k == n) v = -a.rk[(size_t)b * C + jg];
+      if (k < C) { if (k / c == jg / c) x = a.dcos[((size_t)b * C + k) * c + jg % c] / (nrm[k] * nrm[C + jg]); }
+      else if (k == n) x = -a.rk[(size_t)b * C + jg];
     }
     // fp16 storage: 1 / (|q| |k|) factors of degenerate (single-pixel) levels times the loss scale can leave the fp16 range -> saturate
-    wqk[((size_t)b * 2 * C + n) * kpad2 + k] = to16<T>(T::kFmt ? v : fminf(fmaxf(v, -65504.f), 65504.f));
+    v[u] = T::kFmt ? x : fminf(fmaxf(x, -65504.f), 65504.f);
   }
+  uint4 o;
+  o.x = (uint32_t)to16<T>(v[0]) | ((uint32_t)to16<T>(v[1]) << 16);
+  o.y = (uint32_t)to16<T>(v[2]) | ((uint32_t)to16<T>(v[3]) << 16);
+  o.z = (uint32_t)to16<T>(v[4]) | ((uint32_t)to16<T>(v[5]) << 16);
+  o.w = (uint32_t)to16<T>(v[6]) | ((uint32_t)to16<T>(v[7]) << 16);
+  *reinterpret_cast<uint4*>(wqk + ((size_t)b * 2 * C + n) * kpad2 + k0) = o;
 }
 
-// k5b: dWo = inv * sum_b dWoP[b]
-__global__ void __launch_bounds__(256) mdta_bwd_dwo_kernel(const MbArgs a) {
-  const int e = blockIdx.x * 256 + threadIdx.x;
-  if (e >= a.C * a.C) return;
-  a.dst_wo[e] = sum_strided(a.dWoP + e, (size_t)a.C * a.C, a.B) * a.inv_scale;
-}
-
-// k6: temperature gradient (one warp per head) and project_out bias gradient
+// k5b + k6, one launch: block 0 = temperature gradient (one warp per head), then ceil(C/256) blocks of project_out bias gradient
+// (when there is a bias), then ceil(C*C/256) blocks of dWo = inv * sum_b dWoP[b]
 __global__ void __launch_bounds__(256) mdta_bwd_small_kernel(const MbArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nbias = a.dst_bias ? (a.C + 255) / 256 : 0;
   if (blockIdx.x == 0) {
     if (warp < a.heads) {
       float s = 0.f;
+#pragma unroll 8
       for (int e = lane; e < a.B * a.c; e += 32) s += a.dTp[(size_t)(e / a.c) * a.C + warp * a.c + e % a.c];
 #pragma unroll
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) a.dst_temp[warp] = s * a.inv_scale;
     }
-  } else if (a.dst_bias) {
+  } else if ((int)blockIdx.x <= nbias) {
     const int o = (blockIdx.x - 1) * 256 + threadIdx.x;
     if (o < a.C) a.dst_bias[o] = sum_strided(a.colsum_b + o, (size_t)a.C, a.B * a.sb) * a.inv_scale;
+  } else {
+    const int e = (blockIdx.x - 1 - nbias) * 256 + threadIdx.x;
+    if (e < a.C * a.C) a.dst_wo[e] = sum_strided(a.dWoP + e, (size_t)a.C * a.C, a.B) * a.inv_scale;
   }
 }
 
@@ -940,6 +969,7 @@ extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
   if (!d) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: null descriptor");
   if (d->B <= 0 || d->C <= 0 || d->heads <= 0 || d->splits_f <= 0 || d->splits_b <= 0) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: empty problem");
   if (d->C % d->heads) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: C must be divisible by heads");
+  if (d->C % 8) return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: C must be a multiple of 8");
   if (d->C / d->heads > 768 || d->heads > 8) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_mdta_bwd: head dim > 768 or heads > 8");
   if (!d->ws_f || !d->ws_b || !d->temperature || !d->wo || !d->scratch || !d->wft || !d->wqk || !d->dst_wo || !d->dst_temp)
     return pir_fail(PIR_ERR_ARG, "pir_mdta_bwd: missing pointers");
@@ -983,9 +1013,9 @@ extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
   if (c <= 256) mdta_bwd_rows_kernel<8><<<dim3((C + 7) / 8, B), 256, 0, s>>>(a);
   else mdta_bwd_rows_kernel<24><<<dim3((C + 7) / 8, B), 256, 0, s>>>(a);
   if (int e = pir_check_launch("pir_mdta_bwd(rows)")) return e;
-  mdta_bwd_cols_kernel<<<(B * C + 255) / 256, 256, 0, s>>>(a);
+  mdta_bwd_cols_kernel<<<(B * C + 7) / 8, 256, 0, s>>>(a);
   if (int e = pir_check_launch("pir_mdta_bwd(cols)")) return e;
-  dim3 gw((4 * C * C + 255) / 256, B);
+  dim3 gw((unsigned)(((long long)2 * C * (2 * C / 8) + 255) / 256), B);
   if (bf) mdta_bwd_weights_kernel<BF16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2);
   else mdta_bwd_weights_kernel<FP16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2);
   if (int e = pir_check_launch("pir_mdta_bwd(weights)")) return e;
@@ -1007,10 +1037,8 @@ extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
     sgemm(g);
     if (int e = pir_check_launch("pir_mdta_bwd(dwo part)")) return e;
   }
-  mdta_bwd_dwo_kernel<<<(C * C + 255) / 256, 256, 0, s>>>(a);
-  if (int e = pir_check_launch("pir_mdta_bwd(dwo)")) return e;
-  mdta_bwd_small_kernel<<<1 + (d->dst_bias ? (C + 255) / 256 : 0), 256, 0, s>>>(a);
-  return pir_check_launch("pir_mdta_bwd(small)");
+  mdta_bwd_small_kernel<<<1 + (d->dst_bias ? (C + 255) / 256 : 0) + (C * C + 255) / 256, 256, 0, s>>>(a);
+  return pir_check_launch("pir_mdta_bwd(dwo, small)");
 }
 
 extern "C" int64_t pir_prompt_bwd_ws_floats(int32_t B, int32_t L, int32_t D, int32_t S) {
