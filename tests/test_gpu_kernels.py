@@ -121,6 +121,25 @@ def test_gemm_batched_weights(dt):
     report_mismatch("gemm_batched", x, ref, *tol(dt))
 
 
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", [(6, 74, 128, 48), (7, 37, 128, 96), (20, 16, 24, 96), (5, 40, 40, 192)], ids=lambda c: "B%dH%dW%dC%d" % c)
+def test_gemm_batched_weights_many_images_per_cta(case, dt):
+    """More tiles than SMs: every persistent CTA walks three or more images, each with its own weight matrix."""
+    B, H, W, C = case
+    torch.manual_seed(C + B)
+    qkv, _ = rand_act(B, H, W, 3 * C, dt)
+    x, _ = rand_act(B, H, W, C, dt)
+    kp = packing.kpad_of(C)
+    wf = torch.zeros(B, C, kp, device=DEV, dtype=dt)
+    wf[:, :, :C] = (torch.randn(B, C, C, device=DEV) / C ** 0.5).to(dt)
+    ref = x.clone()
+    emulator.emu_gemm(dict(a=qkv[..., 2 * C:], w=wf, out=ref, n=C, taps=1, out_mode=OUT_NHWC16, res=x.clone(), ln_mode=0, ln_s=None,
+                           vec_t=None, img=None, w_batched=True))
+    ops.gemm(qkv[..., 2 * C:], wf, x, n=C, res=x, w_batched=True)(stream())
+    torch.cuda.synchronize()
+    report_mismatch("gemm_batched", x, ref, *tol(dt))
+
+
 def test_gemm_fp32_out_exact_small_integers():
     """Small-integer operands make every product and partial sum exact: the fp32 result must be bit-exact,
     which pins the UMMA/TMA descriptor layouts independently of any rounding."""
