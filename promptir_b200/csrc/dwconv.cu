@@ -221,6 +221,18 @@ dwconv_gate_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
     unsigned short* outp = reinterpret_cast<unsigned short*>(a.out) + (size_t)b * a.out_bstride + c;
     const uint8_t* col = dw_smem + (size_t)buf * TILE_BYTES + (size_t)tx * ROW_BYTES + cg * 8;
 
+    // gate backward: this thread's dg values of the whole tile are fetched up front, so their latency hides behind the stencil
+    uint2 dgv[BWD ? TH : 1];
+    if (BWD) {
+#pragma unroll
+      for (int o = 0; o < TH; ++o) {
+        const int y = y0 + o;
+        dgv[o] = (c_ok && x_ok && y < a.H)
+                     ? __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(a.dg) + (size_t)b * a.dg_bstride +
+                                                            ((size_t)y * a.W + x) * a.dg_pitch + c))
+                     : make_uint2(0u, 0u);
+      }
+    }
     float p[3][4], q[3][4];
 #pragma unroll
     for (int r = 0; r < TH + 2; ++r) {
@@ -267,8 +279,7 @@ dwconv_gate_kernel(const __grid_constant__ CUtensorMap tmIn, const DwArgs a) {
             ov.y = pack2<T>(gelu_erf(pp[2]) * qq[2], gelu_erf(pp[3]) * qq[3]);
             *reinterpret_cast<uint2*>(outp + ((size_t)y * a.W + x) * a.out_pitch) = ov;
           } else {
-            const uint2 dv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned short*>(a.dg) + (size_t)b * a.dg_bstride +
-                                                                  ((size_t)y * a.W + x) * a.dg_pitch + c));
+            const uint2 dv = dgv[BWD ? o : 0];
             const float d[4] = {unpack_lo<T>(dv.x), unpack_hi<T>(dv.x), unpack_lo<T>(dv.y), unpack_hi<T>(dv.y)};
             float o1[4], o2[4];
 #pragma unroll
