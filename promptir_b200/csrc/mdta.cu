@@ -10,7 +10,8 @@
 //   (2) pir_mdta_finalize : reduce partials, logits = G / (|q_i| |k_j|) * temperature, softmax over j,
 //                           then fold into project_out:  Wf[b][o][hc+j] = sum_i Wo[o][hc+i] A[b,h][i][j]
 //                           so that (attn @ v) and project_out become ONE pointwise GEMM on v (pir_gemm with
-//                           per-image weights) -- the attention output is never materialised.
+//                           per-image weights) -- the attention output is never materialised.  One clustered
+//                           kernel for head dims <= 192 (mdta_finalize_fused_kernel), softmax + fold kernels above.
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "host.h"
@@ -256,25 +257,12 @@ mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// finalize 1: softmax rows.  grid (ceil(C/8), B), 256 threads: one warp per attention row (i = channel of q).
-// The split-K partials are summed with four independent accumulators so the loads overlap.
+// finalize, two-kernel path (head dims > 192, or PIR_MDTA_FUSED=0).  1: softmax rows.  grid (ceil(C/8), B), 256 threads:
+// one warp per attention row (i = channel of q).
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sum_splits(const float* p, size_t stride, int splits) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int sp = 0;
-  for (; sp + 4 <= splits; sp += 4) {
-    s0 += p[(size_t)sp * stride];
-    s1 += p[(size_t)(sp + 1) * stride];
-    s2 += p[(size_t)(sp + 2) * stride];
-    s3 += p[(size_t)(sp + 3) * stride];
-  }
-  for (; sp < splits; ++sp) s0 += p[(size_t)sp * stride];
-  return (s0 + s1) + (s2 + s3);
-}
-
 // Sums the split-K partials of four items at a time, eight loads in flight each (32 independent loads per thread and
-// round); per item the additions happen in sum_splits() order (four accumulators over the multiple-of-4 prefix, the
-// remainder onto the first), so every finalize path produces the same bits.  A null pointer skips the item.
+// round); per item the additions happen in one fixed order (four accumulators over the multiple-of-4 prefix of the
+// splits, the remainder onto the first), so every finalize path produces the same bits.  A null pointer skips the item.
 __device__ __forceinline__ void sum_splits_x4(const float* const (&p)[4], const size_t (&stride)[4], int splits, float (&out)[4]) {
   float acc[4][4];
 #pragma unroll
