@@ -492,14 +492,26 @@ struct SgArgs {
   float* out; unsigned short* out16; long long o_sm, o_sn, o_sb, o_sh;
 };
 
+// Up to three independent problems per launch (the three products of pir_mdta_bwd only depend on its first kernel): a flat grid,
+// each problem owns a contiguous range of blocks = (image, head) x its own m x n tiles.
+struct SgMulti {
+  SgArgs g[3];
+  int bend[3];        // exclusive prefix ends of each problem's block range
+  int nt_m[3], nt_n[3];
+};
+
 template <class T>
-__global__ void __launch_bounds__(256) sgemm_strided_kernel(const SgArgs g) {
+__global__ void __launch_bounds__(256) sgemm_strided_kernel(const SgMulti mp) {
   __shared__ __align__(16) float As[16][64];
   __shared__ __align__(16) float Bs[16][64];
-  const int z = blockIdx.z, b = z / g.heads, h = z % g.heads;
+  const int which = (int)blockIdx.x < mp.bend[0] ? 0 : ((int)blockIdx.x < mp.bend[1] ? 1 : 2);
+  const SgArgs& g = mp.g[which];
+  const int idx = (int)blockIdx.x - (which ? mp.bend[which - 1] : 0);
+  const int tiles = mp.nt_m[which] * mp.nt_n[which];
+  const int z = idx / tiles, tile = idx % tiles, b = z / g.heads, h = z % g.heads;
+  const int m0 = (tile / mp.nt_n[which]) * 64, n0 = (tile % mp.nt_n[which]) * 64;
   const float* A = g.A + (size_t)b * g.a_sb + (size_t)h * g.a_sh;
   const float* Bm = g.B + (size_t)b * g.b_sb + (size_t)h * g.b_sh;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   float acc[4][4];
 #pragma unroll
@@ -995,20 +1007,39 @@ extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
   const bool bf = d->dtype == PIR_DTYPE_BF16;
   const int kpad1 = (C + 63) / 64 * 64, kpad2 = (2 * C + 63) / 64 * 64;
   const int heads = d->heads;
-  auto sgemm = [&](const SgArgs& g) {
-    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, B * heads);
-    if (bf) sgemm_strided_kernel<BF16><<<grid, 256, 0, s>>>(g); else sgemm_strided_kernel<FP16><<<grid, 256, 0, s>>>(g);
-  };
   mdta_bwd_reduce_kernel<<<dim3((C * C + 255) / 256, B), 256, 0, s>>>(a);
   if (int e = pir_check_launch("pir_mdta_bwd(reduce)")) return e;
-  {   // dA_h[i][j] = sum_o Wo[o][hc+i] dWf[b][o][hc+j]  -> dcos buffer
-    SgArgs g{};
-    g.M = c; g.N = c; g.K = C; g.heads = heads;
-    g.A = d->wo; g.a_sm = 1; g.a_sk = C; g.a_sb = 0; g.a_sh = c;
-    g.B = a.dWf; g.b_sk = C; g.b_sn = 1; g.b_sb = (long long)C * C; g.b_sh = c;
-    g.out = a.dcos; g.o_sm = c; g.o_sn = 1; g.o_sb = (long long)C * c; g.o_sh = (long long)c * c;
-    sgemm(g);
-    if (int e = pir_check_launch("pir_mdta_bwd(dA)")) return e;
+  {
+    SgMulti mp{};
+    {   // dA_h[i][j] = sum_o Wo[o][hc+i] dWf[b][o][hc+j]  -> dcos buffer
+      SgArgs& g = mp.g[0];
+      g.M = c; g.N = c; g.K = C; g.heads = heads;
+      g.A = d->wo; g.a_sm = 1; g.a_sk = C; g.a_sb = 0; g.a_sh = c;
+      g.B = a.dWf; g.b_sk = C; g.b_sn = 1; g.b_sb = (long long)C * C; g.b_sh = c;
+      g.out = a.dcos; g.o_sm = c; g.o_sn = 1; g.o_sb = (long long)C * c; g.o_sh = (long long)c * c;
+    }
+    {   // wft[b][hc+j][o] = sum_i A[b,h][i][j] Wo[o][hc+i]
+      SgArgs& g = mp.g[1];
+      g.M = c; g.N = C; g.K = c; g.heads = heads;
+      g.A = a.attn; g.a_sm = 1; g.a_sk = c; g.a_sb = (long long)heads * c * c; g.a_sh = (long long)c * c;
+      g.B = d->wo; g.b_sk = 1; g.b_sn = C; g.b_sb = 0; g.b_sh = c;
+      g.out16 = reinterpret_cast<unsigned short*>(d->wft); g.o_sm = kpad1; g.o_sn = 1; g.o_sb = (long long)C * kpad1; g.o_sh = (long long)c * kpad1;
+    }
+    {   // dWoP[b][o][hc+i] = sum_j dWf[b][o][hc+j] A[b,h][i][j]
+      SgArgs& g = mp.g[2];
+      g.M = C; g.N = c; g.K = c; g.heads = heads;
+      g.A = a.dWf; g.a_sm = C; g.a_sk = 1; g.a_sb = (long long)C * C; g.a_sh = c;
+      g.B = a.attn; g.b_sk = 1; g.b_sn = c; g.b_sb = (long long)heads * c * c; g.b_sh = (long long)c * c;
+      g.out = a.dWoP; g.o_sm = C; g.o_sn = 1; g.o_sb = (long long)C * C; g.o_sh = c;
+    }
+    int total = 0;
+    for (int i = 0; i < 3; ++i) {
+      mp.nt_m[i] = (mp.g[i].M + 63) / 64; mp.nt_n[i] = (mp.g[i].N + 63) / 64;
+      total += mp.nt_m[i] * mp.nt_n[i] * B * heads;
+      mp.bend[i] = total;
+    }
+    if (bf) sgemm_strided_kernel<BF16><<<total, 256, 0, s>>>(mp); else sgemm_strided_kernel<FP16><<<total, 256, 0, s>>>(mp);
+    if (int e = pir_check_launch("pir_mdta_bwd(dA, fold, dwo part)")) return e;
   }
   if (c <= 256) mdta_bwd_rows_kernel<8><<<dim3((C + 7) / 8, B), 256, 0, s>>>(a);
   else mdta_bwd_rows_kernel<24><<<dim3((C + 7) / 8, B), 256, 0, s>>>(a);
@@ -1019,24 +1050,6 @@ extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
   if (bf) mdta_bwd_weights_kernel<BF16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2);
   else mdta_bwd_weights_kernel<FP16><<<gw, 256, 0, s>>>(a, reinterpret_cast<unsigned short*>(d->wqk), kpad2);
   if (int e = pir_check_launch("pir_mdta_bwd(weights)")) return e;
-  {   // wft[b][hc+j][o] = sum_i A[b,h][i][j] Wo[o][hc+i]
-    SgArgs g{};
-    g.M = c; g.N = C; g.K = c; g.heads = heads;
-    g.A = a.attn; g.a_sm = 1; g.a_sk = c; g.a_sb = (long long)heads * c * c; g.a_sh = (long long)c * c;
-    g.B = d->wo; g.b_sk = 1; g.b_sn = C; g.b_sb = 0; g.b_sh = c;
-    g.out16 = reinterpret_cast<unsigned short*>(d->wft); g.o_sm = kpad1; g.o_sn = 1; g.o_sb = (long long)C * kpad1; g.o_sh = (long long)c * kpad1;
-    sgemm(g);
-    if (int e = pir_check_launch("pir_mdta_bwd(fold)")) return e;
-  }
-  {   // dWoP[b][o][hc+i] = sum_j dWf[b][o][hc+j] A[b,h][i][j]
-    SgArgs g{};
-    g.M = C; g.N = c; g.K = c; g.heads = heads;
-    g.A = a.dWf; g.a_sm = C; g.a_sk = 1; g.a_sb = (long long)C * C; g.a_sh = c;
-    g.B = a.attn; g.b_sk = 1; g.b_sn = c; g.b_sb = (long long)heads * c * c; g.b_sh = (long long)c * c;
-    g.out = a.dWoP; g.o_sm = C; g.o_sn = 1; g.o_sb = (long long)C * C; g.o_sh = c;
-    sgemm(g);
-    if (int e = pir_check_launch("pir_mdta_bwd(dwo part)")) return e;
-  }
   mdta_bwd_small_kernel<<<1 + (d->dst_bias ? (C + 255) / 256 : 0) + (C * C + 255) / 256, 256, 0, s>>>(a);
   return pir_check_launch("pir_mdta_bwd(dwo, small)");
 }

@@ -354,7 +354,7 @@ def mdta_bwd(ws: torch.Tensor, rec: dict) -> Launch:
     d.wft, d.wqk = wft.data_ptr(), wqk.data_ptr()
     d.dst_wo, d.dst_temp, d.dst_bias = _f32ptr(rec["dst_wo"], "dst_wo"), _f32ptr(rec["dst_temp"], "dst_temp"), _f32ptr(rec["dst_bias"], "dst_bias")
     keep = (ws, rec["fws"], rec["temperature"], rec["wo"], wft, wqk, rec["dst_wo"], rec["dst_temp"], rec["dst_bias"])
-    return _prepared("pir_mdta_bwd", d, keep, kernels=9)
+    return _prepared("pir_mdta_bwd", d, keep, kernels=6)
 
 
 def pixel_shuffle(x: torch.Tensor, out: torch.Tensor, *, up: bool) -> Launch:

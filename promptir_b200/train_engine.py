@@ -545,5 +545,5 @@ class TrainEngine(Engine):
         self._run("fwd", self.fwd_launches, use_graph)
 
     def kernels_per_step(self) -> int:
-        per = {"mdta_finalize": 2, "prompt": 2, "wgrad_fin": 2, "dw_wgrad": 2, "mdta_bwd": 9, "prompt_bwd": 4}
+        per = {"mdta_finalize": 2, "prompt": 2, "wgrad_fin": 2, "dw_wgrad": 2, "mdta_bwd": 6, "prompt_bwd": 4}
         return sum(getattr(r.get("launch"), "kernels", per.get(r["kind"], 1)) for r in self.ops)

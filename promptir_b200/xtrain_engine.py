@@ -201,5 +201,5 @@ class XTrainEngine(TrainEngine):
         self._tconv3(pg.conv, cat, out, g_cat, g_out, tag="pconv")
 
     def kernels_per_step(self) -> int:
-        per = {"mdta_finalize": 2, "prompt": 2, "wgrad_fin": 2, "dw_wgrad": 2, "mdta_bwd": 9, "prompt_bwd": 4, "ocab_bwd": 3}
+        per = {"mdta_finalize": 2, "prompt": 2, "wgrad_fin": 2, "dw_wgrad": 2, "mdta_bwd": 6, "prompt_bwd": 4, "ocab_bwd": 3}
         return sum(getattr(r.get("launch"), "kernels", per.get(r["kind"], 1)) for r in self.ops)
