@@ -362,6 +362,33 @@ typedef struct PirOcabBwd {
 int64_t pir_ocab_bwd_ws_floats(int32_t B, int32_t H, int32_t W, int32_t heads);
 int pir_ocab_bwd(const PirOcabBwd* d, void* stream);
 
+/* ---- derived weight caches rebuilt on the device (host spec: promptir_b200/packing.py) -----------------------------------------
+ * The reference keeps fp32 nn.Parameters and lets cuDNN/cuBLAS read them directly (model.py:88-92,111-113,164,174,223); the sm_100a
+ * kernels read 16-bit K-major copies (LayerNorm gamma/beta of model.py:60-63 folded in, zero padding, GDFN [x1 | x2] padded channel
+ * space, tap-major 3x3 layouts, transposed / tap-flipped variants for the backward).  pir_repack rebuilds ALL of them from the live
+ * parameters in one launch: after optimizer.step() (train.py:52-56), after load_state_dict, at engine construction.
+ *   jobs_dev      n_jobs records in DEVICE memory (every pointer inside is a device pointer)
+ *   first_row_dev n_jobs + 1 int32 in device memory: exclusive prefix sum of pir_repack_rows(job); n_rows = first_row[n_jobs]
+ * inverse channel map of a job axis (split, hp): split == 0 -> identity (indices >= source length are zero padding); else indices
+ * [0, split) map to themselves, [split, hp) are padding and hp + j maps to source split + j.                                    */
+enum { PIR_PACK_POINTWISE = 0, PIR_PACK_CONV3X3 = 1, PIR_PACK_DEPTHWISE = 2, PIR_PACK_VEC = 3, PIR_PACK_PROMPT = 4 };
+typedef struct PirPackJob {
+  int32_t kind;
+  int32_t dst_dtype;               /* 16-bit kinds: PIR_DTYPE_*; VEC / PROMPT write fp32                                          */
+  int32_t n, k;                    /* logical source rows / columns (POINTWISE: N x K; CONV3X3: N x Cin; DEPTHWISE / VEC: n = length; PROMPT: L x D) */
+  int32_t transpose;               /* POINTWISE: source stored [k][n]; CONV3X3: source stored [Cin][N][3][3]                      */
+  int32_t flip;                    /* CONV3X3 / DEPTHWISE: taps reversed (tap -> 8 - tap), i.e. the kernel rotated by 180 degrees  */
+  int32_t n_total, k_pad;          /* destination rows / row length (PROMPT: n_total = S*S; VEC / DEPTHWISE: n_total = length)    */
+  int32_t row_split, row_hp;       /* inverse map of the destination row (DEPTHWISE / VEC: channel) axis                          */
+  int32_t col_split, col_hp;       /* inverse map of the destination column axis (POINTWISE)                                      */
+  int32_t gamma_axis;              /* POINTWISE: 0 none, 1 gamma[source column], 2 gamma[source row]                              */
+  int32_t reserved;
+  const float* src; const float* gamma; const float* beta; const float* bias;
+  void* dst; float* ln_s; float* vec_t;
+} PirPackJob;
+int64_t pir_repack_rows(const PirPackJob* job);
+int pir_repack(const PirPackJob* jobs_dev, const int32_t* first_row_dev, int32_t n_jobs, int32_t n_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

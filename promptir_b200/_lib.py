@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpromptir_b200.so")
+# PROMPTIR_B200_LIB: another build of the same library (same-box A/B timing of kernel changes); default = the in-tree build
+LIB_PATH = os.environ.get("PROMPTIR_B200_LIB") or os.path.join(_HERE, "libpromptir_b200.so")
 
 DTYPE_FP16, DTYPE_BF16 = 0, 1
 OUT_NHWC16, OUT_UNSHUFFLE16, OUT_SHUFFLE16, OUT_FINAL_NCHW32, OUT_NHWC32 = 0, 1, 2, 3, 4

@@ -49,6 +49,7 @@ struct FwArgs {
   int n_chunks;
   int n_vec;               // length of the per-channel shared-memory vectors (covers every index a chunk may touch)
   int tiles_x, tiles_y, n_items;
+  uint32_t mg_per_img, mg_tiles_x;
   int has_bias;            // depthwise bias present
   int has_t;               // additive per-channel vector present
   int scb;                 // chunks per super-chunk (<= SC of the configuration)
@@ -92,12 +93,15 @@ __device__ __forceinline__ float2 h2_to_f2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
 
+__device__ __forceinline__ uint32_t fw_div(uint32_t n, uint32_t magic) { return magic ? __umulhi(n, magic) : n; }
+
 // Compile-time shape of one kernel variant.  A compute group has 256 threads = 4 channel groups x 64 pixel columns;
 // the 64 columns are BANDS = 64 / TW row bands of R rows over a TW-wide tile.
 //   GATE : 4 gated channels per thread (16 gated channels per chunk), fp16 tile = two planes of 32-byte rows
 //   plain: 8 channels per thread       (32 channels per chunk),      fp16 tile = one plane of 64-byte rows
-template <int MT_, int TW_, int R_, bool GATE_, int NA_, int SC_, int NG_ = 2>
+template <int MT_, int TW_, int R_, bool GATE_, int NA_, int SC_, int NG_ = 2, int NKB_ = 0>
 struct FwCfg {
+  static constexpr int NKB = NKB_;
   static constexpr int MT = MT_, TW = TW_, R = R_;
   static constexpr int NG = NG_;                             // compute groups: 2 x 8 warps or 4 x 4 warps, one chunk in flight per group
   static constexpr int GT = kFwCompute / NG_;                // threads per group = 4 channel groups x GT/4 pixel columns
@@ -136,7 +140,9 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t b_stage_bytes = (uint32_t)g.nkb * B_KB_BYTES;
+  constexpr int NKB = Cfg::NKB;
+  const int nkb = NKB ? NKB : g.nkb;
+  const uint32_t b_stage_bytes = (uint32_t)nkb * B_KB_BYTES;
   const unsigned short* sdw = reinterpret_cast<const unsigned short*>(base_ptr + g.off_dw);
   float* svec = reinterpret_cast<float*>(base_ptr + g.off_vec);              // [n_vec] additive vector t
   const uint32_t* sseed = reinterpret_cast<const uint32_t*>(base_ptr + g.off_bias);   // [2][n_chunks * 32] fp16 accumulator seeds
@@ -195,22 +201,29 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   pdl_wait();                                    // barrier init, TMEM allocation and the staging of the (static) depthwise taps / seeds above
                                                  // overlapped the previous kernel's tail; x itself is only read from here on
   const int per_img = g.tiles_x * g.tiles_y;
+  auto item_geo = [&](int item, int& b, int& x0, int& y0) {
+    b = (int)fw_div((uint32_t)item, g.mg_per_img);
+    const int rr = item - b * per_img;
+    const int ty = (int)fw_div((uint32_t)rr, g.mg_tiles_x);
+    x0 = (rr - ty * g.tiles_x) * TW; y0 = ty * TH;
+  };
   const int n_super = (g.n_chunks + g.scb - 1) / g.scb;
   const int scb = g.scb;                                                   // chunks per super-chunk
-  const uint32_t a_buf_bytes = (uint32_t)g.nkb * A_KB_BYTES;               // one x-tile buffer
+  const uint32_t a_buf_bytes = (uint32_t)nkb * A_KB_BYTES;               // one x-tile buffer
 
   if (warp == 0) {
     // ========================================= TMA producer ==========================================
     // order: A(0) | A(1) B(0,*) | A(2) B(1,*) | ...   (NA == 2: the next item's tile is requested before this item's weights)
     auto load_a = [&](int item, uint32_t it) {
-      const int b = item / per_img, r = item % per_img;
-      const int x0 = (r % g.tiles_x) * TW - 1, y0 = (r / g.tiles_x) * TH - 1;
+      int b, x0, y0;
+      item_geo(item, b, x0, y0);
+      x0 -= 1; y0 -= 1;
       const uint32_t ab = it % NA;
       mbar_wait_sleep(smem_u32(&bar_aempty[ab]), ((it / NA) & 1u) ^ 1u);
       if (elect_one()) {
         const uint32_t full = smem_u32(&bar_afull[ab]);
-        mbar_expect_tx(full, (uint32_t)g.nkb * (uint32_t)(NPIX * 128));
-        for (int kb = 0; kb < g.nkb; ++kb) tma_load_4d(base + ab * a_buf_bytes + (uint32_t)kb * A_KB_BYTES, &tmA, full, kb * 64, x0, y0, b);
+        mbar_expect_tx(full, (uint32_t)nkb * (uint32_t)(NPIX * 128));
+        for (int kb = 0; kb < nkb; ++kb) tma_load_4d(base + ab * a_buf_bytes + (uint32_t)kb * A_KB_BYTES, &tmA, full, kb * 64, x0, y0, b);
       }
       __syncwarp();
     };
@@ -229,8 +242,8 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (elect_one()) {
           const uint32_t full = smem_u32(&bar_bfull[st]);
           const uint32_t dst = base + g.off_b + st * b_stage_bytes;
-          mbar_expect_tx(full, (uint32_t)g.nkb * (uint32_t)nvalid * 4096u);
-          for (int kb = 0; kb < g.nkb; ++kb) {
+          mbar_expect_tx(full, (uint32_t)nkb * (uint32_t)nvalid * 4096u);
+          for (int kb = 0; kb < nkb; ++kb) {
             for (int j = 0; j < nvalid; ++j) {               // chunk c occupies rows [32 j, 32 j + 32) of the stage
               const int c = sc * scb + j;
               const int r0 = GATE ? c * 16 : c * 32, r1 = GATE ? g.hp + c * 16 : c * 32 + 16;
@@ -262,7 +275,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         if (elect_one()) {
           const uint32_t b_lo = (base + g.off_b + st * b_stage_bytes) >> 4;
-          for (int kb = 0; kb < g.nkb; ++kb) {
+          for (int kb = 0; kb < nkb; ++kb) {
             const int rem = g.C - kb * 64;
             const int ksteps = rem >= 64 ? 4 : (rem + 15) >> 4;
             const uint64_t bd = desc_hi | (uint64_t)((b_lo + (uint32_t)kb * (B_KB_BYTES >> 4)) & 0x3fffu);
@@ -320,8 +333,8 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     auto grp_bar = [](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(GT) : "memory"); };
     // ---- LayerNorm of an item's halo'd tile in place; pixels outside the image stay zero ----
     auto layernorm_tile = [&](int item, uint32_t itn) {
-      const int rr = item % per_img;
-      const int x0 = (rr % g.tiles_x) * TW, y0 = (rr / g.tiles_x) * TH;
+      int b_, x0, y0;
+      item_geo(item, b_, x0, y0);
       const uint32_t ab = itn % NA;
       uint8_t* a_tile = base_ptr + (size_t)ab * a_buf_bytes;
       mbar_wait(smem_u32(&bar_afull[ab]), (itn / NA) & 1u);
@@ -335,8 +348,9 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int py = y0 - 1 + (ln_yx[r] >> 8), px = x0 - 1 + (ln_yx[r] & 255);
           const bool act = m < NPIX && py >= 0 && py < g.H && px >= 0 && px < g.W;
           float s1 = 0.f, s2 = 0.f, s1b = 0.f, s2b = 0.f;
-          for (int kb = 0; kb < g.nkb; ++kb) {
-            if (act) {
+#pragma unroll
+          for (int kb = 0; kb < (NKB ? NKB : 3); ++kb) {
+            if (act && kb < nkb) {
               const uint8_t* a_row = a_tile + (size_t)kb * A_KB_BYTES + (size_t)m * 128;
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
@@ -360,8 +374,9 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const float mu = s1 * inv_k;
           const float rstd = rsqrtf(fmaxf(fmaf(s2, inv_k, -mu * mu), 0.f) + 1e-5f);
           const float shift = g.ln_mode == 2 ? 0.f : -rstd * mu;            // BiasFree: numerator not centred
-          for (int kb = 0; kb < g.nkb; ++kb) {
-            if (act) {
+#pragma unroll
+          for (int kb = 0; kb < (NKB ? NKB : 3); ++kb) {
+            if (act && kb < nkb) {
               uint8_t* a_row = a_tile + (size_t)kb * A_KB_BYTES + (size_t)m * 128;
               const int valid = min(64, g.C - kb * 64);                       // channels of this k-block that exist
 #pragma unroll
@@ -388,8 +403,8 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t it = 0, uses = 0;
     if (NA == 2 && (int)blockIdx.x < g.n_items) layernorm_tile(blockIdx.x, 0);
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
-      const int b = item / per_img, rr = item % per_img;
-      const int x0 = (rr % g.tiles_x) * TW, y0 = (rr / g.tiles_x) * TH;
+      int b, x0, y0;
+      item_geo(item, b, x0, y0);
       if (NA == 2) {
         if (item + (int)gridDim.x < g.n_items) layernorm_tile(item + gridDim.x, it + 1);   // next item's tile, one item ahead
       } else {
@@ -605,6 +620,12 @@ static bool plan_fits(const PirPwDw* d, FwPlan* p, int mt, int na, int sc, int n
   g.tiles_x = (d->W + p->tw - 1) / p->tw;
   g.tiles_y = (d->H + th - 1) / th;
   g.n_items = g.tiles_x * g.tiles_y * d->B;
+  {
+    auto magic = [](uint32_t dv) { return dv <= 1 ? 0u : (uint32_t)((0x100000000ull + dv - 1) / dv); };
+    const uint64_t per_img = (uint64_t)g.tiles_x * g.tiles_y;
+    if ((uint64_t)g.n_items * per_img >= 0x100000000ull) return false;
+    g.mg_per_img = magic((uint32_t)per_img); g.mg_tiles_x = magic((uint32_t)g.tiles_x);
+  }
   return true;
 }
 
@@ -684,6 +705,12 @@ static int launch_pwdw(const PirPwDw* d, cudaStream_t stream) {
     const uint64_t strides[1] = {kpad * 2};
     const uint32_t box[2] = {64, 16};
     if (int e = pir_make_tmap(&tmB, dt, 2, d->w, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  }
+  static const bool generic = getenv("PIR_PWDW_NKB0") != nullptr;
+  if (!generic) {
+    if (p.g.nkb == 1 && p.mt == 2 && p.na == 2 && p.sc == 4 && p.ng == 4) return launch_cfg<T, FwCfg<2, 16, 6, GATE, 2, 4, 4, 1>>(p, tmA, tmB, stream);
+    if (p.g.nkb == 2 && p.mt == 2 && p.na == 1 && p.sc == 4 && p.ng == 4) return launch_cfg<T, FwCfg<2, 16, 6, GATE, 1, 4, 4, 2>>(p, tmA, tmB, stream);
+    if (p.g.nkb == 3 && p.mt == 2 && p.na == 1 && p.sc == 2 && p.ng == 2) return launch_cfg<T, FwCfg<2, 16, 3, GATE, 1, 2, 2, 3>>(p, tmA, tmB, stream);
   }
   if (p.mt == 2 && p.na == 2 && p.sc == 4 && p.ng == 4) return launch_cfg<T, FwCfg<2, 16, 6, GATE, 2, 4, 4>>(p, tmA, tmB, stream);
   if (p.mt == 2 && p.na == 1 && p.sc == 4 && p.ng == 4) return launch_cfg<T, FwCfg<2, 16, 6, GATE, 1, 4, 4>>(p, tmA, tmB, stream);
