@@ -723,6 +723,10 @@ static int launch_pwdw(const PirPwDw* d, cudaStream_t stream) {
   return pir_fail(PIR_ERR_UNSUPPORTED, "pir_pwdw: configuration <%d,%d,%d> is not compiled", p.mt, p.na, p.sc);
 }
 
+// channel-major variant (pwdwt.cu)
+bool pwdwt_supported(const PirPwDw* d);
+int pwdwt_run(const PirPwDw* d, cudaStream_t stream);
+
 }  // namespace pir
 
 extern "C" int pir_pwdw_supported(int32_t C, int32_t N, int32_t gate) {
@@ -740,6 +744,7 @@ extern "C" int pir_pwdw(const PirPwDw* d, void* stream) {
       ((uintptr_t)d->a & 15) || ((uintptr_t)d->w & 15) || ((uintptr_t)d->out & 15) || ((uintptr_t)d->dw_w & 15))
     return pir_fail(PIR_ERR_ARG, "pir_pwdw: channel counts / pitches / pointers are not 16-byte aligned");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (pir::pwdwt_supported(d)) return pir::pwdwt_run(d, s);
   if (d->dtype == PIR_DTYPE_BF16)
     return d->gate ? pir::launch_pwdw<pir::BF16, true>(d, s) : pir::launch_pwdw<pir::BF16, false>(d, s);
   return d->gate ? pir::launch_pwdw<pir::FP16, true>(d, s) : pir::launch_pwdw<pir::FP16, false>(d, s);

@@ -1,0 +1,544 @@
+// Fused  LayerNorm -> 1x1 conv -> depthwise 3x3 -> GELU gate  (GDFN front half, net/model.py:60-63 + :88-90 + :96-97), second
+// generation: CHANNEL-MAJOR accumulators.  pwdw.cu computes D[pixel][channel] = X . W^T, so a thread that reads its TMEM lane owns
+// ONE pixel and the 3x3 stencil has to go through a shared-memory round trip (drain, barrier, LDS).  Here the product is
+// transposed,
+//        D[channel][pixel] = W . X^T        (A = 128 weight rows, K-major;  B = the LayerNormed x tile, K-major, N = pixels)
+// so a TMEM lane is a CHANNEL and the columns are the pixels of the halo'd tile in raster order: a thread reads rows of ITS channel
+// straight from tensor memory (tcgen05.ld), packs horizontally adjacent pixels into half2 pairs and runs the whole 3x3 stencil, the
+// GELU gate and the store from registers -- no shared-memory tile, no LDS, no group barriers.  x1 and x2 of the gate (channels c and
+// hidden + c) are two accumulators of the SAME lane (two MMA chains against the two 128-row weight slabs).
+//
+// Per CTA (persistent, one per SM, 576 threads): warp 0 TMA producer | warp 1 MMA issuer | warps 2-17 compute.
+// Item = (image, 12 x 16 output tile); halo'd tile 14 x 18 = 252 pixels (256 rows in shared memory), LayerNorm in place as in pwdw.cu.
+// Per item, per block of 128 gated channels, three sub-units of 6 halo'd rows (4 output rows): N = 112 columns (6 x 18 = 108 used)
+// per accumulator, two accumulators (x1 | x2) per TMEM buffer, two buffers (512 columns).  The B operand of a sub-unit is the x
+// tile at row offset 72 * third (9 KiB: swizzle-atom aligned), so the overlapping rows are never copied.
+// Compute warp w: lane quarter q = w & 3 (channels 32 q .. 32 q + 31 of the block), column patch s = (w - 2) >> 2 (output columns
+// 4 s .. 4 s + 3); per sub-unit a thread produces 4 x 4 gated outputs of one channel.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace pir {
+
+constexpr int kTwThreads = 576;
+constexpr int kTwCompute = 512;
+constexpr int kTwTW = 16, kTwTH = 12, kTwSW = 18, kTwNPIX = 14 * 18;     // output tile, halo'd width, halo'd pixels
+constexpr int kTwN = 112;                                                  // UMMA N of a sub-unit (6 x 18 = 108 columns used)
+constexpr int kTwRowsPerThird = 4;
+
+struct TwArgs {
+  int B, H, W, C;
+  int hp;                  // gated channels (multiple of 128)
+  int n_cb;                // hp / 128
+  int ln_mode;
+  int tiles_x, tiles_y, n_items;
+  uint32_t mg_per_img, mg_tiles_x;
+  uint32_t off_w, off_tab, off_vt;    // byte offsets from the 1024-aligned base: weight ring, per-channel tap table, t vectors
+  const void* dw_w;        // [9][2 hp] fp16
+  const float* dw_bias;    // [2 hp] or null
+  const float* vec_t;      // [2 hp] or null
+  void* out;
+  long long out_pitch, out_bstride;
+};
+
+__device__ __forceinline__ uint32_t tw_div(uint32_t n, uint32_t magic) { return magic ? __umulhi(n, magic) : n; }
+__device__ __forceinline__ uint32_t tw_pack_sat(float lo, float hi) {
+  uint32_t r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r;
+}
+__device__ __forceinline__ uint32_t tw_fma2(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ uint32_t tw_mul2(uint32_t a, uint32_t b) {
+  uint32_t r; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t tw_min2(uint32_t a, uint32_t b) {
+  uint32_t r; asm("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t tw_tanh2(uint32_t a) {
+  uint32_t r; asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a)); return r;
+}
+__device__ __forceinline__ uint32_t tw_bcast_lo(uint32_t v) { uint32_t r; asm("prmt.b32 %0, %1, %1, 0x1010;" : "=r"(r) : "r"(v)); return r; }
+__device__ __forceinline__ uint32_t tw_bcast_hi(uint32_t v) { uint32_t r; asm("prmt.b32 %0, %1, %1, 0x3232;" : "=r"(r) : "r"(v)); return r; }
+// gelu(p) * q on packed fp16 pairs: the three-coefficient erf-GELU fit of common.cuh in its tanh form (see pwdw.cu)
+__device__ __forceinline__ uint32_t tw_gate2(uint32_t p, uint32_t q) {
+  constexpr uint32_t kA = 0x3a613a61u, kB = 0x28bd28bdu, kC = 0x8dc28dc2u, k25 = 0x4e404e40u, kHalf = 0x38003800u;
+  const uint32_t u = tw_min2(tw_mul2(p, p), k25);
+  const uint32_t t = tw_fma2(u, tw_fma2(u, kC, kB), kA);
+  const uint32_t th = tw_tanh2(tw_mul2(p, t));
+  const uint32_t hx = tw_mul2(p, kHalf);
+  return tw_mul2(tw_fma2(hx, th, hx), q);
+}
+__device__ __forceinline__ float2 tw_h2f2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tw_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
+
+
+// One sub-unit of one thread: 6 halo'd rows x 6 columns of its channel's two accumulators (x1 at tcol, x2 at tcol + 128) -> 4 x 4
+// gated outputs.  BORDER: the tile touches the image border -- t is added to in-image pixels only (the zero padding of the depthwise
+// conv must stay zero) and stores are bounds-checked; interior tiles take the straight-line path.
+template <class T, bool GATE32, bool BORDER>
+__device__ __forceinline__ void tw_subunit(uint32_t tcol, const uint32_t (&w1)[9], const uint32_t (&w2)[9], uint32_t seed1, uint32_t seed2,
+                                           float2 tv, uint32_t col_in, int yo, int xo, int H, int W, unsigned short* orow, int pitch,
+                                           size_t row_stride) {
+  constexpr int SW = kTwSW;
+  uint32_t a1[3][2], a2[3][2];                             // accumulator rows (mod 3) x 2 pixel pairs, per tensor
+  uint32_t r1[8], r2[8];
+  tw_ld8(tcol, r1); tw_ld8(tcol + 128u, r2);
+#pragma unroll
+  for (int ri = 0; ri < 6; ++ri) {
+    tmem_ld_wait();
+    if (BORDER) {
+      const int py = yo - 1 + ri;
+      if (py >= 0 && py < H) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          if (col_in & (1u << j)) {
+            r1[j] = __float_as_uint(__uint_as_float(r1[j]) + tv.x);
+            r2[j] = __float_as_uint(__uint_as_float(r2[j]) + tv.y);
+          }
+        }
+      }
+    }
+    // pairs of horizontally adjacent pixels: E_j = (v[2j], v[2j+1]), O_j = (v[2j+1], v[2j+2])
+    uint32_t e1[3], o1[2], e2[3], o2[2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      e1[j] = tw_pack_sat(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+      e2[j] = tw_pack_sat(__uint_as_float(r2[2 * j]), __uint_as_float(r2[2 * j + 1]));
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      o1[j] = tw_pack_sat(__uint_as_float(r1[2 * j + 1]), __uint_as_float(r1[2 * j + 2]));
+      o2[j] = tw_pack_sat(__uint_as_float(r2[2 * j + 1]), __uint_as_float(r2[2 * j + 2]));
+    }
+    if (ri < 5) { tw_ld8(tcol + (uint32_t)((ri + 1) * SW), r1); tw_ld8(tcol + 128u + (uint32_t)((ri + 1) * SW), r2); }
+    if (ri < 4) { a1[ri % 3][0] = seed1; a1[ri % 3][1] = seed1; a2[ri % 3][0] = seed2; a2[ri % 3][1] = seed2; }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ro = ri - ky;
+      if (ro >= 0 && ro < 4) {
+        uint32_t* p = a1[ro % 3];
+        uint32_t* qq = a2[ro % 3];
+        p[0] = tw_fma2(e1[0], w1[ky * 3], p[0]); p[0] = tw_fma2(o1[0], w1[ky * 3 + 1], p[0]); p[0] = tw_fma2(e1[1], w1[ky * 3 + 2], p[0]);
+        p[1] = tw_fma2(e1[1], w1[ky * 3], p[1]); p[1] = tw_fma2(o1[1], w1[ky * 3 + 1], p[1]); p[1] = tw_fma2(e1[2], w1[ky * 3 + 2], p[1]);
+        qq[0] = tw_fma2(e2[0], w2[ky * 3], qq[0]); qq[0] = tw_fma2(o2[0], w2[ky * 3 + 1], qq[0]); qq[0] = tw_fma2(e2[1], w2[ky * 3 + 2], qq[0]);
+        qq[1] = tw_fma2(e2[1], w2[ky * 3], qq[1]); qq[1] = tw_fma2(o2[1], w2[ky * 3 + 1], qq[1]); qq[1] = tw_fma2(e2[2], w2[ky * 3 + 2], qq[1]);
+      }
+    }
+    if (ri >= 2) {
+      const int ro = ri - 2;
+      uint32_t g0, g1;
+      if (GATE32) {
+        const float2 pa = tw_h2f2(a1[ro % 3][0]), pb = tw_h2f2(a1[ro % 3][1]);
+        const float2 qa = tw_h2f2(a2[ro % 3][0]), qb = tw_h2f2(a2[ro % 3][1]);
+        g0 = pack2<T>(gelu_erf(pa.x) * qa.x, gelu_erf(pa.y) * qa.y);
+        g1 = pack2<T>(gelu_erf(pb.x) * qb.x, gelu_erf(pb.y) * qb.y);
+      } else {
+        g0 = tw_gate2(a1[ro % 3][0], a2[ro % 3][0]);
+        g1 = tw_gate2(a1[ro % 3][1], a2[ro % 3][1]);
+        if (T::kFmt == 1) {                                   // bf16 storage: fp16 pairs -> bf16 pairs
+          const float2 fa = tw_h2f2(g0), fb = tw_h2f2(g1);
+          g0 = pack2<T>(fa.x, fa.y); g1 = pack2<T>(fb.x, fb.y);
+        }
+      }
+      if (!BORDER) {
+        orow[0] = (unsigned short)(g0 & 0xffffu);
+        orow[pitch] = (unsigned short)(g0 >> 16);
+        orow[2 * pitch] = (unsigned short)(g1 & 0xffffu);
+        orow[3 * pitch] = (unsigned short)(g1 >> 16);
+      } else if (yo + ro < H) {
+        if (xo + 0 < W) orow[0] = (unsigned short)(g0 & 0xffffu);
+        if (xo + 1 < W) orow[pitch] = (unsigned short)(g0 >> 16);
+        if (xo + 2 < W) orow[2 * pitch] = (unsigned short)(g1 & 0xffffu);
+        if (xo + 3 < W) orow[3 * pitch] = (unsigned short)(g1 >> 16);
+      }
+      orow += row_stride;
+      asm volatile("" : "+l"(orow));
+    }
+  }
+}
+
+// Shared-memory matrix descriptor with the swizzle mode as a parameter (2: 128-byte rows, 4: 64-byte rows); see make_sdesc_sw128
+__device__ __forceinline__ uint64_t tw_sdesc(uint32_t sbo_bytes, uint32_t layout) {
+  return ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+
+// Shared-memory plan (bytes from the 1024-aligned base):
+//   [x tile: 2 x NKB k-blocks x 256 rows x KBB B] [weights, resident: NKB k-blocks x 2 hp rows x KBB B] [tap table: hp x 48 B] [t: hp x 8 B]
+// KBB = bytes of a k-block row: 128 (64 channels, 128-byte swizzle; C = 48) or 64 (32 channels, 64-byte swizzle; C = 96 = 3 x 32, so
+// nothing is padded, two x tiles and the WHOLE weight matrix fit next to each other: the weights are fetched once per CTA and the
+// next item's tile is loaded and LayerNormed while the current one is multiplied).
+template <class T, int NKB, int KBB, bool GATE32>
+__global__ void __launch_bounds__(kTwThreads, 1)
+pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TwArgs g) {
+  constexpr int TW = kTwTW, TH = kTwTH, SW = kTwSW, NPIX = kTwNPIX;
+  constexpr int NA = 2;
+  constexpr int KCH = KBB / 2;                                 // channels per k-block
+  constexpr uint32_t A_KB = 256 * KBB;                         // one k-block of the halo'd x tile (256 rows)
+  constexpr uint32_t X_BYTES = NKB * A_KB;
+  constexpr uint32_t SW_LAYOUT = KBB == 128 ? 2u : 4u;
+  constexpr uint32_t SBO = 8 * KBB;                            // 8-row swizzle atom
+  const uint32_t w_kb_bytes = (uint32_t)(2 * g.hp) * KBB;      // one k-block of the resident weights (all 2 hp rows)
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_afull[NA], bar_aready[NA], bar_aempty[NA];
+  __shared__ __align__(8) uint64_t bar_wfull;
+  __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  uint4* stab = reinterpret_cast<uint4*>(base_ptr + g.off_tab);          // [hp][3] x 16 B: w1[9] w2[9] seed1i seed2i bias1 bias2 0 0 (fp16)
+  float2* svt = reinterpret_cast<float2*>(base_ptr + g.off_vt);          // [hp] (t1, t2)
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW);
+    for (int i = 0; i < NA; ++i) {
+      mbar_init(smem_u32(&bar_afull[i]), 1); mbar_init(smem_u32(&bar_aready[i]), kTwCompute / 32); mbar_init(smem_u32(&bar_aempty[i]), 1);
+    }
+    mbar_init(smem_u32(&bar_wfull), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tfull[i]), 1); mbar_init(smem_u32(&bar_tempty[i]), kTwCompute / 32); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), 512); tmem_relinquish(); }
+  // per-CTA tables: taps, accumulator seeds and t of every gated channel
+  {
+    const unsigned short* src = reinterpret_cast<const unsigned short*>(g.dw_w);
+    unsigned short* tab = reinterpret_cast<unsigned short*>(stab);
+    const int n_pre = 2 * g.hp;
+    for (int i = threadIdx.x; i < g.hp; i += kTwThreads) {
+      float ws1 = 0.f, ws2 = 0.f;
+      for (int tap = 0; tap < 9; ++tap) {
+        const unsigned short a = src[(size_t)tap * n_pre + i], b = src[(size_t)tap * n_pre + g.hp + i];
+        tab[i * 24 + tap] = a; tab[i * 24 + 9 + tap] = b;
+        ws1 += __half2float(__ushort_as_half(a)); ws2 += __half2float(__ushort_as_half(b));
+      }
+      const float b1 = g.dw_bias ? g.dw_bias[i] : 0.f, b2 = g.dw_bias ? g.dw_bias[g.hp + i] : 0.f;
+      const float t1 = g.vec_t ? g.vec_t[i] : 0.f, t2 = g.vec_t ? g.vec_t[g.hp + i] : 0.f;
+      tab[i * 24 + 18] = __half_as_ushort(__float2half_rn(b1 + t1 * ws1));      // interior tiles: the conv of the constant t is a constant
+      tab[i * 24 + 19] = __half_as_ushort(__float2half_rn(b2 + t2 * ws2));
+      tab[i * 24 + 20] = __half_as_ushort(__float2half_rn(b1));
+      tab[i * 24 + 21] = __half_as_ushort(__float2half_rn(b2));
+      tab[i * 24 + 22] = 0; tab[i * 24 + 23] = 0;
+      svt[i] = make_float2(t1, t2);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int per_img = g.tiles_x * g.tiles_y;
+  auto item_geo = [&](int item, int& b, int& x0, int& y0) {
+    b = (int)tw_div((uint32_t)item, g.mg_per_img);
+    const int rr = item - b * per_img;
+    const int ty = (int)tw_div((uint32_t)rr, g.mg_tiles_x);
+    x0 = (rr - ty * g.tiles_x) * TW; y0 = ty * TH;
+  };
+
+  if (warp == 0) {
+    // ========================================= TMA producer ==========================================
+    if (elect_one()) {                               // the whole weight matrix, once
+      const uint32_t full = smem_u32(&bar_wfull);
+      mbar_expect_tx(full, (uint32_t)NKB * w_kb_bytes);
+      for (int kb = 0; kb < NKB; ++kb)
+        for (int r0 = 0; r0 < 2 * g.hp; r0 += 128)
+          tma_load_2d(base + g.off_w + (uint32_t)kb * w_kb_bytes + (uint32_t)r0 * KBB, &tmW, full, kb * KCH, r0);
+    }
+    __syncwarp();
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+      int b, x0, y0;
+      item_geo(item, b, x0, y0);
+      const uint32_t ab = it % NA;
+      mbar_wait_sleep(smem_u32(&bar_aempty[ab]), ((it / NA) & 1u) ^ 1u);
+      if (elect_one()) {
+        const uint32_t full = smem_u32(&bar_afull[ab]);
+        mbar_expect_tx(full, (uint32_t)NKB * (uint32_t)(NPIX * KBB));
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) tma_load_4d(base + ab * X_BYTES + (uint32_t)kb * A_KB, &tmA, full, kb * KCH, x0 - 1, y0 - 1, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ========================================= MMA issuer ============================================
+    const uint64_t desc_hi = tw_sdesc(SBO, SW_LAYOUT);
+    const uint32_t idesc = make_idesc_f16(T::kFmt, 128, kTwN, 0, 0);
+    mbar_wait(smem_u32(&bar_wfull), 0);
+    uint32_t it = 0, tq = 0;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+      const uint32_t ab = it % NA;
+      mbar_wait(smem_u32(&bar_aready[ab]), (it / NA) & 1u);
+      tc_fence_after();
+      for (int cb = 0; cb < g.n_cb; ++cb) {
+        for (int third = 0; third < 3; ++third, ++tq) {
+          const uint32_t tb = tq & 1u;
+          mbar_wait(smem_u32(&bar_tempty[tb]), ((tq >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d1 = tmem_base + tb * 256u, d2 = d1 + 128u;
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
+              const int rem = g.C - kb * KCH;
+              const int ksteps = rem >= KCH ? KCH / 16 : (rem + 15) >> 4;
+              const uint32_t x_lo = (base + ab * X_BYTES + (uint32_t)kb * A_KB + (uint32_t)third * (72u * KBB)) >> 4;
+              const uint32_t w_lo = (base + g.off_w + (uint32_t)kb * w_kb_bytes + (uint32_t)(cb * 128) * KBB) >> 4;
+              const uint64_t xd = desc_hi | (uint64_t)(x_lo & 0x3fffu);
+              const uint64_t w1d = desc_hi | (uint64_t)(w_lo & 0x3fffu);
+              const uint64_t w2d = desc_hi | (uint64_t)((w_lo + (((uint32_t)g.hp * KBB) >> 4)) & 0x3fffu);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                umma_f16(d1, w1d + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idesc, acc);
+                umma_f16(d2, w2d + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idesc, acc);
+              }
+            }
+            umma_commit(smem_u32(&bar_tfull[tb]));
+            if (third == 2 && cb == g.n_cb - 1) umma_commit(smem_u32(&bar_aempty[ab]));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ============================ LayerNorm in place, then stencil + gate + store from TMEM ============================
+    const int ct = threadIdx.x - 64;                 // 0..511
+    const int q = warp & 3;                          // TMEM lane quarter of this warp
+    const int s = (warp - 2) >> 2;                   // column patch: output columns 4 s .. 4 s + 3
+    constexpr int LNR = (NPIX * 4 + kTwCompute - 1) / kTwCompute;
+    const float inv_k = 1.0f / (float)g.C;
+    auto layernorm_tile = [&](int x0, int y0, uint32_t itn) {
+      const uint32_t ab = itn % NA;
+      uint8_t* a_tile = base_ptr + (size_t)ab * X_BYTES;
+      mbar_wait(smem_u32(&bar_afull[ab]), (itn / NA) & 1u);
+      if (g.ln_mode) {
+#pragma unroll
+        for (int r = 0; r < LNR; ++r) {
+          const int task = r * kTwCompute + ct;
+          const int m = task >> 2, part = task & 3;
+          const int my = m / SW;
+          const int py = y0 - 1 + my, px = x0 - 1 + (m - my * SW);
+          const bool act = m < NPIX && py >= 0 && py < g.H && px >= 0 && px < g.W;
+          // a thread owns CPT physical 16-byte chunks of every k-block row: 2 part + (e ^ (m & 1)) of 8 (128-byte rows; the row parity
+          // keeps the quarter-warp's LDS.128 conflict free) or chunk `part` of 4 (64-byte rows)
+          constexpr int CPT = KBB / 64;
+          const int sw = KBB == 128 ? (m & 7) : ((m >> 1) & 3);               // logical chunk = physical chunk ^ sw
+          float s1 = 0.f, s2 = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb) {
+            if (act) {
+              const uint8_t* a_row = a_tile + (size_t)kb * A_KB + (size_t)m * KBB;
+#pragma unroll
+              for (int e = 0; e < CPT; ++e) {
+                const int j = KBB == 128 ? 2 * part + (e ^ (m & 1)) : part;
+                const uint4 v = *reinterpret_cast<const uint4*>(a_row + (j << 4));
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const unsigned short lo = lo16(w4[i]), hi = hi16(w4[i]);
+                  s1 = fma16<T>(lo, T::kOne, s1);
+                  s1b = fma16<T>(hi, T::kOne, s1b);
+                  s2 = fma16<T>(lo, lo, s2);
+                  s2b = fma16<T>(hi, hi, s2b);
+                }
+              }
+            }
+          }
+          s1 += s1b; s2 += s2b;
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+          const float mu = s1 * inv_k;
+          const float rstd = rsqrtf(fmaxf(fmaf(s2, inv_k, -mu * mu), 0.f) + 1e-5f);
+          const float shift = g.ln_mode == 2 ? 0.f : -rstd * mu;
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb) {
+            if (act) {
+              uint8_t* a_row = a_tile + (size_t)kb * A_KB + (size_t)m * KBB;
+              const int valid = g.C - kb * KCH;                               // the zero padding above C (last k-block) must stay zero
+#pragma unroll
+              for (int e = 0; e < CPT; ++e) {
+                const int j = KBB == 128 ? 2 * part + (e ^ (m & 1)) : part;
+                if ((j ^ sw) * 8 < valid) {
+                  uint4 v = *reinterpret_cast<const uint4*>(a_row + (j << 4));
+                  uint32_t* w4 = &v.x;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    w4[i] = pack2<T>(fmaf(unpack_lo<T>(w4[i]), rstd, shift), fmaf(unpack_hi<T>(w4[i]), rstd, shift));
+                  *reinterpret_cast<uint4*>(a_row + (j << 4)) = v;
+                }
+              }
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_aready[ab]));
+    };
+
+    uint32_t it = 0, tq = 0;
+    int b = 0, x0 = 0, y0 = 0;
+    if ((int)blockIdx.x < g.n_items) {
+      item_geo(blockIdx.x, b, x0, y0);
+      if (NA == 2) layernorm_tile(x0, y0, 0);
+    }
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(4 * s);
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
+      if (NA == 2) {
+        if (item + (int)gridDim.x < g.n_items) {
+          int nb_, nx0, ny0;
+          item_geo(item + gridDim.x, nb_, nx0, ny0);
+          layernorm_tile(nx0, ny0, it + 1);
+        }
+      } else {
+        layernorm_tile(x0, y0, it);
+      }
+      const bool interior = x0 >= 1 && y0 >= 1 && x0 + TW + 1 <= g.W && y0 + TH + 1 <= g.H;
+      // validity of this thread's six input columns (halo'd columns 4 s .. 4 s + 5) and its four output columns
+      uint32_t col_in = 0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { const int px = x0 - 1 + 4 * s + j; if (px >= 0 && px < g.W) col_in |= 1u << j; }
+      const int xo = x0 + 4 * s;                       // first output column
+      unsigned short* out_img = reinterpret_cast<unsigned short*>(g.out) + (size_t)b * g.out_bstride;
+      const int pitch = (int)g.out_pitch;
+      const size_t row_stride = (size_t)g.W * g.out_pitch;
+
+      for (int cb = 0; cb < g.n_cb; ++cb) {
+        const int ch = cb * 128 + q * 32 + lane;       // gated channel of this thread
+        // taps (packed pairs), seeds
+        const uint4 ta = stab[ch * 3], tb4 = stab[ch * 3 + 1], tc = stab[ch * 3 + 2];
+        // halves: ta = w1[0..7]; tb4 = w1[8] w2[0..6]; tc = w2[7] w2[8] s1i s2i b1 b2 0 0
+        uint32_t w1[9], w2[9];
+        w1[0] = tw_bcast_lo(ta.x); w1[1] = tw_bcast_hi(ta.x); w1[2] = tw_bcast_lo(ta.y); w1[3] = tw_bcast_hi(ta.y);
+        w1[4] = tw_bcast_lo(ta.z); w1[5] = tw_bcast_hi(ta.z); w1[6] = tw_bcast_lo(ta.w); w1[7] = tw_bcast_hi(ta.w);
+        w1[8] = tw_bcast_lo(tb4.x);
+        w2[0] = tw_bcast_hi(tb4.x); w2[1] = tw_bcast_lo(tb4.y); w2[2] = tw_bcast_hi(tb4.y); w2[3] = tw_bcast_lo(tb4.z);
+        w2[4] = tw_bcast_hi(tb4.z); w2[5] = tw_bcast_lo(tb4.w); w2[6] = tw_bcast_hi(tb4.w); w2[7] = tw_bcast_lo(tc.x);
+        w2[8] = tw_bcast_hi(tc.x);
+        const uint32_t seed1 = interior ? tw_bcast_lo(tc.y) : tw_bcast_lo(tc.z);
+        const uint32_t seed2 = interior ? tw_bcast_hi(tc.y) : tw_bcast_hi(tc.z);
+        const float2 tv = svt[ch];
+        const bool add_t = !interior && g.vec_t != nullptr;
+
+        // running output pointer of this thread: (first output row of the sub-unit, first output column, channel)
+        unsigned short* orow = out_img + ((size_t)y0 * g.W + xo) * g.out_pitch + ch;
+        for (int third = 0; third < 3; ++third, ++tq) {
+          const uint32_t tb = tq & 1u;
+          mbar_wait(smem_u32(&bar_tfull[tb]), (tq >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t tcol = t_lane + tb * 256u;
+          const int yo = y0 + third * kTwRowsPerThird;            // first output row of the sub-unit
+          if (interior) tw_subunit<T, GATE32, false>(tcol, w1, w2, seed1, seed2, tv, 0u, yo, xo, g.H, g.W, orow, pitch, row_stride);
+          else tw_subunit<T, GATE32, true>(tcol, w1, w2, seed1, seed2, add_t ? tv : make_float2(0.f, 0.f), col_in, yo, xo, g.H, g.W, orow, pitch, row_stride);
+          orow += 4 * row_stride;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[tb]));
+        }
+      }
+      if (item + (int)gridDim.x < g.n_items) item_geo(item + gridDim.x, b, x0, y0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <class T, int NKB, int KBB, bool GATE32>
+static int tw_launch(const TwArgs& g, uint32_t smem, const CUtensorMap& tmA, const CUtensorMap& tmW, cudaStream_t stream) {
+  static bool set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16 || !set[dev]) {
+    if (cudaFuncSetAttribute(pwdwt_kernel<T, NKB, KBB, GATE32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+      return pir_fail(PIR_ERR_CUDA, "pir_pwdw: cannot raise dynamic shared memory limit");
+    if (dev >= 0 && dev < 16) set[dev] = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const int grid = g.n_items < num_sms ? g.n_items : num_sms;
+  pwdwt_kernel<T, NKB, KBB, GATE32><<<dim3(grid), dim3(kTwThreads), smem, stream>>>(tmA, tmW, g);
+  return pir_check_launch("pir_pwdw (channel-major)");
+}
+
+// k-block geometry: C <= 64 -> one 64-channel block (128-byte rows); C = 96 -> three 32-channel blocks (64-byte rows, no padding)
+static bool tw_shape(int C, int* nkb, int* kbb) {
+  if (C <= 64) { *nkb = 1; *kbb = 128; return true; }
+  if (C == 96) { *nkb = 3; *kbb = 64; return true; }
+  return false;
+}
+
+// gate == 1, C <= 64 or C == 96, hidden a multiple of 128 and the plan fits shared memory
+bool pwdwt_supported(const PirPwDw* d) {
+  static const bool off = [] { const char* e = getenv("PIR_PWDW_T"); return e && e[0] == '0'; }();
+  if (off || !d->gate) return false;
+  int nkb, kbb;
+  if (!tw_shape(d->C, &nkb, &kbb) || d->N % 128 != 0) return false;
+  const uint32_t need = 2u * nkb * 256u * kbb + (uint32_t)nkb * 2u * d->N * kbb + (uint32_t)d->N * 56u + 1024u;
+  return need <= 227u * 1024u - 1024u;
+}
+
+template <class T>
+static int tw_run(const PirPwDw* d, cudaStream_t stream) {
+  TwArgs g{};
+  g.B = d->B; g.H = d->H; g.W = d->W; g.C = d->C;
+  g.hp = d->N; g.n_cb = d->N / 128; g.ln_mode = d->ln_mode;
+  g.tiles_x = (d->W + kTwTW - 1) / kTwTW; g.tiles_y = (d->H + kTwTH - 1) / kTwTH;
+  g.n_items = g.tiles_x * g.tiles_y * d->B;
+  {
+    auto magic = [](uint32_t dv) { return dv <= 1 ? 0u : (uint32_t)((0x100000000ull + dv - 1) / dv); };
+    const uint64_t per_img = (uint64_t)g.tiles_x * g.tiles_y;
+    if ((uint64_t)g.n_items * per_img >= 0x100000000ull) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_pwdw: too many tiles");
+    g.mg_per_img = magic((uint32_t)per_img); g.mg_tiles_x = magic((uint32_t)g.tiles_x);
+  }
+  int nkb = 0, kbb = 0;
+  tw_shape(d->C, &nkb, &kbb);
+  const int kch = kbb / 2;
+  uint32_t off = 2u * nkb * 256u * kbb;
+  g.off_w = off; off += (uint32_t)nkb * 2u * g.hp * kbb;
+  g.off_tab = off; off += (uint32_t)g.hp * 48u;
+  g.off_vt = off; off += (uint32_t)g.hp * 8u;
+  const uint32_t smem = off + 1024u;
+  if (smem > 227u * 1024u - 1024u) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_pwdw: shared-memory plan does not fit");
+  g.dw_w = d->dw_w; g.dw_bias = d->dw_bias; g.vec_t = d->vec_t;
+  g.out = d->out; g.out_pitch = d->out_pitch; g.out_bstride = d->out_bstride;
+  const CUtensorMapDataType dt = T::kFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = kbb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMap tmA, tmW;
+  {
+    const uint64_t dims[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    const uint64_t strides[3] = {(uint64_t)d->a_pitch * 2, (uint64_t)d->a_pitch * 2 * d->W, (uint64_t)d->a_bstride * 2};
+    const uint32_t box[4] = {(uint32_t)kch, (uint32_t)kTwSW, (uint32_t)(kTwTH + 2), 1};
+    if (int e = pir_make_tmap(&tmA, dt, 4, d->a, dims, strides, box, sw)) return e;
+  }
+  {
+    const uint64_t kpad = (uint64_t)((d->C + 63) / 64) * 64;           // row length of the packed weights (packing.kpad_of)
+    const uint64_t dims[2] = {kpad, (uint64_t)(2 * d->N)};
+    const uint64_t strides[1] = {kpad * 2};
+    const uint32_t box[2] = {(uint32_t)kch, 128};
+    if (int e = pir_make_tmap(&tmW, dt, 2, d->w, dims, strides, box, sw)) return e;
+  }
+  // fp16 storage keeps the fp32 erf-GELU gate unless PIR_PWDW_GATE16=1 (A/B); bf16 storage uses the packed fp16 gate
+  static const bool gate16 = [] { const char* e = getenv("PIR_PWDW_GATE16"); return e && e[0] == '1'; }();
+  const bool g32 = T::kFmt == 0 && !gate16;
+  if (nkb == 1) return g32 ? tw_launch<T, 1, 128, true>(g, smem, tmA, tmW, stream) : tw_launch<T, 1, 128, false>(g, smem, tmA, tmW, stream);
+  return g32 ? tw_launch<T, 3, 64, true>(g, smem, tmA, tmW, stream) : tw_launch<T, 3, 64, false>(g, smem, tmA, tmW, stream);
+}
+
+int pwdwt_run(const PirPwDw* d, cudaStream_t stream) {
+  return d->dtype == PIR_DTYPE_BF16 ? tw_run<BF16>(d, stream) : tw_run<FP16>(d, stream);
+}
+
+}  // namespace pir

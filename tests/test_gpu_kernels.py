@@ -260,6 +260,12 @@ PWDW_CASES = [
     (1, 16, 24, 160, 480, False, LN_NONE, None, 0, False, False),        # no LayerNorm
     (3, 8, 8, 48, 128, True, LN_WITHBIAS, None, 0, False, False),        # tiny images, several per CTA
     (1, 64, 64, 96, 256, True, LN_WITHBIAS, None, 0, False, False),      # many tiles per CTA: ring/phase wrap
+    # channel-major kernel (pwdwt.cu: gate, C <= 128, hidden % 128 == 0): ragged right/bottom tiles, biases, BiasFree, odd batch
+    (2, 40, 72, 48, 128, True, LN_WITHBIAS, None, 0, True, True),
+    (3, 20, 28, 96, 256, True, LN_BIASFREE, None, 0, False, True),
+    (1, 8, 8, 96, 256, True, LN_NONE, None, 0, True, False),
+    (5, 16, 16, 48, 128, True, LN_WITHBIAS, 96, 48, False, False),
+    (2, 128, 128, 96, 256, True, LN_WITHBIAS, None, 0, False, False),
 ]
 
 
