@@ -63,14 +63,16 @@ __device__ __forceinline__ uint32_t tw_bcast_lo(uint32_t v) { uint32_t r; asm("p
 __device__ __forceinline__ uint32_t tw_bcast_hi(uint32_t v) { uint32_t r; asm("prmt.b32 %0, %1, %1, 0x3232;" : "=r"(r) : "r"(v)); return r; }
 // gelu(p) * q on packed fp16 pairs: the three-coefficient erf-GELU fit of common.cuh in its tanh form (see pwdw.cu)
 __device__ __forceinline__ uint32_t tw_gate2(uint32_t p, uint32_t q) {
-  constexpr uint32_t kA = 0x3a613a61u, kB = 0x28bd28bdu, kC = 0x8dc28dc2u, k25 = 0x4e404e40u, kHalf = 0x38003800u;
+  constexpr uint32_t kA = 0x3a613a61u, kB = 0x28bd28bdu, kC = 0x8dc28dc2u, k25 = 0x4e404e40u;
   const uint32_t u = tw_min2(tw_mul2(p, p), k25);
   const uint32_t t = tw_fma2(u, tw_fma2(u, kC, kB), kA);
   const uint32_t th = tw_tanh2(tw_mul2(p, t));
-  const uint32_t hx = tw_mul2(p, kHalf);
-  return tw_mul2(tw_fma2(hx, th, hx), q);
+  return tw_mul2(tw_fma2(p, th, p), q);        // q already carries the factor 0.5
 }
 __device__ __forceinline__ float2 tw_h2f2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ void tw_wait_backoff(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
 // 32 lanes x 8 consecutive fp32 columns
 __device__ __forceinline__ void tw_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -82,11 +84,12 @@ __device__ __forceinline__ void tw_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 // One sub-unit of one thread: 6 halo'd rows x 6 columns of its channel's two accumulators (x1 at tcol, x2 at tcol + 128) -> 4 x 4
 // gated outputs.  BORDER: the tile touches the image border -- t is added to in-image pixels only (the zero padding of the depthwise
 // conv must stay zero) and stores are bounds-checked; interior tiles take the straight-line path.
-template <class T, bool GATE32, bool BORDER>
+template <class T, bool GATE32, bool BORDER, int PITCH>
 __device__ __forceinline__ void tw_subunit(uint32_t tcol, const uint32_t (&w1)[9], const uint32_t (&w2)[9], uint32_t seed1, uint32_t seed2,
-                                           float2 tv, uint32_t col_in, int yo, int xo, int H, int W, unsigned short* orow, int pitch,
+                                           float2 tv, uint32_t col_in, int yo, int xo, int H, int W, unsigned short* orow, int pitch_rt,
                                            size_t row_stride) {
   constexpr int SW = kTwSW;
+  const int pitch = PITCH ? PITCH : pitch_rt;           // compile-time pixel pitch (dense output): the four pixel stores share one address
   uint32_t a1[3][2], a2[3][2];                             // accumulator rows (mod 3) x 2 pixel pairs, per tensor
   uint32_t r1[8], r2[8];
   tw_ld8(tcol, r1); tw_ld8(tcol + 128u, r2);
@@ -174,7 +177,7 @@ __device__ __forceinline__ uint64_t tw_sdesc(uint32_t sbo_bytes, uint32_t layout
 // KBB = bytes of a k-block row: 128 (64 channels, 128-byte swizzle; C = 48) or 64 (32 channels, 64-byte swizzle; C = 96 = 3 x 32, so
 // nothing is padded, two x tiles and the WHOLE weight matrix fit next to each other: the weights are fetched once per CTA and the
 // next item's tile is loaded and LayerNormed while the current one is multiplied).
-template <class T, int NKB, int KBB, bool GATE32>
+template <class T, int NKB, int KBB, bool GATE32, int PITCH>
 __global__ void __launch_bounds__(kTwThreads, 1)
 pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TwArgs g) {
   constexpr int TW = kTwTW, TH = kTwTH, SW = kTwSW, NPIX = kTwNPIX;
@@ -214,14 +217,17 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const unsigned short* src = reinterpret_cast<const unsigned short*>(g.dw_w);
     unsigned short* tab = reinterpret_cast<unsigned short*>(stab);
     const int n_pre = 2 * g.hp;
+    // packed gate: 0.5 p (1 + tanh(.)) q = (p tanh(.) + p) (0.5 q); the 0.5 rides on the x2 branch's taps and bias (exact, a power of two)
+    const float qs = GATE32 ? 1.0f : 0.5f;
     for (int i = threadIdx.x; i < g.hp; i += kTwThreads) {
       float ws1 = 0.f, ws2 = 0.f;
       for (int tap = 0; tap < 9; ++tap) {
         const unsigned short a = src[(size_t)tap * n_pre + i], b = src[(size_t)tap * n_pre + g.hp + i];
-        tab[i * 24 + tap] = a; tab[i * 24 + 9 + tap] = b;
-        ws1 += __half2float(__ushort_as_half(a)); ws2 += __half2float(__ushort_as_half(b));
+        const float bf = __half2float(__ushort_as_half(b)) * qs;
+        tab[i * 24 + tap] = a; tab[i * 24 + 9 + tap] = __half_as_ushort(__float2half_rn(bf));
+        ws1 += __half2float(__ushort_as_half(a)); ws2 += bf;
       }
-      const float b1 = g.dw_bias ? g.dw_bias[i] : 0.f, b2 = g.dw_bias ? g.dw_bias[g.hp + i] : 0.f;
+      const float b1 = g.dw_bias ? g.dw_bias[i] : 0.f, b2 = (g.dw_bias ? g.dw_bias[g.hp + i] : 0.f) * qs;
       const float t1 = g.vec_t ? g.vec_t[i] : 0.f, t2 = g.vec_t ? g.vec_t[g.hp + i] : 0.f;
       tab[i * 24 + 18] = __half_as_ushort(__float2half_rn(b1 + t1 * ws1));      // interior tiles: the conv of the constant t is a constant
       tab[i * 24 + 19] = __half_as_ushort(__float2half_rn(b2 + t2 * ws2));
@@ -272,16 +278,16 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ========================================= MMA issuer ============================================
     const uint64_t desc_hi = tw_sdesc(SBO, SW_LAYOUT);
     const uint32_t idesc = make_idesc_f16(T::kFmt, 128, kTwN, 0, 0);
-    mbar_wait(smem_u32(&bar_wfull), 0);
+    mbar_wait_sleep(smem_u32(&bar_wfull), 0);
     uint32_t it = 0, tq = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
       const uint32_t ab = it % NA;
-      mbar_wait(smem_u32(&bar_aready[ab]), (it / NA) & 1u);
+      tw_wait_backoff(smem_u32(&bar_aready[ab]), (it / NA) & 1u);    // a spinning issuer warp takes issue slots from the compute warps of its scheduler
       tc_fence_after();
       for (int cb = 0; cb < g.n_cb; ++cb) {
         for (int third = 0; third < 3; ++third, ++tq) {
           const uint32_t tb = tq & 1u;
-          mbar_wait(smem_u32(&bar_tempty[tb]), ((tq >> 1) & 1u) ^ 1u);
+          tw_wait_backoff(smem_u32(&bar_tempty[tb]), ((tq >> 1) & 1u) ^ 1u);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t d1 = tmem_base + tb * 256u, d2 = d1 + 128u;
@@ -435,8 +441,8 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t tcol = t_lane + tb * 256u;
           const int yo = y0 + third * kTwRowsPerThird;            // first output row of the sub-unit
-          if (interior) tw_subunit<T, GATE32, false>(tcol, w1, w2, seed1, seed2, tv, 0u, yo, xo, g.H, g.W, orow, pitch, row_stride);
-          else tw_subunit<T, GATE32, true>(tcol, w1, w2, seed1, seed2, add_t ? tv : make_float2(0.f, 0.f), col_in, yo, xo, g.H, g.W, orow, pitch, row_stride);
+          if (interior) tw_subunit<T, GATE32, false, PITCH>(tcol, w1, w2, seed1, seed2, tv, 0u, yo, xo, g.H, g.W, orow, pitch, row_stride);
+          else tw_subunit<T, GATE32, true, PITCH>(tcol, w1, w2, seed1, seed2, add_t ? tv : make_float2(0.f, 0.f), col_in, yo, xo, g.H, g.W, orow, pitch, row_stride);
           orow += 4 * row_stride;
           tc_fence_before();
           __syncwarp();
@@ -453,13 +459,13 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <class T, int NKB, int KBB, bool GATE32>
+template <class T, int NKB, int KBB, bool GATE32, int PITCH>
 static int tw_launch(const TwArgs& g, uint32_t smem, const CUtensorMap& tmA, const CUtensorMap& tmW, cudaStream_t stream) {
   static bool set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 16 || !set[dev]) {
-    if (cudaFuncSetAttribute(pwdwt_kernel<T, NKB, KBB, GATE32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(pwdwt_kernel<T, NKB, KBB, GATE32, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
       return pir_fail(PIR_ERR_CUDA, "pir_pwdw: cannot raise dynamic shared memory limit");
     if (dev >= 0 && dev < 16) set[dev] = true;
   }
@@ -469,7 +475,7 @@ static int tw_launch(const TwArgs& g, uint32_t smem, const CUtensorMap& tmA, con
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = g.n_items < num_sms ? g.n_items : num_sms;
-  pwdwt_kernel<T, NKB, KBB, GATE32><<<dim3(grid), dim3(kTwThreads), smem, stream>>>(tmA, tmW, g);
+  pwdwt_kernel<T, NKB, KBB, GATE32, PITCH><<<dim3(grid), dim3(kTwThreads), smem, stream>>>(tmA, tmW, g);
   return pir_check_launch("pir_pwdw (channel-major)");
 }
 
@@ -533,8 +539,13 @@ static int tw_run(const PirPwDw* d, cudaStream_t stream) {
   // fp16 storage keeps the fp32 erf-GELU gate unless PIR_PWDW_GATE16=1 (A/B); bf16 storage uses the packed fp16 gate
   static const bool gate16 = [] { const char* e = getenv("PIR_PWDW_GATE16"); return e && e[0] == '1'; }();
   const bool g32 = T::kFmt == 0 && !gate16;
-  if (nkb == 1) return g32 ? tw_launch<T, 1, 128, true>(g, smem, tmA, tmW, stream) : tw_launch<T, 1, 128, false>(g, smem, tmA, tmW, stream);
-  return g32 ? tw_launch<T, 3, 64, true>(g, smem, tmA, tmW, stream) : tw_launch<T, 3, 64, false>(g, smem, tmA, tmW, stream);
+  // the networks write a dense gated tensor (pitch == hidden): those two pitches are compiled in
+  if (nkb == 1) {
+    if (d->out_pitch == 128) return g32 ? tw_launch<T, 1, 128, true, 128>(g, smem, tmA, tmW, stream) : tw_launch<T, 1, 128, false, 128>(g, smem, tmA, tmW, stream);
+    return g32 ? tw_launch<T, 1, 128, true, 0>(g, smem, tmA, tmW, stream) : tw_launch<T, 1, 128, false, 0>(g, smem, tmA, tmW, stream);
+  }
+  if (d->out_pitch == 256) return g32 ? tw_launch<T, 3, 64, true, 256>(g, smem, tmA, tmW, stream) : tw_launch<T, 3, 64, false, 256>(g, smem, tmA, tmW, stream);
+  return g32 ? tw_launch<T, 3, 64, true, 0>(g, smem, tmA, tmW, stream) : tw_launch<T, 3, 64, false, 0>(g, smem, tmA, tmW, stream);
 }
 
 int pwdwt_run(const PirPwDw* d, cudaStream_t stream) {

@@ -1,6 +1,8 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_gpu_kernels.py -x -q -k "pwdw" 2>&1 | tail -15
+python -m pytest tests/test_gpu_kernels.py -x -q -k "pwdw" 2>&1 | tail -5
 for a in "96 256 1" "48 128 1"; do
-  PIR_PWDW_T=0 python tools/time_pwdw.py 16 256 256 $a 20 2>&1 | grep "pwdw B" | sed "s/^/old /"
-  python tools/time_pwdw.py 16 256 256 $a 20 2>&1 | grep "pwdw B" | sed "s/^/new /"
+  PIR_PWDW_T=0 python tools/time_pwdw.py 16 256 256 $a 20 2>&1 | grep "pwdw B" | sed "s/^/old bf16 /"
+  python tools/time_pwdw.py 16 256 256 $a 20 2>&1 | grep "pwdw B" | sed "s/^/new bf16 /"
+  PIR_TIME_DTYPE=fp16 python tools/time_pwdw.py 16 256 256 $a 20 2>&1 | grep "pwdw B" | sed "s/^/new fp16 gate32 /"
+  PIR_PWDW_GATE16=1 PIR_TIME_DTYPE=fp16 python tools/time_pwdw.py 16 256 256 $a 20 2>&1 | grep "pwdw B" | sed "s/^/new fp16 gate16 /"
 done | tee gpurun_out/r2_pwdw_ab3.txt

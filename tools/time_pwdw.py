@@ -13,7 +13,7 @@ from promptir_b200._lib import LN_WITHBIAS  # noqa: E402
 def main():
     B, H, W, C, N, gate = (int(v) for v in sys.argv[1:7])
     reps = int(sys.argv[7]) if len(sys.argv) > 7 else 10
-    dt = torch.bfloat16
+    dt = torch.float16 if os.environ.get('PIR_TIME_DTYPE') == 'fp16' else torch.bfloat16
     torch.manual_seed(0)
     npre = 2 * N if gate else N
     x = torch.randn(B, H, W, C, device="cuda").to(dt)
