@@ -221,7 +221,7 @@ def run_ours(args):
     classes = {}
     for i, r in enumerate(eng.ops):
         tag = r.get("tag") or r["kind"]
-        src = r.get("a") if r.get("a") is not None else (r.get("x") if r.get("x") is not None else r.get("qkv"))
+        src = next((r[k] for k in ("a", "x", "qk", "qkv") if r.get(k) is not None), None)
         shape = tuple(src.shape) if src is not None else ()
         t_ms = statistics.mean(evs[rep][i][0].elapsed_time(evs[rep][i][1]) for rep in range(nrep))
         by, fl = op_cost(r)

@@ -88,7 +88,8 @@ int pir_dwconv3x3(const PirDwConv* d, void* stream);
  * gate == 0: out[b,p,n] = dw3x3( W . LN(x) )[n],                                   n < N      (model.py:60-63,111-112,120)
  * gate == 1: out[b,p,n] = gelu_erf(dw3x3(W . LN(x))[n]) * dw3x3(W . LN(x))[N + n], n < N      (model.py:60-63,88-90,96-97)
  * Same function as pir_gemm (ln fold) followed by pir_dwconv3x3, but the pre-conv tensor (N resp. 2N channels per
- * pixel) stays in shared memory as fp16 (values saturate at +-65504) and the LayerNorm is applied to the x tile
+ * pixel) never reaches HBM: it is converted from the fp32 accumulators to fp16 for the stencil (values saturate at +-65504;
+ * shared-memory tile in pwdw.cu, straight from tensor memory in pwdwt.cu) and the LayerNorm is applied to the x tile
  * before the GEMM (normalised rows rounded to the 16-bit type; gamma lives in w, beta in vec_t).  w: packed
  * [N or 2N][Kpad] 16-bit like pir_gemm; vec_t: fp32 [N or 2N] additive vector (W.beta + conv bias) or NULL;
  * dw_w: [3][3][N or 2N] fp16 (always IEEE half, also when dtype is bf16); dw_bias fp32 or NULL.
@@ -102,8 +103,13 @@ typedef struct PirPwDw {
   const float* vec_t;
   const void* dw_w; const float* dw_bias;
   void* out; int64_t out_pitch, out_bstride;
+  /* gate == 0 only, optional: channels n >= split are written to out2[..., n - split] instead (MDTA: q|k and v as two dense
+   * tensors, model.py:121, so the Gram and attn.v kernels stream contiguous rows).  out2 == NULL or split <= 0: one tensor.   */
+  void* out2; int64_t out2_pitch, out2_bstride;
+  int32_t split;
 } PirPwDw;
 int pir_pwdw_supported(int32_t C, int32_t N, int32_t gate);
+int pir_pwdw_split_supported(int32_t C, int32_t N);   /* gate == 0 with out2 / split */
 int pir_pwdw(const PirPwDw* d, void* stream);
 
 /* ---- MDTA: transposed (channel) attention -----------------------------------------------------------

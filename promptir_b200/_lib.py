@@ -42,7 +42,8 @@ class PirPwDw(C.Structure):
     _fields_ = [("dtype", i32), ("gate", i32), ("ln_mode", i32), ("B", i32), ("H", i32), ("W", i32), ("C", i32), ("N", i32),
                 ("a", vp), ("a_pitch", i64), ("a_bstride", i64),
                 ("w", vp), ("vec_t", vp), ("dw_w", vp), ("dw_bias", vp),
-                ("out", vp), ("out_pitch", i64), ("out_bstride", i64)]
+                ("out", vp), ("out_pitch", i64), ("out_bstride", i64),
+                ("out2", vp), ("out2_pitch", i64), ("out2_bstride", i64), ("split", i32)]
 
 
 class PirMdta(C.Structure):
@@ -153,6 +154,16 @@ class PirToNhwc16(C.Structure):
                 ("src", vp), ("out", vp), ("out_pitch", i64), ("out_bstride", i64), ("scale", f32)]
 
 
+class PirPackJob(C.Structure):
+    _fields_ = [("kind", i32), ("dst_dtype", i32), ("n", i32), ("k", i32), ("transpose", i32), ("flip", i32),
+                ("n_total", i32), ("k_pad", i32), ("row_split", i32), ("row_hp", i32), ("col_split", i32), ("col_hp", i32),
+                ("gamma_axis", i32), ("reserved", i32),
+                ("src", vp), ("gamma", vp), ("beta", vp), ("bias", vp),
+                ("dst", vp), ("ln_s", vp), ("vec_t", vp)]
+
+
+PACK_POINTWISE, PACK_CONV3X3, PACK_DEPTHWISE, PACK_VEC, PACK_PROMPT = 0, 1, 2, 3, 4
+
 # every symbol include/promptir_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "pir_abi_version": (i32, []),
@@ -161,6 +172,7 @@ SYMBOLS = {
     "pir_gemm": (i32, [C.POINTER(PirGemm), vp]),
     "pir_dwconv3x3": (i32, [C.POINTER(PirDwConv), vp]),
     "pir_pwdw_supported": (i32, [i32, i32, i32]),
+    "pir_pwdw_split_supported": (i32, [i32, i32]),
     "pir_pwdw": (i32, [C.POINTER(PirPwDw), vp]),
     "pir_mdta_splits": (i32, [i32, i32, i32]),
     "pir_mdta_ws_floats": (i64, [i32, i32, i32]),
@@ -193,6 +205,8 @@ SYMBOLS = {
     "pir_psnr_ssim_ws_bytes": (i64, [i32, i32, i32, i32]),
     "pir_psnr_ssim": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
     "pir_add_noise": (i32, [vp, vp, i64, f32, C.c_uint64, vp]),
+    "pir_repack_rows": (i64, [C.POINTER(PirPackJob)]),
+    "pir_repack": (i32, [vp, vp, i32, i32, vp]),
 }
 
 _lib = None

@@ -61,6 +61,9 @@ struct FwArgs {
   const float* vec_t;      // [n_pre] or null
   void* out;
   long long out_pitch, out_bstride;
+  void* out2;              // plain only: channels >= split go here (channel - split); == out / n_pre when there is one tensor
+  long long out2_pitch, out2_bstride;
+  int split;
 };
 
 __device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {
@@ -425,6 +428,10 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       unsigned short* out_item = reinterpret_cast<unsigned short*>(g.out) + (size_t)b * g.out_bstride +
                                  ((size_t)(y0 + band * R) * g.W + (x0 + tx)) * g.out_pitch;
       const size_t out_row = (size_t)g.W * g.out_pitch;
+      // plain kernel with two output tensors (q|k and v): second base pointer / row stride, selected per chunk
+      unsigned short* out_item2 = GATE ? nullptr : reinterpret_cast<unsigned short*>(g.out2) + (size_t)b * g.out2_bstride +
+                                                   ((size_t)(y0 + band * R) * g.W + (x0 + tx)) * g.out2_pitch - g.split;
+      const size_t out_row2 = (size_t)g.W * g.out2_pitch;
 
       for (int sc = 0; sc < n_super; ++sc, ++uses) {
       // the group's chunks of this super-chunk: j = j0, j0 + 2, ... (j0 alternates per item so odd chunk counts balance out)
@@ -543,7 +550,10 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t bb[4] = {sd[0], sd[1], sd[2], sd[3]};
           const int x = x0 + tx;
           const bool ok = ch < g.n_pre && x < g.W;
-          unsigned short* outp = out_item + ch;
+          // q|k and v may be two dense tensors (split is a multiple of 8, so a thread's 8 channels never straddle it)
+          const bool second = ch >= g.split;
+          unsigned short* outp = (second ? out_item2 : out_item) + ch;
+          const size_t orow_stride = second ? out_row2 : out_row;
           const uint8_t* src = conv_buf + (size_t)((band * R) * SW + tx) * 64;
           uint32_t p[3][4];
 #pragma unroll
@@ -575,7 +585,7 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const float2 f = h2_to_f2(p[o % 3][e]);
                 op[e] = pack2<T>(f.x, f.y);
               }
-              if (ok && y0 + band * R + o < g.H && !(FW_DBG(g) & 4)) *reinterpret_cast<uint4*>(outp + o * out_row) = ov;
+              if (ok && y0 + band * R + o < g.H && !(FW_DBG(g) & 4)) *reinterpret_cast<uint4*>(outp + o * orow_stride) = ov;
             }
           }
         }
@@ -690,6 +700,13 @@ static int launch_pwdw(const PirPwDw* d, cudaStream_t stream) {
     p.g.rot = (mode & 2) ? 1 : 0;
   }
   p.g.out = d->out; p.g.out_pitch = d->out_pitch; p.g.out_bstride = d->out_bstride;
+  {
+    const bool two = !d->gate && d->out2 != nullptr && d->split > 0 && d->split < d->N;
+    if (two && (d->split % 8 || d->out2_pitch % 8 || d->out2_bstride % 8 || ((uintptr_t)d->out2 & 15)))
+      return pir_fail(PIR_ERR_ARG, "pir_pwdw: split / out2 pitch / out2 pointer are not 16-byte aligned");
+    p.g.split = two ? d->split : p.g.n_pre;
+    p.g.out2 = two ? d->out2 : d->out; p.g.out2_pitch = two ? d->out2_pitch : d->out_pitch; p.g.out2_bstride = two ? d->out2_bstride : d->out_bstride;
+  }
   const CUtensorMapDataType dt = T::kFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap tmA, tmB;
   {
@@ -735,6 +752,14 @@ extern "C" int pir_pwdw_supported(int32_t C, int32_t N, int32_t gate) {
   pir::FwPlan p;
   if ((C % 8) || (N % 8) || C <= 0 || N <= 0) return 0;
   return pir::plan_pwdw(&d, &p) == PIR_OK ? 1 : 0;
+}
+
+extern "C" int pir_pwdw_split_supported(int32_t C, int32_t N) {
+  PirPwDw d{};
+  d.B = 1; d.H = 64; d.W = 64; d.C = C; d.N = N; d.gate = 0;
+  if ((C % 8) || (N % 8) || C <= 0 || N <= 0) return 0;
+  pir::FwPlan p;
+  return (pir::pwdwt_supported(&d) || pir::plan_pwdw(&d, &p) == PIR_OK) ? 1 : 0;
 }
 
 extern "C" int pir_pwdw(const PirPwDw* d, void* stream) {

@@ -30,8 +30,10 @@ constexpr int kTwRowsPerThird = 4;
 
 struct TwArgs {
   int B, H, W, C;
-  int hp;                  // gated channels (multiple of 128)
-  int n_cb;                // hp / 128
+  int hp;                  // gate: gated channels (multiple of 128); plain: 0
+  int n_rows;              // pre-conv channels = weight rows (gate: 2 hp; plain: N)
+  int n_cb;                // channel blocks per item: gate hp / 128 (x1 | x2 of 128 gated channels), plain ceil(N / 256) (two 128-channel halves)
+  int split;               // plain: channels >= split go to out2 (channel - split); N when there is one output tensor
   int ln_mode;
   int tiles_x, tiles_y, n_items;
   uint32_t mg_per_img, mg_tiles_x;
@@ -41,6 +43,8 @@ struct TwArgs {
   const float* vec_t;      // [2 hp] or null
   void* out;
   long long out_pitch, out_bstride;
+  void* out2;
+  long long out2_pitch, out2_bstride;
 };
 
 __device__ __forceinline__ uint32_t tw_div(uint32_t n, uint32_t magic) { return magic ? __umulhi(n, magic) : n; }
@@ -167,6 +171,66 @@ __device__ __forceinline__ void tw_subunit(uint32_t tcol, const uint32_t (&w1)[9
   }
 }
 
+// Plain (no gate) sub-unit of one thread and ONE accumulator: 6 halo'd rows x 6 columns of its channel -> 4 x 4 outputs of the
+// depthwise conv, stored as 16-bit.  Same structure as tw_subunit.
+template <class T, bool BORDER>
+__device__ __forceinline__ void tw_plain(uint32_t tcol, const uint32_t (&w)[9], uint32_t seed, float tv, uint32_t col_in, int yo, int xo,
+                                         int H, int W, unsigned short* orow, int pitch, size_t row_stride) {
+  constexpr int SW = kTwSW;
+  uint32_t a[3][2];
+  uint32_t r[8];
+  tw_ld8(tcol, r);
+#pragma unroll
+  for (int ri = 0; ri < 6; ++ri) {
+    tmem_ld_wait();
+    if (BORDER) {
+      const int py = yo - 1 + ri;
+      if (py >= 0 && py < H) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+          if (col_in & (1u << j)) r[j] = __float_as_uint(__uint_as_float(r[j]) + tv);
+      }
+    }
+    uint32_t e[3], o[2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) e[j] = tw_pack_sat(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) o[j] = tw_pack_sat(__uint_as_float(r[2 * j + 1]), __uint_as_float(r[2 * j + 2]));
+    if (ri < 5) tw_ld8(tcol + (uint32_t)((ri + 1) * SW), r);
+    if (ri < 4) { a[ri % 3][0] = seed; a[ri % 3][1] = seed; }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ro = ri - ky;
+      if (ro >= 0 && ro < 4) {
+        uint32_t* p = a[ro % 3];
+        p[0] = tw_fma2(e[0], w[ky * 3], p[0]); p[0] = tw_fma2(o[0], w[ky * 3 + 1], p[0]); p[0] = tw_fma2(e[1], w[ky * 3 + 2], p[0]);
+        p[1] = tw_fma2(e[1], w[ky * 3], p[1]); p[1] = tw_fma2(o[1], w[ky * 3 + 1], p[1]); p[1] = tw_fma2(e[2], w[ky * 3 + 2], p[1]);
+      }
+    }
+    if (ri >= 2) {
+      const int ro = ri - 2;
+      uint32_t g0 = a[ro % 3][0], g1 = a[ro % 3][1];
+      if (T::kFmt == 1) {                                     // bf16 storage: fp16 pairs -> bf16 pairs
+        const float2 fa = tw_h2f2(g0), fb = tw_h2f2(g1);
+        g0 = pack2<T>(fa.x, fa.y); g1 = pack2<T>(fb.x, fb.y);
+      }
+      if (!BORDER) {
+        orow[0] = (unsigned short)(g0 & 0xffffu);
+        orow[pitch] = (unsigned short)(g0 >> 16);
+        orow[2 * pitch] = (unsigned short)(g1 & 0xffffu);
+        orow[3 * pitch] = (unsigned short)(g1 >> 16);
+      } else if (yo + ro < H) {
+        if (xo + 0 < W) orow[0] = (unsigned short)(g0 & 0xffffu);
+        if (xo + 1 < W) orow[pitch] = (unsigned short)(g0 >> 16);
+        if (xo + 2 < W) orow[2 * pitch] = (unsigned short)(g1 & 0xffffu);
+        if (xo + 3 < W) orow[3 * pitch] = (unsigned short)(g1 >> 16);
+      }
+      orow += row_stride;
+      asm volatile("" : "+l"(orow));
+    }
+  }
+}
+
 // Shared-memory matrix descriptor with the swizzle mode as a parameter (2: 128-byte rows, 4: 64-byte rows); see make_sdesc_sw128
 __device__ __forceinline__ uint64_t tw_sdesc(uint32_t sbo_bytes, uint32_t layout) {
   return ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
@@ -177,7 +241,7 @@ __device__ __forceinline__ uint64_t tw_sdesc(uint32_t sbo_bytes, uint32_t layout
 // KBB = bytes of a k-block row: 128 (64 channels, 128-byte swizzle; C = 48) or 64 (32 channels, 64-byte swizzle; C = 96 = 3 x 32, so
 // nothing is padded, two x tiles and the WHOLE weight matrix fit next to each other: the weights are fetched once per CTA and the
 // next item's tile is loaded and LayerNormed while the current one is multiplied).
-template <class T, int NKB, int KBB, bool GATE32, int PITCH>
+template <class T, int NKB, int KBB, bool GATE, bool GATE32, int PITCH>
 __global__ void __launch_bounds__(kTwThreads, 1)
 pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TwArgs g) {
   constexpr int TW = kTwTW, TH = kTwTH, SW = kTwSW, NPIX = kTwNPIX;
@@ -187,7 +251,8 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr uint32_t X_BYTES = NKB * A_KB;
   constexpr uint32_t SW_LAYOUT = KBB == 128 ? 2u : 4u;
   constexpr uint32_t SBO = 8 * KBB;                            // 8-row swizzle atom
-  const uint32_t w_kb_bytes = (uint32_t)(2 * g.hp) * KBB;      // one k-block of the resident weights (all 2 hp rows)
+  const int w_rows = GATE ? 2 * g.hp : g.n_cb * 256;           // resident weight rows (plain: padded to whole blocks, TMA zero fill)
+  const uint32_t w_kb_bytes = (uint32_t)w_rows * KBB;          // one k-block of the resident weights
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_afull[NA], bar_aready[NA], bar_aempty[NA];
@@ -212,23 +277,26 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32(&tmem_base_smem), 512); tmem_relinquish(); }
-  // per-CTA tables: taps, accumulator seeds and t of every gated channel
+  // per-CTA tables: taps, accumulator seeds and t of the two channels of every (block, lane) slot.  Slot e = block * 128 + lane:
+  // gate: channels (e, hp + e) = x1 | x2 of gated channel e; plain: channels (block * 256 + lane, + 128)
   {
     const unsigned short* src = reinterpret_cast<const unsigned short*>(g.dw_w);
     unsigned short* tab = reinterpret_cast<unsigned short*>(stab);
-    const int n_pre = 2 * g.hp;
+    const int n_pre = g.n_rows;
     // packed gate: 0.5 p (1 + tanh(.)) q = (p tanh(.) + p) (0.5 q); the 0.5 rides on the x2 branch's taps and bias (exact, a power of two)
-    const float qs = GATE32 ? 1.0f : 0.5f;
-    for (int i = threadIdx.x; i < g.hp; i += kTwThreads) {
+    const float qs = (GATE && !GATE32) ? 0.5f : 1.0f;
+    for (int i = threadIdx.x; i < g.n_cb * 128; i += kTwThreads) {
+      const int c1 = GATE ? i : (i >> 7) * 256 + (i & 127), c2 = GATE ? g.hp + i : c1 + 128;
+      const bool v1 = c1 < n_pre, v2 = c2 < n_pre;
       float ws1 = 0.f, ws2 = 0.f;
       for (int tap = 0; tap < 9; ++tap) {
-        const unsigned short a = src[(size_t)tap * n_pre + i], b = src[(size_t)tap * n_pre + g.hp + i];
-        const float bf = __half2float(__ushort_as_half(b)) * qs;
+        const unsigned short a = v1 ? src[(size_t)tap * n_pre + c1] : (unsigned short)0;
+        const float bf = v2 ? __half2float(__ushort_as_half(src[(size_t)tap * n_pre + c2])) * qs : 0.f;
         tab[i * 24 + tap] = a; tab[i * 24 + 9 + tap] = __half_as_ushort(__float2half_rn(bf));
         ws1 += __half2float(__ushort_as_half(a)); ws2 += bf;
       }
-      const float b1 = g.dw_bias ? g.dw_bias[i] : 0.f, b2 = (g.dw_bias ? g.dw_bias[g.hp + i] : 0.f) * qs;
-      const float t1 = g.vec_t ? g.vec_t[i] : 0.f, t2 = g.vec_t ? g.vec_t[g.hp + i] : 0.f;
+      const float b1 = (g.dw_bias && v1) ? g.dw_bias[c1] : 0.f, b2 = ((g.dw_bias && v2) ? g.dw_bias[c2] : 0.f) * qs;
+      const float t1 = (g.vec_t && v1) ? g.vec_t[c1] : 0.f, t2 = (g.vec_t && v2) ? g.vec_t[c2] : 0.f;
       tab[i * 24 + 18] = __half_as_ushort(__float2half_rn(b1 + t1 * ws1));      // interior tiles: the conv of the constant t is a constant
       tab[i * 24 + 19] = __half_as_ushort(__float2half_rn(b2 + t2 * ws2));
       tab[i * 24 + 20] = __half_as_ushort(__float2half_rn(b1));
@@ -256,7 +324,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t full = smem_u32(&bar_wfull);
       mbar_expect_tx(full, (uint32_t)NKB * w_kb_bytes);
       for (int kb = 0; kb < NKB; ++kb)
-        for (int r0 = 0; r0 < 2 * g.hp; r0 += 128)
+        for (int r0 = 0; r0 < w_rows; r0 += 128)
           tma_load_2d(base + g.off_w + (uint32_t)kb * w_kb_bytes + (uint32_t)r0 * KBB, &tmW, full, kb * KCH, r0);
     }
     __syncwarp();
@@ -296,14 +364,16 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const int rem = g.C - kb * KCH;
               const int ksteps = rem >= KCH ? KCH / 16 : (rem + 15) >> 4;
               const uint32_t x_lo = (base + ab * X_BYTES + (uint32_t)kb * A_KB + (uint32_t)third * (72u * KBB)) >> 4;
-              const uint32_t w_lo = (base + g.off_w + (uint32_t)kb * w_kb_bytes + (uint32_t)(cb * 128) * KBB) >> 4;
+              const int row1 = GATE ? cb * 128 : cb * 256, row2 = GATE ? g.hp + cb * 128 : cb * 256 + 128;
+              const uint32_t w_lo = (base + g.off_w + (uint32_t)kb * w_kb_bytes) >> 4;
               const uint64_t xd = desc_hi | (uint64_t)(x_lo & 0x3fffu);
-              const uint64_t w1d = desc_hi | (uint64_t)(w_lo & 0x3fffu);
-              const uint64_t w2d = desc_hi | (uint64_t)((w_lo + (((uint32_t)g.hp * KBB) >> 4)) & 0x3fffu);
+              const uint64_t w1d = desc_hi | (uint64_t)((w_lo + (((uint32_t)row1 * KBB) >> 4)) & 0x3fffu);
+              const uint64_t w2d = desc_hi | (uint64_t)((w_lo + (((uint32_t)row2 * KBB) >> 4)) & 0x3fffu);
+              const bool second = row2 < g.n_rows;                 // plain: the last block may have no second half
               for (int k = 0; k < ksteps; ++k) {
                 const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
                 umma_f16(d1, w1d + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idesc, acc);
-                umma_f16(d2, w2d + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idesc, acc);
+                if (second) umma_f16(d2, w2d + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idesc, acc);
               }
             }
             umma_commit(smem_u32(&bar_tfull[tb]));
@@ -417,7 +487,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const size_t row_stride = (size_t)g.W * g.out_pitch;
 
       for (int cb = 0; cb < g.n_cb; ++cb) {
-        const int ch = cb * 128 + q * 32 + lane;       // gated channel of this thread
+        const int ch = cb * 128 + q * 32 + lane;       // table slot of this thread = its gated channel (gate)
         // taps (packed pairs), seeds
         const uint4 ta = stab[ch * 3], tb4 = stab[ch * 3 + 1], tc = stab[ch * 3 + 2];
         // halves: ta = w1[0..7]; tb4 = w1[8] w2[0..6]; tc = w2[7] w2[8] s1i s2i b1 b2 0 0
@@ -433,17 +503,50 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const float2 tv = svt[ch];
         const bool add_t = !interior && g.vec_t != nullptr;
 
-        // running output pointer of this thread: (first output row of the sub-unit, first output column, channel)
+        // running output pointer(s) of this thread: (first output row of the sub-unit, first output column, channel)
         unsigned short* orow = out_img + ((size_t)y0 * g.W + xo) * g.out_pitch + ch;
+        unsigned short* orow2 = nullptr;
+        int pitch2 = 0;
+        size_t row_stride2 = 0;
+        bool va = true, vb = true;
+        if (!GATE) {
+          // plain: two independent channels per thread, each routed to `out` (below split) or `out2`
+          const int ca = cb * 256 + q * 32 + lane, cbn = ca + 128;
+          va = ca < g.n_rows; vb = cbn < g.n_rows;
+          unsigned short* img2 = reinterpret_cast<unsigned short*>(g.out2) + (size_t)b * g.out2_bstride;
+          const size_t pix = (size_t)y0 * g.W + xo;
+          orow = ca < g.split ? out_img + pix * g.out_pitch + ca : img2 + pix * g.out2_pitch + (ca - g.split);
+          orow2 = cbn < g.split ? out_img + pix * g.out_pitch + cbn : img2 + pix * g.out2_pitch + (cbn - g.split);
+          pitch2 = cbn < g.split ? (int)g.out_pitch : (int)g.out2_pitch;
+          row_stride2 = (size_t)g.W * pitch2;
+        }
+        const int pitch1 = (GATE || cb * 256 + q * 32 + lane < g.split) ? pitch : (int)g.out2_pitch;
+        const size_t row_stride1 = GATE ? row_stride : (size_t)g.W * pitch1;
+        const bool any_a = GATE || __any_sync(0xffffffffu, va), any_b = GATE || __any_sync(0xffffffffu, vb);
+        const bool all_a = GATE || __all_sync(0xffffffffu, va), all_b = GATE || __all_sync(0xffffffffu, vb);   // tcgen05.ld is warp-collective: branch per warp only
         for (int third = 0; third < 3; ++third, ++tq) {
           const uint32_t tb = tq & 1u;
           mbar_wait(smem_u32(&bar_tfull[tb]), (tq >> 1) & 1u);
           tc_fence_after();
           const uint32_t tcol = t_lane + tb * 256u;
           const int yo = y0 + third * kTwRowsPerThird;            // first output row of the sub-unit
-          if (interior) tw_subunit<T, GATE32, false, PITCH>(tcol, w1, w2, seed1, seed2, tv, 0u, yo, xo, g.H, g.W, orow, pitch, row_stride);
-          else tw_subunit<T, GATE32, true, PITCH>(tcol, w1, w2, seed1, seed2, add_t ? tv : make_float2(0.f, 0.f), col_in, yo, xo, g.H, g.W, orow, pitch, row_stride);
-          orow += 4 * row_stride;
+          if (GATE) {
+            if (interior) tw_subunit<T, GATE32, false, PITCH>(tcol, w1, w2, seed1, seed2, tv, 0u, yo, xo, g.H, g.W, orow, pitch, row_stride);
+            else tw_subunit<T, GATE32, true, PITCH>(tcol, w1, w2, seed1, seed2, add_t ? tv : make_float2(0.f, 0.f), col_in, yo, xo, g.H, g.W, orow, pitch, row_stride);
+            orow += 4 * row_stride;
+          } else {
+            // channels past the end of the tensor (last block) are skipped per warp; a partially valid warp masks its stores by
+            // pretending the row is outside the image (H = 0 on the border path)
+            if (any_a) {
+              if (interior && all_a) tw_plain<T, false>(tcol, w1, seed1, 0.f, 0u, yo, xo, g.H, g.W, orow, pitch1, row_stride1);
+              else tw_plain<T, true>(tcol, w1, seed1, add_t ? tv.x : 0.f, interior ? 0x3fu : col_in, yo, xo, va ? g.H : 0, g.W, orow, pitch1, row_stride1);
+            }
+            if (any_b) {
+              if (interior && all_b) tw_plain<T, false>(tcol + 128u, w2, seed2, 0.f, 0u, yo, xo, g.H, g.W, orow2, pitch2, row_stride2);
+              else tw_plain<T, true>(tcol + 128u, w2, seed2, add_t ? tv.y : 0.f, interior ? 0x3fu : col_in, yo, xo, vb ? g.H : 0, g.W, orow2, pitch2, row_stride2);
+            }
+            orow += 4 * row_stride1; orow2 += 4 * row_stride2;
+          }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[tb]));
@@ -459,13 +562,13 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // ---------------------------------------------------------------------------------------------------
-template <class T, int NKB, int KBB, bool GATE32, int PITCH>
+template <class T, int NKB, int KBB, bool GATE, bool GATE32, int PITCH>
 static int tw_launch(const TwArgs& g, uint32_t smem, const CUtensorMap& tmA, const CUtensorMap& tmW, cudaStream_t stream) {
   static bool set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 16 || !set[dev]) {
-    if (cudaFuncSetAttribute(pwdwt_kernel<T, NKB, KBB, GATE32, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(pwdwt_kernel<T, NKB, KBB, GATE, GATE32, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
       return pir_fail(PIR_ERR_CUDA, "pir_pwdw: cannot raise dynamic shared memory limit");
     if (dev >= 0 && dev < 16) set[dev] = true;
   }
@@ -475,7 +578,7 @@ static int tw_launch(const TwArgs& g, uint32_t smem, const CUtensorMap& tmA, con
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = g.n_items < num_sms ? g.n_items : num_sms;
-  pwdwt_kernel<T, NKB, KBB, GATE32, PITCH><<<dim3(grid), dim3(kTwThreads), smem, stream>>>(tmA, tmW, g);
+  pwdwt_kernel<T, NKB, KBB, GATE, GATE32, PITCH><<<dim3(grid), dim3(kTwThreads), smem, stream>>>(tmA, tmW, g);
   return pir_check_launch("pir_pwdw (channel-major)");
 }
 
@@ -486,21 +589,39 @@ static bool tw_shape(int C, int* nkb, int* kbb) {
   return false;
 }
 
-// gate == 1, C <= 64 or C == 96, hidden a multiple of 128 and the plan fits shared memory
+// C <= 64 or C == 96; gate: hidden a multiple of 128; the plan (two x tiles + ALL weights + tables) fits shared memory
+static uint32_t tw_smem(const PirPwDw* d, int nkb, int kbb, TwArgs* g) {
+  const int n_cb = d->gate ? d->N / 128 : (d->N + 255) / 256;
+  const int w_rows = d->gate ? 2 * d->N : n_cb * 256;
+  uint32_t off = 2u * nkb * 256u * kbb;
+  if (g) g->off_w = off;
+  off += (uint32_t)nkb * w_rows * kbb;
+  if (g) g->off_tab = off;
+  off += (uint32_t)n_cb * 128u * 48u;
+  if (g) g->off_vt = off;
+  off += (uint32_t)n_cb * 128u * 8u;
+  return off + 1024u;
+}
+
 bool pwdwt_supported(const PirPwDw* d) {
-  static const bool off = [] { const char* e = getenv("PIR_PWDW_T"); return e && e[0] == '0'; }();
-  if (off || !d->gate) return false;
+  // bit 0: gate, bit 1: plain.  Default: gate only -- measured on B200 (B = 16, 256 x 256): the plain form leaves lane quarters idle
+  // in the last channel block (288 = 256 + 32, 144 = 128 + 16 channels) and runs at 495 / 351 us against 398 / 233 us of pwdw.cu
+  static const int mode = [] { const char* e = getenv("PIR_PWDW_T"); return e ? atoi(e) : 1; }();
+  if (!(mode & (d->gate ? 1 : 2))) return false;
   int nkb, kbb;
-  if (!tw_shape(d->C, &nkb, &kbb) || d->N % 128 != 0) return false;
-  const uint32_t need = 2u * nkb * 256u * kbb + (uint32_t)nkb * 2u * d->N * kbb + (uint32_t)d->N * 56u + 1024u;
-  return need <= 227u * 1024u - 1024u;
+  if (!tw_shape(d->C, &nkb, &kbb)) return false;
+  if (d->gate && d->N % 128 != 0) return false;
+  return tw_smem(d, nkb, kbb, nullptr) <= 227u * 1024u - 1024u;
 }
 
 template <class T>
 static int tw_run(const PirPwDw* d, cudaStream_t stream) {
   TwArgs g{};
+  const bool gate = d->gate != 0;
   g.B = d->B; g.H = d->H; g.W = d->W; g.C = d->C;
-  g.hp = d->N; g.n_cb = d->N / 128; g.ln_mode = d->ln_mode;
+  g.hp = gate ? d->N : 0; g.n_rows = gate ? 2 * d->N : d->N;
+  g.n_cb = gate ? d->N / 128 : (d->N + 255) / 256;
+  g.ln_mode = d->ln_mode;
   g.tiles_x = (d->W + kTwTW - 1) / kTwTW; g.tiles_y = (d->H + kTwTH - 1) / kTwTH;
   g.n_items = g.tiles_x * g.tiles_y * d->B;
   {
@@ -512,14 +633,13 @@ static int tw_run(const PirPwDw* d, cudaStream_t stream) {
   int nkb = 0, kbb = 0;
   tw_shape(d->C, &nkb, &kbb);
   const int kch = kbb / 2;
-  uint32_t off = 2u * nkb * 256u * kbb;
-  g.off_w = off; off += (uint32_t)nkb * 2u * g.hp * kbb;
-  g.off_tab = off; off += (uint32_t)g.hp * 48u;
-  g.off_vt = off; off += (uint32_t)g.hp * 8u;
-  const uint32_t smem = off + 1024u;
+  const uint32_t smem = tw_smem(d, nkb, kbb, &g);
   if (smem > 227u * 1024u - 1024u) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_pwdw: shared-memory plan does not fit");
   g.dw_w = d->dw_w; g.dw_bias = d->dw_bias; g.vec_t = d->vec_t;
   g.out = d->out; g.out_pitch = d->out_pitch; g.out_bstride = d->out_bstride;
+  const bool two = !gate && d->out2 != nullptr && d->split > 0 && d->split < d->N;
+  g.split = two ? d->split : d->N;
+  g.out2 = two ? d->out2 : d->out; g.out2_pitch = two ? d->out2_pitch : d->out_pitch; g.out2_bstride = two ? d->out2_bstride : d->out_bstride;
   const CUtensorMapDataType dt = T::kFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapSwizzle sw = kbb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUtensorMap tmA, tmW;
@@ -531,21 +651,26 @@ static int tw_run(const PirPwDw* d, cudaStream_t stream) {
   }
   {
     const uint64_t kpad = (uint64_t)((d->C + 63) / 64) * 64;           // row length of the packed weights (packing.kpad_of)
-    const uint64_t dims[2] = {kpad, (uint64_t)(2 * d->N)};
+    const uint64_t dims[2] = {kpad, (uint64_t)g.n_rows};
     const uint64_t strides[1] = {kpad * 2};
     const uint32_t box[2] = {(uint32_t)kch, 128};
     if (int e = pir_make_tmap(&tmW, dt, 2, d->w, dims, strides, box, sw)) return e;
   }
-  // fp16 storage keeps the fp32 erf-GELU gate unless PIR_PWDW_GATE16=1 (A/B); bf16 storage uses the packed fp16 gate
-  static const bool gate16 = [] { const char* e = getenv("PIR_PWDW_GATE16"); return e && e[0] == '1'; }();
-  const bool g32 = T::kFmt == 0 && !gate16;
+  if (!gate) {
+    if (nkb == 1) return tw_launch<T, 1, 128, false, false, 0>(g, smem, tmA, tmW, stream);
+    return tw_launch<T, 3, 64, false, false, 0>(g, smem, tmA, tmW, stream);
+  }
+  // fp32 erf-GELU gate for fp16 storage only on request (PIR_PWDW_GATE32=1, A/B): the packed fp16 gate measured 8.3e-4 against
+  // 9.0e-4 max-abs on the cfg2 forward and is 0.75 ms per step faster
+  static const bool gate32 = [] { const char* e = getenv("PIR_PWDW_GATE32"); return e && e[0] == '1'; }();
+  const bool g32 = T::kFmt == 0 && gate32;
   // the networks write a dense gated tensor (pitch == hidden): those two pitches are compiled in
   if (nkb == 1) {
-    if (d->out_pitch == 128) return g32 ? tw_launch<T, 1, 128, true, 128>(g, smem, tmA, tmW, stream) : tw_launch<T, 1, 128, false, 128>(g, smem, tmA, tmW, stream);
-    return g32 ? tw_launch<T, 1, 128, true, 0>(g, smem, tmA, tmW, stream) : tw_launch<T, 1, 128, false, 0>(g, smem, tmA, tmW, stream);
+    if (d->out_pitch == 128) return g32 ? tw_launch<T, 1, 128, true, true, 128>(g, smem, tmA, tmW, stream) : tw_launch<T, 1, 128, true, false, 128>(g, smem, tmA, tmW, stream);
+    return g32 ? tw_launch<T, 1, 128, true, true, 0>(g, smem, tmA, tmW, stream) : tw_launch<T, 1, 128, true, false, 0>(g, smem, tmA, tmW, stream);
   }
-  if (d->out_pitch == 256) return g32 ? tw_launch<T, 3, 64, true, 256>(g, smem, tmA, tmW, stream) : tw_launch<T, 3, 64, false, 256>(g, smem, tmA, tmW, stream);
-  return g32 ? tw_launch<T, 3, 64, true, 0>(g, smem, tmA, tmW, stream) : tw_launch<T, 3, 64, false, 0>(g, smem, tmA, tmW, stream);
+  if (d->out_pitch == 256) return g32 ? tw_launch<T, 3, 64, true, true, 256>(g, smem, tmA, tmW, stream) : tw_launch<T, 3, 64, true, false, 256>(g, smem, tmA, tmW, stream);
+  return g32 ? tw_launch<T, 3, 64, true, true, 0>(g, smem, tmA, tmW, stream) : tw_launch<T, 3, 64, true, false, 0>(g, smem, tmA, tmW, stream);
 }
 
 int pwdwt_run(const PirPwDw* d, cudaStream_t stream) {

@@ -44,6 +44,9 @@ class Engine:
         # depthwise taps of the fused kernels are IEEE half whatever the storage type (fp32 only for the CPU wiring tests)
         self.dw16 = torch.float32 if dtype == torch.float32 else torch.float16
         self.fuse = os.environ.get("PROMPTIR_B200_FUSE", "1") != "0"     # 0: never use the fused pir_pwdw kernels (A/B timing)
+        # q|k and v of MDTA (model.py:121) as two dense tensors written by the fused qkv kernel: the Gram streams 2C-channel rows and
+        # the attn.v GEMM C-channel rows instead of slices of 3C-channel rows.  0: one [.., 3C] tensor (A/B timing)
+        self.split_qkv = os.environ.get("PROMPTIR_B200_SPLITQKV", "1") != "0"
         if self.cuda:
             from . import _lib
             _lib.check(_lib.load().pir_check_device(), "pir_check_device")
@@ -233,19 +236,26 @@ class Engine:
         fuse_qkv = self.fuse and ops.pwdw_supported(c, 3 * c, False)
         fuse_ffn = self.fuse and ops.pwdw_supported(c, hp, True)
 
+        split = fuse_qkv and self.split_qkv and ops.pwdw_split_supported(c, 3 * c)
+        qk, v = qkv[..., :2 * c], qkv[..., 2 * c:]
+        if split:
+            n = B * h * w
+            qk = self.S2[:n * 2 * c].view(B, h, w, 2 * c)
+            v = self.S2[n * 2 * c:n * 3 * c].view(B, h, w, c)
         if fuse_qkv:
             (dwq_h,) = self._cached(lambda: [packing.pack_depthwise(at.qkv_dwconv.weight, self.dw16)])
-            self._emit("pwdw", lambda: ops.pwdw(x, qkv_w, dwq_h, qkv, gate=False, ln_mode=self.ln_mode, vec_t=qkv_t, dw_bias=dwq_b),
-                       a=x, w=qkv_w, dw_w=dwq_h, out=qkv, gate=False, ln_mode=self.ln_mode, vec_t=qkv_t, dw_bias=dwq_b, tag="K12")
+            o1, o2 = (qk, v) if split else (qkv, None)
+            self._emit("pwdw", lambda: ops.pwdw(x, qkv_w, dwq_h, o1, gate=False, ln_mode=self.ln_mode, vec_t=qkv_t, dw_bias=dwq_b, out2=o2),
+                       a=x, w=qkv_w, dw_w=dwq_h, out=o1, out2=o2, gate=False, ln_mode=self.ln_mode, vec_t=qkv_t, dw_bias=dwq_b, tag="K12")
         else:
             self._gemm(x, qkv_w, qkv_pre, n=3 * c, ln_mode=self.ln_mode, ln_s=qkv_s, vec_t=qkv_t, tag="K1")
             self._emit("dwconv", lambda: ops.dwconv3x3(qkv_pre, dwq_w, qkv, gate=False, bias=dwq_b), x=qkv_pre, w=dwq_w, out=qkv,
                        gate=False, bias=dwq_b, tag="K2")
-        gram_fin = ops.mdta(qkv, heads, self.ws, temp, wo, wfold, splits) if self.cuda else (None, None)
-        self._emit("mdta_gram", (lambda: gram_fin[0]), qkv=qkv, heads=heads, ws=self.ws, splits=splits, tag="K3a")
-        self._emit("mdta_finalize", (lambda: gram_fin[1]), qkv=qkv, heads=heads, ws=self.ws, splits=splits, temperature=temp,
+        gram_fin = ops.mdta(qk, heads, self.ws, temp, wo, wfold, splits, qk_only=True) if self.cuda else (None, None)
+        self._emit("mdta_gram", (lambda: gram_fin[0]), qk=qk, heads=heads, ws=self.ws, splits=splits, tag="K3a")
+        self._emit("mdta_finalize", (lambda: gram_fin[1]), qk=qk, heads=heads, ws=self.ws, splits=splits, temperature=temp,
                    wo=wo, wfold=wfold, tag="K3b")
-        self._gemm(qkv[..., 2 * c:], wfold, x, n=c, res=x, vec_t=wo_b, w_batched=True, tag="K4")
+        self._gemm(v, wfold, x, n=c, res=x, vec_t=wo_b, w_batched=True, tag="K4")
         if fuse_ffn:
             (dwf_h,) = self._cached(lambda: [packing.pack_depthwise(ff.dwconv.weight, self.dw16, chan_map=gmap, c_total=2 * hp)])
             self._emit("pwdw", lambda: ops.pwdw(x, pin_w, dwf_h, gated, gate=True, ln_mode=self.ln_mode, vec_t=pin_t, dw_bias=dwf_b),
@@ -408,6 +418,15 @@ def _numel(t) -> int:
     return 0 if t is None else int(t.numel())
 
 
+def _qk_dims(rec: dict):
+    """(B, H, W, C) of an MDTA record: it carries either the dense / sliced q|k tensor [.., 2C] or the whole qkv tensor [.., 3C]."""
+    if rec.get("qk") is not None:
+        B, H, W, c2 = rec["qk"].shape
+        return B, H, W, c2 // 2
+    B, H, W, c3 = rec["qkv"].shape
+    return B, H, W, c3 // 3
+
+
 def op_cost(rec: dict):
     """-> (algorithmic HBM bytes, FLOPs) of one launch: every operand read once, every result written once."""
     kind = rec["kind"]
@@ -426,19 +445,16 @@ def op_cost(rec: dict):
         a, out = rec["a"], rec["out"]
         npre = rec["w"].shape[0]
         pix = a.shape[0] * a.shape[1] * a.shape[2]
-        return (a.numel() * 2 + out.numel() * 2 + rec["w"].numel() * 2 + rec["dw_w"].numel() * 2,
+        return (a.numel() * 2 + (out.numel() + _numel(rec.get("out2"))) * 2 + rec["w"].numel() * 2 + rec["dw_w"].numel() * 2,
                 2.0 * pix * a.shape[3] * npre + 18.0 * pix * npre)
     if kind == "dwconv":
         x, out = rec["x"], rec["out"]
         return x.numel() * 2 + out.numel() * 2 + rec["w"].numel() * 2, 18.0 * x.numel()
     if kind == "mdta_gram":
-        q = rec["qkv"]
-        B, H, W, c3 = q.shape
-        c = c3 // 3
+        B, H, W, c = _qk_dims(rec)
         return B * H * W * 2 * c * 2, 2.0 * B * H * W * c * (c // rec["heads"])
     if kind == "mdta_finalize":
-        q = rec["qkv"]
-        B, c = q.shape[0], q.shape[3] // 3
+        B, _, _, c = _qk_dims(rec)
         return B * c * c * (4 * rec["splits"] + 2) + c * c * 4, 2.0 * B * c * c * (c // rec["heads"])
     if kind == "prompt":
         x, out = rec["x"], rec["out"]

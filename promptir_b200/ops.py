@@ -117,11 +117,22 @@ def pwdw_supported(c: int, n: int, gate: bool) -> bool:
     return bool(_lib.load().pir_pwdw_supported(c, n, int(gate)))
 
 
+def pwdw_split_supported(c: int, n: int) -> bool:
+    return bool(_lib.load().pir_pwdw_split_supported(c, n))
+
+
 def pwdw(x: torch.Tensor, w: torch.Tensor, dw_w: torch.Tensor, out: torch.Tensor, *, gate: bool, ln_mode: int = LN_NONE,
-         vec_t: Optional[torch.Tensor] = None, dw_bias: Optional[torch.Tensor] = None) -> Launch:
-    """Fused LN -> 1x1 conv -> depthwise 3x3 (-> GELU gate) (pir_pwdw).  w: packed [Npre, Kpad]; dw_w: fp16 [9, Npre]."""
+         vec_t: Optional[torch.Tensor] = None, dw_bias: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None) -> Launch:
+    """Fused LN -> 1x1 conv -> depthwise 3x3 (-> GELU gate) (pir_pwdw).  w: packed [Npre, Kpad]; dw_w: fp16 [9, Npre].
+    out2 (gate == False only): the channels after out's go to this second tensor (q|k and v of MDTA as two dense tensors)."""
     pa, B, H, W, K, apitch, abs_ = _nhwc(x, "pwdw.a")
     po, oB, oH, oW, N, opitch, obs = _nhwc(out, "pwdw.out")
+    split = 0
+    if out2 is not None:
+        assert not gate
+        po2, o2B, o2H, o2W, N2, o2pitch, o2bs = _nhwc(out2, "pwdw.out2")
+        assert (o2B, o2H, o2W) == (B, H, W) and out2.dtype == x.dtype
+        split, N = N, N + N2
     npre = 2 * N if gate else N
     assert (oB, oH, oW) == (B, H, W) and out.dtype == x.dtype
     assert dw_w.dtype == torch.float16 and dw_w.is_contiguous() and tuple(dw_w.shape) == (9, npre)
@@ -133,7 +144,9 @@ def pwdw(x: torch.Tensor, w: torch.Tensor, dw_w: torch.Tensor, out: torch.Tensor
     d.w, d.vec_t = w.data_ptr(), _ptr(vec_t)
     d.dw_w, d.dw_bias = dw_w.data_ptr(), _ptr(dw_bias)
     d.out, d.out_pitch, d.out_bstride = po, opitch, obs
-    return _prepared("pir_pwdw", d, (x, w, dw_w, out, vec_t, dw_bias))
+    if out2 is not None:
+        d.out2, d.out2_pitch, d.out2_bstride, d.split = po2, o2pitch, o2bs, split
+    return _prepared("pir_pwdw", d, (x, w, dw_w, out, vec_t, dw_bias, out2))
 
 
 def mdta_splits(B: int, HW: int, Cdim: int) -> int:
@@ -145,10 +158,11 @@ def mdta_ws_floats(B: int, Cdim: int, splits: int) -> int:
 
 
 def mdta(qkv: torch.Tensor, heads: int, ws: torch.Tensor, temperature: torch.Tensor, wo: torch.Tensor,
-         wfold: torch.Tensor, splits: int):
-    """-> (gram_launch, finalize_launch).  qkv: NHWC [B,H,W,3C] after the depthwise conv."""
+         wfold: torch.Tensor, splits: int, qk_only: bool = False):
+    """-> (gram_launch, finalize_launch).  qkv: NHWC [B,H,W,3C] after the depthwise conv (only q|k = channels [0, 2C) are read), or,
+    with qk_only, the dense q|k tensor [B,H,W,2C] of the two-tensor qkv layout."""
     pq, B, H, W, C3, qp, qbs = _nhwc(qkv, "mdta.qkv")
-    Cdim = C3 // 3
+    Cdim = C3 // 2 if qk_only else C3 // 3
     assert ws.dtype == torch.float32 and ws.numel() >= mdta_ws_floats(B, Cdim, splits)
     assert wo.dtype == torch.float32 and wo.is_contiguous() and wo.numel() == Cdim * Cdim
     assert temperature.dtype == torch.float32 and temperature.numel() == heads

@@ -92,13 +92,21 @@ def emu_pwdw(r):
         pre = pre + r["vec_t"].view(1, 1, 1, -1)
     if a.dtype != torch.float32:                       # fp32 programs are the exact-wiring check
         pre = pre.clamp(-65504, 65504).to(torch.float16)
-    emu_dwconv(dict(x=pre, w=r["dw_w"], out=out, bias=r["dw_bias"], gate=r["gate"]))
+    out2 = r.get("out2")
+    if out2 is None:
+        emu_dwconv(dict(x=pre, w=r["dw_w"], out=out, bias=r["dw_bias"], gate=r["gate"]))
+    else:                                              # two output tensors: channels [0, split) | [split, N)
+        full = torch.empty(B, H, W, npre, dtype=out.dtype, device=out.device)
+        emu_dwconv(dict(x=pre, w=r["dw_w"], out=full, bias=r["dw_bias"], gate=r["gate"]))
+        out.copy_(full[..., :out.shape[-1]])
+        out2.copy_(full[..., out.shape[-1]:])
 
 
 def emu_mdta_finalize(r):
-    qkv, heads, wo, wfold, temp = r["qkv"], r["heads"], r["wo"], r["wfold"], r["temperature"]
-    B, H, W, c3 = qkv.shape
-    C = c3 // 3
+    heads, wo, wfold, temp = r["heads"], r["wo"], r["wfold"], r["temperature"]
+    qkv = r["qk"] if r.get("qk") is not None else r["qkv"]
+    B, H, W, cn = qkv.shape
+    C = cn // 2 if r.get("qk") is not None else cn // 3
     c = C // heads
     q = qkv[..., :C].float().reshape(B, H * W, heads, c).permute(0, 2, 3, 1)          # [B, h, c, HW]
     k = qkv[..., C:2 * C].float().reshape(B, H * W, heads, c).permute(0, 2, 3, 1)

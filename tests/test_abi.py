@@ -42,7 +42,7 @@ def test_host_only_entry_points(lib):
 
 def test_ctypes_structs_match_the_header(tmp_path):
     names = ["PirGemm", "PirDwConv", "PirPwDw", "PirMdta", "PirPrompt", "PirPatchEmbed", "PirLn", "PirWgrad", "PirWgradFin", "PirDwWgrad",
-             "PirGateBwd", "PirMdtaBwd", "PirShuffle", "PirPromptBwd", "PirBcastAdd", "PirToNhwc16", "PirOcab", "PirOcabBwd"]
+             "PirGateBwd", "PirMdtaBwd", "PirShuffle", "PirPromptBwd", "PirBcastAdd", "PirToNhwc16", "PirOcab", "PirOcabBwd", "PirPackJob"]
     fields = {n: [f[0].rstrip("_") if f[0] == "in_" else f[0] for f in getattr(_lib, n)._fields_] for n in names}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for n in names:

@@ -266,6 +266,11 @@ PWDW_CASES = [
     (1, 8, 8, 96, 256, True, LN_NONE, None, 0, True, False),
     (5, 16, 16, 48, 128, True, LN_WITHBIAS, 96, 48, False, False),
     (2, 128, 128, 96, 256, True, LN_WITHBIAS, None, 0, False, False),
+    # ... and its plain form (qkv): 144 = 128 + 16 channels, 288 = 256 + 32 (last block has one valid warp quarter)
+    (2, 40, 72, 96, 288, False, LN_WITHBIAS, None, 0, True, True),
+    (3, 20, 28, 48, 144, False, LN_BIASFREE, None, 0, False, True),
+    (2, 128, 128, 96, 288, False, LN_WITHBIAS, None, 0, False, False),
+    (1, 8, 8, 48, 144, False, LN_NONE, None, 0, True, False),
 ]
 
 
@@ -296,6 +301,28 @@ def test_pwdw(case, dt):
     atol, rtol = tol(dt, 2.0)
     report_mismatch("pwdw", out, ref, atol + 1.5e-3 * ref.abs().max().item(), rtol)
     assert float(out_buf[..., N:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", [(2, 40, 56, 96), (3, 24, 24, 48), (1, 128, 128, 96)], ids=lambda c: "B%dH%dW%dC%d" % c)
+def test_pwdw_split_outputs(case, dt):
+    """qkv with q|k and v written to two dense tensors == the single-tensor result (model.py:121 chunk)."""
+    B, H, W, Cc = case
+    N = 3 * Cc
+    assert ops.pwdw_split_supported(Cc, N)
+    torch.manual_seed(Cc)
+    x, _ = rand_act(B, H, W, Cc, dt, None, 0, scale=2.0)
+    wt = torch.randn(N, Cc, device=DEV) / Cc ** 0.5
+    w16, _, vec_t = packing.pack_pointwise(wt, dt, gamma=torch.rand(Cc, device=DEV) + 0.5, beta=torch.randn(Cc, device=DEV) * 0.2)
+    dw = packing.pack_depthwise(torch.randn(N, 1, 3, 3, device=DEV) / 3, torch.float16)
+    one = torch.zeros(B, H, W, N, device=DEV, dtype=dt)
+    qk = torch.zeros(B, H, W, 2 * Cc, device=DEV, dtype=dt)
+    v = torch.zeros(B, H, W, Cc, device=DEV, dtype=dt)
+    ops.pwdw(x, w16, dw, one, gate=False, ln_mode=LN_WITHBIAS, vec_t=vec_t)(stream())
+    ops.pwdw(x, w16, dw, qk, gate=False, ln_mode=LN_WITHBIAS, vec_t=vec_t, out2=v)(stream())
+    torch.cuda.synchronize()
+    assert torch.equal(one[..., :2 * Cc], qk) and torch.equal(one[..., 2 * Cc:], v)
+    assert float(one.abs().max()) > 0
 
 
 # --------------------------------------------------------------------------------------------------
