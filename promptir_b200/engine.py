@@ -26,6 +26,7 @@ from typing import Callable, Dict, List, Optional
 import torch
 
 from . import ops, packing
+from .repack import Packer
 from ._lib import (LN_BIASFREE, LN_NONE, LN_WITHBIAS, OUT_FINAL_NCHW32, OUT_NHWC16, OUT_SHUFFLE16, OUT_UNSHUFFLE16)
 
 Tensor = torch.Tensor
@@ -52,10 +53,16 @@ class Engine:
             _lib.check(_lib.load().pir_check_device(), "pir_check_device")
         self.ops: List[dict] = []
         self._packers: List[Callable[[], None]] = []
+        # derived weight caches: requests recorded while the program is built, filled / refreshed by ONE pir_repack launch
+        self.pk = Packer(self.device, verify=os.environ.get("PROMPTIR_B200_PACK_VERIFY") == "1")
         self._graph = None
         self._param_version = -1
         self._io = (img_in, out)
         self._build()
+        if self.cuda:
+            self.pk.run()
+        self._ptr_fingerprint = self._pointer_fingerprint()
+        self._param_version = self._current_version()
 
     # ------------------------------------------------------------------------------------------------
     # helpers
@@ -159,8 +166,7 @@ class Engine:
 
         # ---- encoder -----------------------------------------------------------------------------------
         pe = m.patch_embed.proj
-        pe_w, pe_b = self._cached(lambda: [pe.weight.detach().float().contiguous(),
-                                           None if pe.bias is None else pe.bias.detach().float().contiguous()])
+        pe_w, pe_b = self.pk.f32(pe.weight), self.pk.f32(pe.bias)
         self._emit("patch_embed", lambda: ops.patch_embed(self.img_in, pe_w, pe_b, enc1), img=self.img_in, w=pe_w, bias=pe_b,
                    out=enc1)
         self._stage(m.encoder_level1, enc1)
@@ -190,11 +196,9 @@ class Engine:
         self._stage(m.decoder_level1, self.cat1)
         self._stage(m.refinement, self.cat1)
         oc = m.output
-        (ow,) = self._cached(lambda: [packing.pack_conv3x3(oc.weight, dt)])
-        (ob,) = self._cached(lambda: [None if oc.bias is None else oc.bias.detach().float().contiguous()])
+        ow, ob = self.pk.conv3x3(oc.weight, dt), self.pk.f32(oc.bias)
         self._gemm(self.cat1, ow, self.out, n=oc.out_channels, taps=9, out_mode=OUT_FINAL_NCHW32, vec_t=ob, img=self.img_in,
                    tag="output")
-        self._param_version = self._current_version()
         self.launches = [r["launch"] for r in self.ops]
 
     def _stage(self, mod, x: Tensor) -> None:
@@ -212,19 +216,14 @@ class Engine:
         at, ff = blk.attn, blk.ffn
         beta = lambda n: getattr(n, "bias", None)
 
-        qkv_w, qkv_s, qkv_t = self._cached(lambda: list(packing.pack_pointwise(
-            at.qkv.weight, dt, gamma=n1.weight, beta=beta(n1), bias=at.qkv.bias)))
-        dwq_w, dwq_b = self._cached(lambda: [packing.pack_depthwise(at.qkv_dwconv.weight, dt),
-                                             None if at.qkv_dwconv.bias is None else at.qkv_dwconv.bias.detach().float().contiguous()])
-        temp, wo, wo_b = self._cached(lambda: [at.temperature.detach().float().reshape(-1).contiguous(),
-                                               at.project_out.weight.detach().float().reshape(c, c).contiguous(),
-                                               None if at.project_out.bias is None else at.project_out.bias.detach().float().contiguous()])
-        pin_w, pin_s, pin_t = self._cached(lambda: list(packing.pack_pointwise(
-            ff.project_in.weight, dt, gamma=n2.weight, beta=beta(n2), bias=ff.project_in.bias, row_map=gmap, n_total=2 * hp)))
-        dwf_w, dwf_b = self._cached(lambda: [packing.pack_depthwise(ff.dwconv.weight, dt, chan_map=gmap, c_total=2 * hp),
-                                             packing.scatter_vec(ff.dwconv.bias, gmap, 2 * hp)])
-        pout_w, _, pout_t = self._cached(lambda: list(packing.pack_pointwise(ff.project_out.weight, dt, bias=ff.project_out.bias,
-                                                                            k_total=hp)))
+        pk = self.pk
+        qkv_w, qkv_s, qkv_t = pk.pointwise(at.qkv.weight, dt, gamma=n1.weight, beta=beta(n1), bias=at.qkv.bias)
+        dwq_b = pk.f32(at.qkv_dwconv.bias)
+        temp, wo, wo_b = pk.f32(at.temperature, (-1,)), pk.f32(at.project_out.weight, (c, c)), pk.f32(at.project_out.bias)
+        pin_w, pin_s, pin_t = pk.pointwise(ff.project_in.weight, dt, gamma=n2.weight, beta=beta(n2), bias=ff.project_in.bias,
+                                           rows=(hid, hp), n_total=2 * hp)
+        dwf_b = pk.vec(ff.dwconv.bias, (hid, hp), 2 * hp)
+        pout_w, _, pout_t = pk.pointwise(ff.project_out.weight, dt, bias=ff.project_out.bias, k_total=hp)
 
         qkv_pre = self._scratch(self.S1, h, w, 3 * c)
         qkv = self._scratch(self.S2, h, w, 3 * c)
@@ -243,11 +242,12 @@ class Engine:
             qk = self.S2[:n * 2 * c].view(B, h, w, 2 * c)
             v = self.S2[n * 2 * c:n * 3 * c].view(B, h, w, c)
         if fuse_qkv:
-            (dwq_h,) = self._cached(lambda: [packing.pack_depthwise(at.qkv_dwconv.weight, self.dw16)])
+            dwq_h = pk.depthwise(at.qkv_dwconv.weight, self.dw16)
             o1, o2 = (qk, v) if split else (qkv, None)
             self._emit("pwdw", lambda: ops.pwdw(x, qkv_w, dwq_h, o1, gate=False, ln_mode=self.ln_mode, vec_t=qkv_t, dw_bias=dwq_b, out2=o2),
                        a=x, w=qkv_w, dw_w=dwq_h, out=o1, out2=o2, gate=False, ln_mode=self.ln_mode, vec_t=qkv_t, dw_bias=dwq_b, tag="K12")
         else:
+            dwq_w = pk.depthwise(at.qkv_dwconv.weight, dt)
             self._gemm(x, qkv_w, qkv_pre, n=3 * c, ln_mode=self.ln_mode, ln_s=qkv_s, vec_t=qkv_t, tag="K1")
             self._emit("dwconv", lambda: ops.dwconv3x3(qkv_pre, dwq_w, qkv, gate=False, bias=dwq_b), x=qkv_pre, w=dwq_w, out=qkv,
                        gate=False, bias=dwq_b, tag="K2")
@@ -257,10 +257,11 @@ class Engine:
                    wo=wo, wfold=wfold, tag="K3b")
         self._gemm(v, wfold, x, n=c, res=x, vec_t=wo_b, w_batched=True, tag="K4")
         if fuse_ffn:
-            (dwf_h,) = self._cached(lambda: [packing.pack_depthwise(ff.dwconv.weight, self.dw16, chan_map=gmap, c_total=2 * hp)])
+            dwf_h = pk.depthwise(ff.dwconv.weight, self.dw16, split=(hid, hp), c_total=2 * hp)
             self._emit("pwdw", lambda: ops.pwdw(x, pin_w, dwf_h, gated, gate=True, ln_mode=self.ln_mode, vec_t=pin_t, dw_bias=dwf_b),
                        a=x, w=pin_w, dw_w=dwf_h, out=gated, gate=True, ln_mode=self.ln_mode, vec_t=pin_t, dw_bias=dwf_b, tag="K56")
         else:
+            dwf_w = pk.depthwise(ff.dwconv.weight, dt, split=(hid, hp), c_total=2 * hp)
             self._gemm(x, pin_w, hid_pre, n=2 * hp, ln_mode=self.ln_mode, ln_s=pin_s, vec_t=pin_t, tag="K5")
             self._emit("dwconv", lambda: ops.dwconv3x3(hid_pre, dwf_w, gated, gate=True, bias=dwf_b), x=hid_pre, w=dwf_w, out=gated,
                        gate=True, bias=dwf_b, tag="K6")
@@ -268,26 +269,24 @@ class Engine:
 
     def _down(self, mod, x: Tensor, out: Tensor) -> None:
         conv = mod.body[0]                                  # model.py:164-165
-        (w,) = self._cached(lambda: [packing.pack_conv3x3(conv.weight, self.dtype)])
+        w = self.pk.conv3x3(conv.weight, self.dtype)
         self._gemm(x, w, out, n=conv.out_channels, taps=9, out_mode=OUT_UNSHUFFLE16, tag="down")
 
     def _up(self, mod, x: Tensor, out: Tensor) -> None:
         conv = mod.body[0]                                  # model.py:174-175
-        (w,) = self._cached(lambda: [packing.pack_conv3x3(conv.weight, self.dtype)])
+        w = self.pk.conv3x3(conv.weight, self.dtype)
         self._gemm(x, w, out, n=conv.out_channels, taps=9, out_mode=OUT_SHUFFLE16, tag="up")
 
     def _reduce(self, conv, x: Tensor, out: Tensor) -> None:
-        w, _, t = self._cached(lambda: list(packing.pack_pointwise(conv.weight, self.dtype, bias=conv.bias)))
+        w, _, t = self.pk.pointwise(conv.weight, self.dtype, bias=conv.bias)
         self._gemm(x, w, out, n=conv.out_channels, vec_t=t, tag="reduce")
 
     def _prompt(self, pg, x: Tensor, out: Tensor) -> None:
         """PromptGenBlock (model.py:226-235): fused pool/linear/softmax/mix/bilinear, then the 3x3 conv."""
         B, h, w, _ = x.shape
         d = pg.conv3x3.in_channels
-        prm, lw, lb = self._cached(lambda: [packing.pack_prompt(pg.prompt_param),
-                                            pg.linear_layer.weight.detach().float().contiguous(),
-                                            pg.linear_layer.bias.detach().float().contiguous()])
-        (cw,) = self._cached(lambda: [packing.pack_conv3x3(pg.conv3x3.weight, self.dtype)])
+        prm, lw, lb = self.pk.prompt(pg.prompt_param), self.pk.f32(pg.linear_layer.weight), self.pk.f32(pg.linear_layer.bias)
+        cw = self.pk.conv3x3(pg.conv3x3.weight, self.dtype)
         tmp = self._scratch(self.S2, h, w, d)
         self._emit("prompt", lambda: ops.prompt_gen(x, prm, lw, lb, tmp, self.ws), x=x, prompt=prm, lin_w=lw, lin_b=lb, out=tmp,
                    ws=self.ws, tag="K10")
@@ -299,10 +298,22 @@ class Engine:
     def _current_version(self) -> int:
         return sum(p._version for p in self.m.parameters())
 
+    def params_moved(self) -> bool:
+        """True when a parameter's storage was replaced since the engine was built (`p.data = ...`, load_state_dict(assign=True),
+        EMA swaps): the launch descriptors hold raw pointers to the fp32 parameters, so the owner must build a new engine."""
+        return self.cuda and self._ptr_fingerprint != self._pointer_fingerprint()
+
+    def _pointer_fingerprint(self) -> int:
+        h = 0
+        for p in self.m.parameters():                   # the module's CURRENT parameter objects (assign=True swaps the objects too)
+            h = (h * 1000003 + p.data_ptr()) & 0xFFFFFFFFFFFF
+        return h
+
     def refresh_weights(self) -> None:
-        """Rebuild the packed caches in place (keeps pointers, so a captured graph stays valid)."""
+        """Rebuild the packed caches in place (keeps pointers, so a captured graph stays valid): one pir_repack launch."""
+        self.pk.run()
         with torch.no_grad():
-            for fn in self._packers:
+            for fn in self._packers:            # torch packers of subclasses that still use _cached
                 fn()
         self._param_version = self._current_version()
 

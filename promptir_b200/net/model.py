@@ -181,6 +181,9 @@ class PromptIR(nn.Module):
         from ..engine import Engine, SplitEngine
         key = (batch, height, width, str(device), self.compute_dtype)
         eng = self._engines.get(key)
+        if eng is not None and eng.params_moved():          # p.data = ..., load_state_dict(assign=True), EMA swap: raw pointers are stale
+            del self._engines[key]
+            eng = None
         if eng is None:
             if len(self._engines) >= 4:                     # bound the workspace held by stale shapes
                 self._engines.pop(next(iter(self._engines)))
@@ -195,7 +198,7 @@ class PromptIR(nn.Module):
         """The forward+backward program for this shape (one is kept: it holds every block's activations)."""
         from ..train_engine import TrainEngine
         key = (batch, height, width, str(device), self.compute_dtype, input_grad, self.grad_scale)
-        if self._train_engine is None or self._train_engine[0] != key:
+        if self._train_engine is None or self._train_engine[0] != key or self._train_engine[1].params_moved():
             self._train_engine = None                       # free the old arena before building the new one
             self._train_engine = (key, TrainEngine(self, batch, height, width, device, self.compute_dtype,
                                                    grad_scale=self.grad_scale, input_grad=input_grad))

@@ -66,7 +66,11 @@ class TrainEngine(Engine):
 
     def _raw(self, p: Optional[Tensor]) -> Optional[Tensor]:
         """The fp32 parameter itself (finalize kernels read gamma/beta/W from the canonical storage)."""
-        return None if p is None else p.detach()
+        if p is None:
+            return None
+        if self.cuda:
+            self.pk._params.append(p)                   # part of the pointer fingerprint (Engine.params_moved)
+        return p.detach()
 
     def _later(self, fn: Callable[[], None]) -> None:
         self._bwd_stack.append(fn)
@@ -202,8 +206,7 @@ class TrainEngine(Engine):
         # ================================ forward program ================================================
         self.ops = self.fwd_ops = []
         pe = m.patch_embed.proj
-        pe_w, pe_b = self._cached(lambda: [pe.weight.detach().float().contiguous(),
-                                           None if pe.bias is None else pe.bias.detach().float().contiguous()])
+        pe_w, pe_b = self.pk.f32(pe.weight), self.pk.f32(pe.bias)
         self._emit("patch_embed", lambda: ops.patch_embed(self.img_in, pe_w, pe_b, enc1), img=self.img_in, w=pe_w, bias=pe_b, out=enc1)
         self._later(lambda: self._patch_embed_bwd(pe, g_enc1))
         self._tstage(m.encoder_level1, enc1, g_enc1)
@@ -234,8 +237,7 @@ class TrainEngine(Engine):
         self._tstage(m.decoder_level1, self.cat1, self.g_dec1, first_out=self.dec1)
         self._tstage(m.refinement, self.dec1, self.g_dec1)
         oc = m.output
-        (ow,) = self._cached(lambda: [packing.pack_conv3x3(oc.weight, dt)])
-        (ob,) = self._cached(lambda: [None if oc.bias is None else oc.bias.detach().float().contiguous()])
+        ow, ob = self.pk.conv3x3(oc.weight, dt), self.pk.f32(oc.bias)
         self._gemm(self.dec1, ow, self.out, n=oc.out_channels, taps=9, out_mode=OUT_FINAL_NCHW32, vec_t=ob, img=self.img_in, tag="output")
         self._later(lambda: self._output_bwd(oc))
 
@@ -244,11 +246,12 @@ class TrainEngine(Engine):
     def _finish_build(self) -> None:
         """Emit the backward program from the closures the forward construction left on the stack (in reverse), after a dry pass that
         sizes the shared fp32 workspace of the weight-gradient kernels."""
-        npk = len(self._packers)
+        npk, mark = len(self._packers), self.pk.mark()
         self.ops, self._dry = [], True
         for fn in reversed(self._bwd_stack):
             fn()
         del self._packers[npk:]
+        self.pk.rollback(mark)                          # the dry pass's cache requests are made again by the real pass
         self.wg_ws = self._f32(max(self._wg_need, 1))
         self.ops, self._dry = [], False
         self.bwd_ops = self.ops
@@ -293,13 +296,12 @@ class TrainEngine(Engine):
         n1 = norm.body
         beta1 = getattr(n1, "bias", None)
         flip = lambda wt: wt.detach().flip(2, 3)
-        qkv_w, _, qkv_t = self._cached(lambda: list(packing.pack_pointwise(at.qkv.weight, dt, gamma=n1.weight, beta=beta1, bias=at.qkv.bias)))
-        (qkv_wT,) = self._cached(lambda: [packing.pack_pointwise((at.qkv.weight.detach().reshape(3 * c, c) * n1.weight.detach().view(1, -1)).t(), dt)[0]])
-        dwq_w, dwq_f, dwq_b = self._cached(lambda: [packing.pack_depthwise(at.qkv_dwconv.weight, dt), packing.pack_depthwise(flip(at.qkv_dwconv.weight), dt),
-                                                    None if at.qkv_dwconv.bias is None else at.qkv_dwconv.bias.detach().float().contiguous()])
-        temp, wo, wo_b = self._cached(lambda: [at.temperature.detach().float().reshape(-1).contiguous(),
-                                               at.project_out.weight.detach().float().reshape(c, c).contiguous(),
-                                               None if at.project_out.bias is None else at.project_out.bias.detach().float().contiguous()])
+        pk = self.pk
+        qkv_w, _, qkv_t = pk.pointwise(at.qkv.weight, dt, gamma=n1.weight, beta=beta1, bias=at.qkv.bias)
+        qkv_wT = pk.pointwise(at.qkv.weight, dt, gamma=n1.weight, transpose=True)[0]            # (W diag(gamma))^T for the dgrad GEMM
+        dwq_w, dwq_f = pk.depthwise(at.qkv_dwconv.weight, dt), pk.depthwise(at.qkv_dwconv.weight, dt, flip=True)
+        dwq_b = pk.f32(at.qkv_dwconv.bias)
+        temp, wo, wo_b = pk.f32(at.temperature, (-1,)), pk.f32(at.project_out.weight, (c, c)), pk.f32(at.project_out.bias)
         keep = lambda ch: self._zeros(B, h, w, ch)
         xh1, qkv_pre, qkv = keep(c), keep(3 * c), keep(3 * c)
         rstd1 = self._f32(B * h * w)
@@ -350,16 +352,15 @@ class TrainEngine(Engine):
         n2 = norm.body
         beta2 = getattr(n2, "bias", None)
         flip = lambda wt: wt.detach().flip(2, 3)
-        pin_w, _, pin_t = self._cached(lambda: list(packing.pack_pointwise(ff.project_in.weight, dt, gamma=n2.weight, beta=beta2,
-                                                                           bias=ff.project_in.bias, row_map=gmap, n_total=2 * hp)))
-        (pin_wT,) = self._cached(lambda: [packing.pack_pointwise((ff.project_in.weight.detach().reshape(2 * hid, c) * n2.weight.detach().view(1, -1)).t(),
-                                                                  dt, col_map=gmap, k_total=2 * hp)[0]])
-        dwf_w, dwf_f, dwf_b = self._cached(lambda: [packing.pack_depthwise(ff.dwconv.weight, dt, chan_map=gmap, c_total=2 * hp),
-                                                    packing.pack_depthwise(flip(ff.dwconv.weight), dt, chan_map=gmap, c_total=2 * hp),
-                                                    packing.scatter_vec(ff.dwconv.bias, gmap, 2 * hp)])
-        pout_w, _, pout_t = self._cached(lambda: list(packing.pack_pointwise(ff.project_out.weight, dt, bias=ff.project_out.bias, k_total=hp)))
-        (pout_wT,) = self._cached(lambda: [packing.pack_pointwise(ff.project_out.weight.detach().reshape(c, hid).t(), dt, n_total=hp,
-                                                                   row_map=torch.arange(hid, device=self.device))[0]])
+        pk = self.pk
+        pin_w, _, pin_t = pk.pointwise(ff.project_in.weight, dt, gamma=n2.weight, beta=beta2, bias=ff.project_in.bias, rows=(hid, hp),
+                                       n_total=2 * hp)
+        pin_wT = pk.pointwise(ff.project_in.weight, dt, gamma=n2.weight, transpose=True, cols=(hid, hp), k_total=2 * hp)[0]
+        dwf_w = pk.depthwise(ff.dwconv.weight, dt, split=(hid, hp), c_total=2 * hp)
+        dwf_f = pk.depthwise(ff.dwconv.weight, dt, flip=True, split=(hid, hp), c_total=2 * hp)
+        dwf_b = pk.vec(ff.dwconv.bias, (hid, hp), 2 * hp)
+        pout_w, _, pout_t = pk.pointwise(ff.project_out.weight, dt, bias=ff.project_out.bias, k_total=hp)
+        pout_wT = pk.pointwise(ff.project_out.weight, dt, transpose=True, n_total=hp)[0]
         keep = lambda ch: self._zeros(B, h, w, ch)
         xh2, hid_pre, gated = keep(c), keep(2 * hp), keep(hp)
         rstd2 = self._f32(B * h * w)
@@ -394,8 +395,7 @@ class TrainEngine(Engine):
     def _tdown(self, mod, x, out, g_x, g_out) -> None:
         conv = mod.body[0]                                   # model.py:164-165: conv3x3 n -> n/2, PixelUnshuffle(2)
         dt = self.dtype
-        (w, wT) = self._cached(lambda: [packing.pack_conv3x3(conv.weight, dt),
-                                        packing.pack_conv3x3(conv.weight.detach().transpose(0, 1).flip(2, 3), dt)])
+        w, wT = self.pk.conv3x3(conv.weight, dt), self.pk.conv3x3(conv.weight, dt, transpose_flip=True)
         self._gemm(x, w, out, n=conv.out_channels, taps=9, out_mode=OUT_UNSHUFFLE16, tag="down")
         B, h, ww, _ = x.shape
 
@@ -410,8 +410,7 @@ class TrainEngine(Engine):
     def _tup(self, mod, x, out, g_x, g_out) -> None:
         conv = mod.body[0]                                   # model.py:174-175: conv3x3 n -> 2n, PixelShuffle(2)
         dt = self.dtype
-        (w, wT) = self._cached(lambda: [packing.pack_conv3x3(conv.weight, dt),
-                                        packing.pack_conv3x3(conv.weight.detach().transpose(0, 1).flip(2, 3), dt)])
+        w, wT = self.pk.conv3x3(conv.weight, dt), self.pk.conv3x3(conv.weight, dt, transpose_flip=True)
         self._gemm(x, w, out, n=conv.out_channels, taps=9, out_mode=OUT_SHUFFLE16, tag="up")
         B, h, ww, _ = x.shape
 
@@ -426,8 +425,7 @@ class TrainEngine(Engine):
     def _tconv3(self, conv, x, out, g_x, g_out, tag="conv3") -> None:
         """out = conv3x3(x) (no bias), g_x = conv3x3^T(g_out) (assigned)."""
         dt = self.dtype
-        (w, wT) = self._cached(lambda: [packing.pack_conv3x3(conv.weight, dt),
-                                        packing.pack_conv3x3(conv.weight.detach().transpose(0, 1).flip(2, 3), dt)])
+        w, wT = self.pk.conv3x3(conv.weight, dt), self.pk.conv3x3(conv.weight, dt, transpose_flip=True)
         self._gemm(x, w, out, n=conv.out_channels, taps=9, tag=tag)
 
         def bwd():
@@ -438,8 +436,8 @@ class TrainEngine(Engine):
 
     def _treduce(self, conv, x, out, g_x, g_out) -> None:
         dt = self.dtype
-        w, _, t = self._cached(lambda: list(packing.pack_pointwise(conv.weight, dt, bias=conv.bias)))
-        (wT,) = self._cached(lambda: [packing.pack_pointwise(conv.weight.detach().reshape(conv.out_channels, conv.in_channels).t(), dt)[0]])
+        w, _, t = self.pk.pointwise(conv.weight, dt, bias=conv.bias)
+        wT = self.pk.pointwise(conv.weight, dt, transpose=True)[0]
         self._gemm(x, w, out, n=conv.out_channels, vec_t=t, tag="reduce")
 
         def bwd():
@@ -455,10 +453,8 @@ class TrainEngine(Engine):
         B, h, w, cx = x.shape
         d = pg.conv3x3.in_channels
         L = pg.prompt_param.shape[1]
-        prm, lw, lb = self._cached(lambda: [packing.pack_prompt(pg.prompt_param), pg.linear_layer.weight.detach().float().contiguous(),
-                                            pg.linear_layer.bias.detach().float().contiguous()])
-        (cw, cwT) = self._cached(lambda: [packing.pack_conv3x3(pg.conv3x3.weight, dt),
-                                          packing.pack_conv3x3(pg.conv3x3.weight.detach().transpose(0, 1).flip(2, 3), dt)])
+        prm, lw, lb = self.pk.prompt(pg.prompt_param), self.pk.f32(pg.linear_layer.weight), self.pk.f32(pg.linear_layer.bias)
+        cw, cwT = self.pk.conv3x3(pg.conv3x3.weight, dt), self.pk.conv3x3(pg.conv3x3.weight, dt, transpose_flip=True)
         up = self._zeros(B, h, w, d)                          # kept: resized prompt (operand of the conv's weight gradient)
         pws = self._f32(ops.prompt_ws_floats(B, h * w, cx))   # kept: pooled partial sums
         wts = self._f32(B, L)                                 # kept: softmax weights
@@ -484,7 +480,7 @@ class TrainEngine(Engine):
     def _output_bwd(self, oc) -> None:
         """out = conv3x3(dec1) + img (model.py:377).  First backward op: dL/dout arrives as fp32 NCHW in self.d_out."""
         dt = self.dtype
-        (wT,) = self._cached(lambda: [packing.pack_conv3x3(oc.weight.detach().transpose(0, 1).flip(2, 3), dt)])
+        wT = self.pk.conv3x3(oc.weight, dt, transpose_flip=True)
         self._emit("to_nhwc16", lambda: ops.nchw32_to_nhwc16(self.d_out, self.d_out8, self.grad_scale), src=self.d_out, out=self.d_out8,
                    scale=self.grad_scale, tag="Bo8")
         wg = self._wgrad(self.d_out8, self.dec1, taps=9, colsum=oc.bias is not None, tag="Bow")
@@ -497,7 +493,7 @@ class TrainEngine(Engine):
         wg = self._wgrad(g_enc1, self.img8, taps=9, colsum=pe.bias is not None, tag="Bew")
         self._wgrad_fin(wg, dst_w=self._grad_of(pe.weight), dst_bias=self._grad_of(pe.bias), tag="Bef")
         if self.input_grad:                                  # d img = d out (through "+ inp_img") + conv^T(g)
-            (wT,) = self._cached(lambda: [packing.pack_conv3x3(pe.weight.detach().transpose(0, 1).flip(2, 3), self.dtype)])
+            wT = self.pk.conv3x3(pe.weight, self.dtype, transpose_flip=True)
             self._gemm(g_enc1, wT, self.d_img, n=pe.in_channels, taps=9, out_mode=OUT_FINAL_NCHW32, img=self.d_out, tag="Bed")
 
     # ------------------------------------------------------------------------------------------------
