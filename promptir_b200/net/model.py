@@ -75,6 +75,17 @@ class OverlapPatchEmbed(nn.Module):                        # model.py:202-206
         self.proj = nn.Conv2d(in_c, embed_dim, 3, 1, 1, bias=bias)
 
 
+class resblock(nn.Module):                                 # model.py:142-155 (never instantiated by the reference; kept for import parity)
+    def __init__(self, dim: int):
+        super().__init__()
+        self.body = nn.Sequential(nn.Conv2d(dim, dim, kernel_size=3, stride=1, padding=1, bias=False), nn.PReLU(),
+                                  nn.Conv2d(dim, dim, kernel_size=3, stride=1, padding=1, bias=False))
+
+    def forward(self, x):
+        # Not on the hot path (no caller in the reference): conv-PReLU-conv residual through torch, like model.py:153-155
+        return self.body(x) + x
+
+
 class Downsample(nn.Module):                               # model.py:160-165
     def __init__(self, n_feat: int):
         super().__init__()
@@ -121,9 +132,14 @@ class _PromptIRFunction(torch.autograd.Function):
                                "forward of the same shape; call backward() before the next forward (as train.py does)")
         eng.backward(d_out.contiguous().float(), use_graph=module.use_cuda_graph)
         grads = []
-        for (name, _), need in zip(module.named_parameters(), ctx.need):
+        for (name, p), need in zip(module.named_parameters(), ctx.need):
             # parameters the forward never reads (chnl_reduce*, reduce_noise_channel_*: model.py:271-287) get no gradient, like autograd
-            grads.append(eng.grads[name] if (need and name in eng.live_params) else None)
+            g = eng.grads[name] if (need and name in eng.live_params) else None
+            # p.grad may already BE this view (ddp.attach_flat_grads): AccumulateGrad would then compute p.grad += p.grad on one
+            # buffer; any other existing .grad would keep a reference into a buffer the next backward overwrites.  A clone is safe.
+            if g is not None and p.grad is not None:
+                g = g.clone()
+            grads.append(g)
         return (None, None, eng.d_img.clone() if ctx.need_img else None, *grads)
 
 

@@ -537,6 +537,10 @@ class TrainEngine(Engine):
         self.d_out.copy_(d_out)
         self._run("bwd", self.bwd_launches, use_graph)
 
+    def run_bwd_range(self, a: int, b: int, use_graph: bool = True) -> None:
+        """Records [a, b) of the backward program (ddp.OverlappedReducer cuts the backward into a few such pieces); d_out is already set."""
+        self._run(("bwd", a, b), self.bwd_launches[a:b], use_graph)
+
     def replay(self, use_graph: bool = True) -> None:
         self._run("fwd", self.fwd_launches, use_graph)
 

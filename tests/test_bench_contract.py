@@ -26,9 +26,12 @@ def test_reference_arm_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "promptir_fwd_megapixels_per_sec" and d["unit"] == "MP/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["n_gpus"] == 1 and d["gpu_launches"] == 0
-    assert d["value"] > 0 and abs(d["value"] - 256 * 256 / 1e6 / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"] + 1e-9
+    # one step = a bounded sample of 4 of the batch's 16 images (said so in config.workload and cpu_baseline.sample)
+    assert d["value"] > 0 and abs(d["value"] - 4 * 256 * 256 / 1e6 / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"] + 1e-9
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "256x256" in cb["sample"]
+    ref_copy = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "net", "model.py"))
+    assert cb["kind"] == ("reference" if ref_copy else "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert "256x256" in cb["sample"] and "bounded sample" in cb["sample"] and "bounded sample" in d["config"]["workload"]
     assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

@@ -40,11 +40,18 @@ def _worker(rank, world, port, q):
     eng = _grads(model, x[sl], d[sl] / per)                   # each rank: mean loss over ITS shard (as under DDP)
     ddp.attach_flat_grads(model, eng)
     ddp.allreduce_gradients(eng)
+    # the overlapped exchange (backward in 4 pieces, finished gradient runs reduced after each piece) gives the same buffer
+    one_shot = eng.grad_flat.clone()
+    red = ddp.OverlappedReducer(eng, segments=4, run_range=lambda a, b: [emulator.DISPATCH[r["kind"]](r) for r in eng.bwd_ops[a:b]])
+    covered = sum(ln for _, _, runs in red.plan for _, ln in runs)
+    live = sum(eng.grads[n].numel() for n in eng.live_params)
+    red.backward_and_reduce(d[sl] / per)
+    overlap_err = ((eng.grad_flat - one_shot).norm() / one_shot.norm()).item()
     dead = [n for n, p in model.named_parameters() if p.grad is None]
     if rank == 0:
         ref = _grads(model, x, d / B).grad_flat               # single process, mean loss over the whole batch
         q.put((((eng.grad_flat - ref).norm() / ref.norm()).item(), len(dead),
-               model.output.weight.grad.data_ptr() == eng.grads["output.weight"].data_ptr()))
+               model.output.weight.grad.data_ptr() == eng.grads["output.weight"].data_ptr(), overlap_err, covered == live, len(red.plan)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,8 +65,9 @@ def test_flat_gradient_allreduce_two_gloo_ranks():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    rel, ndead, zero_copy = q.get(timeout=600)
+    rel, ndead, zero_copy, overlap_err, all_covered, pieces = q.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     assert rel < 1e-4 and ndead == 6 and zero_copy
+    assert overlap_err < 1e-6 and all_covered and pieces == 4, (overlap_err, all_covered, pieces)
