@@ -20,8 +20,10 @@ template <class T> __device__ __forceinline__ uint32_t pack2(float lo, float hi)
 template <> __device__ __forceinline__ uint32_t pack2<BF16>(float lo, float hi) {
   uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r;
 }
+// fp16 storage saturates at +-65504 (same instruction cost): an activation beyond the fp16 range clips instead of turning into inf
+// and, one LayerNorm later, into NaN
 template <> __device__ __forceinline__ uint32_t pack2<FP16>(float lo, float hi) {
-  uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r;
+  uint32_t r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r;
 }
 template <class T> __device__ __forceinline__ float unpack_lo(uint32_t v);
 template <class T> __device__ __forceinline__ float unpack_hi(uint32_t v);

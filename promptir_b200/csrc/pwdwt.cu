@@ -60,6 +60,9 @@ __device__ __forceinline__ uint32_t tw_mul2(uint32_t a, uint32_t b) {
 __device__ __forceinline__ uint32_t tw_min2(uint32_t a, uint32_t b) {
   uint32_t r; asm("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
 }
+__device__ __forceinline__ uint32_t tw_max2(uint32_t a, uint32_t b) {
+  uint32_t r; asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
 __device__ __forceinline__ uint32_t tw_tanh2(uint32_t a) {
   uint32_t r; asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a)); return r;
 }
@@ -71,7 +74,9 @@ __device__ __forceinline__ uint32_t tw_gate2(uint32_t p, uint32_t q) {
   const uint32_t u = tw_min2(tw_mul2(p, p), k25);
   const uint32_t t = tw_fma2(u, tw_fma2(u, kC, kB), kA);
   const uint32_t th = tw_tanh2(tw_mul2(p, t));
-  return tw_mul2(tw_fma2(p, th, p), q);        // q already carries the factor 0.5
+  // q already carries the factor 0.5.  The product saturates at +-65504 instead of overflowing to inf (and to NaN downstream)
+  constexpr uint32_t kMax = 0x7bff7bffu, kMin = 0xfbfffbffu;
+  return tw_max2(tw_min2(tw_mul2(tw_fma2(p, th, p), q), kMax), kMin);
 }
 __device__ __forceinline__ float2 tw_h2f2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
 __device__ __forceinline__ void tw_wait_backoff(uint32_t bar, uint32_t parity) {

@@ -34,7 +34,7 @@ Tensor = torch.Tensor
 
 class Engine:
     def __init__(self, module, batch: int, height: int, width: int, device, dtype: torch.dtype = torch.bfloat16,
-                 img_in: Optional[Tensor] = None, out: Optional[Tensor] = None):
+                 img_in: Optional[Tensor] = None, out: Optional[Tensor] = None, fuse: Optional[bool] = None):
         if height % 8 or width % 8:
             raise ValueError("height and width must be multiples of 8")
         self.m = module
@@ -44,7 +44,8 @@ class Engine:
         self.cuda = self.device.type == "cuda"
         # depthwise taps of the fused kernels are IEEE half whatever the storage type (fp32 only for the CPU wiring tests)
         self.dw16 = torch.float32 if dtype == torch.float32 else torch.float16
-        self.fuse = os.environ.get("PROMPTIR_B200_FUSE", "1") != "0"     # 0: never use the fused pir_pwdw kernels (A/B timing)
+        # fuse=False / PROMPTIR_B200_FUSE=0: never use the fused pir_pwdw kernels (A/B timing, diagnostics.range_report)
+        self.fuse = (os.environ.get("PROMPTIR_B200_FUSE", "1") != "0") if fuse is None else fuse
         # q|k and v of MDTA (model.py:121) as two dense tensors written by the fused qkv kernel: the Gram streams 2C-channel rows and
         # the attn.v GEMM C-channel rows instead of slices of 3C-channel rows.  0: one [.., 3C] tensor (A/B timing)
         self.split_qkv = os.environ.get("PROMPTIR_B200_SPLITQKV", "1") != "0"
