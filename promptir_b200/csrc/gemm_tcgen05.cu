@@ -394,5 +394,15 @@ extern "C" int pir_gemm(const PirGemm* d, void* stream) {
       (d->K % 8) == 0 && (d->a_pitch % 8) == 0 && (d->a_bstride % 8) == 0 && ((uintptr_t)d->a & 15) == 0 && ((uintptr_t)d->w & 15) == 0 &&
       (!d->ln_mode || d->ln_s))
     return pir::pir_gemm_pw(d, s);
+  // dense 3x3 with <= 128 input channels: nine GEMMs over one halo'd shared-memory tile (conv3x3.cu); wider inputs / other cases fall
+  // through to the one-tile-per-CTA kernel with nine shifted TMA boxes
+  if (d->taps == 9 && d->K > 0 && d->N > 0 && d->B > 0 && d->H > 0 && d->W > 0 && (d->a_pitch % 8) == 0 && (d->a_bstride % 8) == 0 &&
+      ((uintptr_t)d->a & 15) == 0 && ((uintptr_t)d->w & 15) == 0 &&
+      !(d->out_mode == PIR_OUT_NHWC16 && ((d->N % 8) || (d->out_pitch % 8) || ((uintptr_t)d->out & 15))) &&
+      !(d->res && (d->out_mode != PIR_OUT_NHWC16 || (d->res_pitch % 8) || ((uintptr_t)d->res & 15))) &&
+      !(d->out_mode == PIR_OUT_FINAL_NCHW32 && !d->img)) {
+    const int r = pir::conv3x3_try(d, s);
+    if (r <= 0) return r;
+  }
   return d->dtype == PIR_DTYPE_BF16 ? pir::launch_gemm<pir::BF16>(d, s) : pir::launch_gemm<pir::FP16>(d, s);
 }

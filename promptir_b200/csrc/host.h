@@ -17,6 +17,8 @@ int pir_make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void
 
 // persistent pointwise GEMM (gemm_pw.cu): taps == 1, NHWC16 output
 namespace pir { int pir_gemm_pw(const PirGemm* d, cudaStream_t stream); }
+// dense 3x3 over one halo'd tile (conv3x3.cu): 1 = shape not taken (fall back), else the launch status
+namespace pir { int conv3x3_try(const PirGemm* d, cudaStream_t stream); }
 
 // Programmatic dependent launch (PDL): a kernel launched with this attribute may start while the previous kernel on the stream is
 // still draining; it runs its prologue (barrier init, TMEM allocation, descriptor prefetch, staging of static weights) and then

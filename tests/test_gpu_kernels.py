@@ -169,6 +169,14 @@ CONV_CASES = [
     (1, 24, 136, 96, 3, OUT_FINAL_NCHW32),
     (1, 4, 4, 320, 320, OUT_NHWC16),
     (1, 9, 5, 128, 128, OUT_NHWC16),
+    # halo-tile kernel (conv3x3.cu, Cin <= 128): many items per CTA (buffer / phase wrap), ragged tiles, channel slices, 8-channel Cin
+    (3, 64, 96, 48, 24, OUT_UNSHUFFLE16),
+    (2, 50, 38, 96, 192, OUT_SHUFFLE16),
+    (16, 32, 32, 64, 64, OUT_NHWC16),
+    (2, 30, 22, 128, 128, OUT_NHWC16),
+    (2, 128, 128, 96, 3, OUT_FINAL_NCHW32),
+    (1, 20, 28, 8, 48, OUT_NHWC16),
+    (1, 16, 16, 3 * 8, 16, OUT_NHWC32),
 ]
 
 
