@@ -141,7 +141,8 @@ int pir_mdta_finalize_kernels(int32_t C, int32_t heads);
 /* ---- PromptGenBlock (model.py:226-232): pool -> linear -> softmax -> weighted prompt sum -> bilinear --
  * x: NHWC 16-bit [B,H,W,C] feature; prompt: fp32 [L][S][S][D] (repacked prompt_param); lin_w fp32 [L][C],
  * lin_b fp32 [L]; out: NHWC 16-bit [B,H,W,D] (the conv3x3 that follows is a pir_gemm with taps = 9).
- * ws: fp32 workspace of pir_prompt_ws_floats() elements.  weights_out (optional) receives softmax [B][L]. */
+ * ws: fp32 workspace of pir_prompt_ws_floats() elements (per-chunk pooled sums; pir_prompt_bwd reads them).  weights_out (optional)
+ * receives softmax [B][L]. */
 typedef struct PirPrompt {
   int32_t dtype;
   int32_t B, H, W, C;       /* feature map                                                                 */
@@ -151,9 +152,13 @@ typedef struct PirPrompt {
   void* out; int64_t out_pitch, out_bstride;
   float* ws; float* weights_out;
   int32_t align_corners;    /* bilinear rule: 0 = net/model.py:231 (PromptGenBlock), 1 = prompt_xrestormer.py:350 (PromptBlock)  */
+  int32_t* sync;            /* optional: two zero-initialised int32 in device memory owned by this call site.  Given: the whole block is
+                             * ONE launch (a persistent grid with a device-wide barrier between the pool and the mix); NULL: two launches.
+                             * pir_prompt_gen_kernels() tells which.                                                                  */
 } PirPrompt;
 int64_t pir_prompt_ws_floats(int32_t B, int32_t HW, int32_t C);
 int pir_prompt_gen(const PirPrompt* d, void* stream);
+int pir_prompt_gen_kernels(const PirPrompt* d);   /* launches pir_prompt_gen enqueues for this descriptor: 1 or 2 */
 
 /* ---- OverlapPatchEmbed (model.py:206): dense 3x3, fp32 NCHW image -> 16-bit NHWC ---------------------
  * w: fp32 [Cout][Cin][3][3] (the parameter itself), bias fp32 [Cout] or NULL.  Cout % 8 == 0.            */

@@ -57,7 +57,7 @@ class PirPrompt(C.Structure):
                 ("x", vp), ("x_pitch", i64), ("x_bstride", i64),
                 ("prompt", vp), ("lin_w", vp), ("lin_b", vp),
                 ("out", vp), ("out_pitch", i64), ("out_bstride", i64),
-                ("ws", vp), ("weights_out", vp), ("align_corners", i32)]
+                ("ws", vp), ("weights_out", vp), ("align_corners", i32), ("sync", vp)]
 
 
 class PirOcab(C.Structure):
@@ -181,6 +181,7 @@ SYMBOLS = {
     "pir_mdta_finalize": (i32, [C.POINTER(PirMdta), vp]),
     "pir_prompt_ws_floats": (i64, [i32, i32, i32]),
     "pir_prompt_gen": (i32, [C.POINTER(PirPrompt), vp]),
+    "pir_prompt_gen_kernels": (i32, [C.POINTER(PirPrompt)]),
     "pir_patch_embed": (i32, [C.POINTER(PirPatchEmbed), vp]),
     "pir_tile_blend": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, vp, i32, i32, vp]),
     "pir_ln_fwd": (i32, [C.POINTER(PirLn), vp]),

@@ -137,6 +137,187 @@ prompt_mix_kernel(const float* __restrict__ partial, int nchunks, int HW, int C,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// PromptGenBlock in ONE launch (net/model.py:226-232): pool -> linear -> softmax -> weighted prompt sum -> bilinear resize.
+// The global mean pool needs every pixel of an image before the first output pixel can be written, so the persistent grid (one
+// CTA per SM at most: all CTAs are co-resident) meets once at a device-wide barrier:
+//   phase 1  per-(image, pixel chunk) partial channel sums -> ws (same layout as the two-kernel path: pir_prompt_bwd reads it);
+//   barrier  arrive counter in `sync` (zero on entry; the last CTA to finish the kernel resets it, so CUDA-graph replays work);
+//   phase 2  per (image, TS x TS output tile): the component weights of the image (pooled mean, linear, softmax: a few hundred
+//            FMAs, redone when the CTA moves to another image), the MIX at source resolution for the source patch the tile needs
+//            (sum_l w_l prompt_l, L float4 loads per source vector, kept in shared memory as fp32), then the bilinear taps from
+//            shared memory.  The two-kernel path mixed at OUTPUT resolution: 40 L2 loads per output vector instead of ~2.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prompt_grid_barrier(int* counter, int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1);
+    while (atomicAdd(counter, 0) < nblocks) __nanosleep(64);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+struct PromptFusedArgs {
+  const unsigned short* x; long long x_pitch, x_bstride;
+  int B, H, W, C, L, D, S, nchunks, chunk;
+  float* partial;
+  const float* lin_w; const float* lin_b; const float* prompt;
+  unsigned short* out; long long out_pitch, out_bstride;
+  float* weights_out;
+  int align, ts, pr, tiles_x, tiles_y;
+  int* sync;
+};
+
+constexpr int kPfThreads = 1024;      // one CTA per SM, many loads in flight: both phases stream (pool: x, mix/resize: out)
+template <class T>
+__global__ void __launch_bounds__(kPfThreads)
+prompt_fused_kernel(const PromptFusedArgs g) {
+  extern __shared__ float smem_f[];
+  __shared__ float slog[kMaxL];
+  const int C = g.C, HW = g.H * g.W, D = g.D, S = g.S, L = g.L;
+  // ---------------- phase 1: pooled partial sums ----------------
+  {
+    float* sred = smem_f;                       // [PL][C]
+    const int groups = C >> 3;
+    const int PL = kPfThreads / groups;
+    const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
+    for (int work = blockIdx.x; work < g.B * g.nchunks; work += gridDim.x) {
+      const int b = work / g.nchunks, ck = work - b * g.nchunks;
+      const int p0 = ck * g.chunk, p1 = min(p0 + g.chunk, HW);
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      if (pl < PL) {
+        const unsigned short* xb = g.x + (size_t)b * g.x_bstride + cg * 8;
+        for (int p = p0 + pl; p < p1; p += PL) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)p * g.x_pitch));
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { acc[2 * q] += unpack_lo<T>(w4[q]); acc[2 * q + 1] += unpack_hi<T>(w4[q]); }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sred[pl * C + cg * 8 + i] = acc[i];
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sm = 0.f;
+        for (int r = 0; r < PL; ++r) sm += sred[r * C + c];
+        g.partial[((size_t)b * g.nchunks + ck) * C + c] = sm;
+      }
+      __syncthreads();
+    }
+  }
+  prompt_grid_barrier(g.sync, (int)gridDim.x);
+
+  // ---------------- phase 2: weights, mix at source resolution, bilinear ----------------
+  float* semb = smem_f;                         // [C] pooled mean, then [4][C] scratch
+  float* smix = smem_f + 5 * C;                 // [pr * pr][D]
+  const int per_img = g.tiles_x * g.tiles_y;
+  const int n_items = g.B * per_img;
+  const int per_cta = (n_items + (int)gridDim.x - 1) / (int)gridDim.x;      // contiguous ranges: a CTA mostly stays inside one image
+  const int i0 = blockIdx.x * per_cta, i1 = min(i0 + per_cta, n_items);
+  const float sh = g.align ? (g.H > 1 ? (float)(S - 1) / (float)(g.H - 1) : 0.f) : (float)S / (float)g.H;
+  const float sw = g.align ? (g.W > 1 ? (float)(S - 1) / (float)(g.W - 1) : 0.f) : (float)S / (float)g.W;
+  auto src = [&](float scale, int dst) { return g.align ? scale * (float)dst : fmaxf(scale * ((float)dst + 0.5f) - 0.5f, 0.f); };
+  float wgt[kMaxL];
+  int cur_b = -1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int item = i0; item < i1; ++item) {
+    const int b = item / per_img, t = item - b * per_img;
+    const int ty = t / g.tiles_x, tx = t - ty * g.tiles_x;
+    if (b != cur_b) {
+      cur_b = b;
+      float* spart = semb + C;
+      for (int idx = threadIdx.x; idx < 4 * C; idx += blockDim.x) {
+        const int c = idx % C, part = idx / C;
+        float s0 = 0.f, s1 = 0.f;
+        int k = part;
+        for (; k + 4 < g.nchunks; k += 8) {
+          s0 += __ldcg(g.partial + ((size_t)b * g.nchunks + k) * C + c);
+          s1 += __ldcg(g.partial + ((size_t)b * g.nchunks + k + 4) * C + c);
+        }
+        if (k < g.nchunks) s0 += __ldcg(g.partial + ((size_t)b * g.nchunks + k) * C + c);
+        spart[part * C + c] = s0 + s1;
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < C; c += blockDim.x) semb[c] = (spart[c] + spart[C + c] + spart[2 * C + c] + spart[3 * C + c]) / (float)HW;
+      __syncthreads();
+      if (warp < L) {
+        float sm = 0.f;
+        for (int c = lane; c < C; c += 32) sm = fmaf(semb[c], g.lin_w[(size_t)warp * C + c], sm);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        if (lane == 0) slog[warp] = sm + g.lin_b[warp];
+      }
+      __syncthreads();
+      float mx = -INFINITY;
+      for (int l = 0; l < L; ++l) mx = fmaxf(mx, slog[l]);
+      float sum = 0.f;
+      for (int l = 0; l < L; ++l) { wgt[l] = expf(slog[l] - mx); sum += wgt[l]; }
+      const float inv = 1.0f / sum;
+      for (int l = 0; l < L; ++l) wgt[l] *= inv;
+      if (g.weights_out && t == 0 && threadIdx.x < L) g.weights_out[b * L + threadIdx.x] = wgt[threadIdx.x];
+      __syncthreads();                           // slog is rewritten for the next image
+    }
+    // source patch of this tile
+    const int oy0 = ty * g.ts, ox0 = tx * g.ts;
+    const int oy1 = min(oy0 + g.ts, g.H) - 1, ox1 = min(ox0 + g.ts, g.W) - 1;
+    const int py0 = min((int)src(sh, oy0), S - 1), px0 = min((int)src(sw, ox0), S - 1);
+    const int py1 = min(min((int)src(sh, oy1), S - 1) + 1, S - 1), px1 = min(min((int)src(sw, ox1), S - 1) + 1, S - 1);
+    const int ph = py1 - py0 + 1, pw = px1 - px0 + 1;
+    const int d4 = D >> 2;
+    for (int e = threadIdx.x; e < ph * pw * d4; e += blockDim.x) {
+      const int dq = e % d4, pp = e / d4;
+      const int yy = pp / pw, xx = pp - yy * pw;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int l = 0; l < L; ++l) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g.prompt + (((size_t)l * S + (py0 + yy)) * S + (px0 + xx)) * D) + dq);
+        acc.x = fmaf(wgt[l], v.x, acc.x); acc.y = fmaf(wgt[l], v.y, acc.y); acc.z = fmaf(wgt[l], v.z, acc.z); acc.w = fmaf(wgt[l], v.w, acc.w);
+      }
+      reinterpret_cast<float4*>(smix + (size_t)pp * D)[dq] = acc;
+    }
+    __syncthreads();
+    const int groups = D >> 3;
+    const int tw = ox1 - ox0 + 1, th = oy1 - oy0 + 1;
+    for (int e = threadIdx.x; e < th * tw * groups; e += blockDim.x) {
+      const int dg = e % groups, pp = e / groups;
+      const int y = oy0 + pp / tw, x = ox0 + pp % tw;
+      const float fy = src(sh, y), fx = src(sw, x);
+      const int y0 = min((int)fy, S - 1), x0 = min((int)fx, S - 1);
+      const int y1 = y0 + (y0 < S - 1 ? 1 : 0), x1 = x0 + (x0 < S - 1 ? 1 : 0);
+      const float ly = fminf(fmaxf(fy - (float)y0, 0.f), 1.f), lx = fminf(fmaxf(fx - (float)x0, 0.f), 1.f);
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      const float* q00 = smix + ((size_t)(y0 - py0) * pw + (x0 - px0)) * D + dg * 8;
+      const float* q01 = smix + ((size_t)(y0 - py0) * pw + (x1 - px0)) * D + dg * 8;
+      const float* q10 = smix + ((size_t)(y1 - py0) * pw + (x0 - px0)) * D + dg * 8;
+      const float* q11 = smix + ((size_t)(y1 - py0) * pw + (x1 - px0)) * D + dg * 8;
+      float acc[8];
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const float4 a = reinterpret_cast<const float4*>(q00)[hlf], bq = reinterpret_cast<const float4*>(q01)[hlf];
+        const float4 cq = reinterpret_cast<const float4*>(q10)[hlf], dq = reinterpret_cast<const float4*>(q11)[hlf];
+        // same association as the two-kernel path for each component would differ in rounding only; here the mix comes first
+        acc[hlf * 4 + 0] = w00 * a.x + w01 * bq.x + w10 * cq.x + w11 * dq.x;
+        acc[hlf * 4 + 1] = w00 * a.y + w01 * bq.y + w10 * cq.y + w11 * dq.y;
+        acc[hlf * 4 + 2] = w00 * a.z + w01 * bq.z + w10 * cq.z + w11 * dq.z;
+        acc[hlf * 4 + 3] = w00 * a.w + w01 * bq.w + w10 * cq.w + w11 * dq.w;
+      }
+      uint4 ov;
+      ov.x = pack2<T>(acc[0], acc[1]); ov.y = pack2<T>(acc[2], acc[3]);
+      ov.z = pack2<T>(acc[4], acc[5]); ov.w = pack2<T>(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(g.out + (size_t)b * g.out_bstride + ((size_t)y * g.W + x) * g.out_pitch + dg * 8) = ov;
+    }
+    __syncthreads();
+  }
+  // the last CTA to get here re-arms the barrier for the next launch (graph replay)
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(g.sync + 1, 1) == (int)gridDim.x - 1) { g.sync[0] = 0; g.sync[1] = 0; __threadfence(); }
+  }
+}
+
 static int pool_chunks(int HW) {
   int n = (HW + 255) / 256;
   return n > 64 ? 64 : (n < 1 ? 1 : n);
@@ -151,6 +332,51 @@ static int launch_prompt(const PirPrompt* d, cudaStream_t s) {
   if (groups > 256) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_prompt_gen: C > 2048");
   const int PL = 256 / groups;
   const int threads = PL * groups;
+  static const bool two = [] { const char* e = getenv("PIR_PROMPT_FUSED"); return e && e[0] == '0'; }();   // A/B: the two-kernel path
+  if (d->sync && !two && (d->D % 8) == 0) {
+    // one launch: output tile size from the shared-memory budget of the source patch (fp32 mix of (ceil(ts * scale) + 2)^2 x D)
+    const float sc_h = d->align_corners ? (d->H > 1 ? (float)(d->S - 1) / (float)(d->H - 1) : 0.f) : (float)d->S / (float)d->H;
+    const float sc_w = d->align_corners ? (d->W > 1 ? (float)(d->S - 1) / (float)(d->W - 1) : 0.f) : (float)d->S / (float)d->W;
+    const float sc = sc_h > sc_w ? sc_h : sc_w;
+    int ts = 16, pr = 0;
+    size_t smem = 0;
+    for (; ts >= 2; ts >>= 1) {
+      pr = (int)((float)(ts - 1) * sc) + 3;
+      if (pr > d->S) pr = d->S;
+      smem = ((size_t)5 * d->C + (size_t)pr * pr * d->D) * sizeof(float);
+      const size_t pool = (size_t)(kPfThreads / groups) * d->C * sizeof(float);
+      if (pool > smem) smem = pool;
+      if (smem <= 160 * 1024) break;
+    }
+    if (ts >= 2) {
+      static bool set[2] = {false, false};
+      if (!set[T::kFmt]) {
+        if (cudaFuncSetAttribute(prompt_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
+          return pir_fail(PIR_ERR_CUDA, "pir_prompt_gen: cannot raise dynamic shared memory limit");
+        set[T::kFmt] = true;
+      }
+      static int num_sms = 0;
+      if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+      }
+      PromptFusedArgs g{};
+      g.x = reinterpret_cast<const unsigned short*>(d->x); g.x_pitch = d->x_pitch; g.x_bstride = d->x_bstride;
+      g.B = d->B; g.H = d->H; g.W = d->W; g.C = d->C; g.L = d->L; g.D = d->D; g.S = d->S; g.nchunks = nchunks; g.chunk = chunk;
+      g.partial = d->ws; g.lin_w = d->lin_w; g.lin_b = d->lin_b; g.prompt = d->prompt;
+      g.out = reinterpret_cast<unsigned short*>(d->out); g.out_pitch = d->out_pitch; g.out_bstride = d->out_bstride;
+      g.weights_out = d->weights_out; g.align = d->align_corners; g.ts = ts; g.pr = pr;
+      g.tiles_x = (d->W + ts - 1) / ts; g.tiles_y = (d->H + ts - 1) / ts;
+      g.sync = d->sync;
+      const int items = d->B * g.tiles_x * g.tiles_y, pool_items = d->B * nchunks;
+      int grid = items > pool_items ? items : pool_items;
+      if (grid > num_sms) grid = num_sms;            // every CTA must be resident: they meet at a device-wide barrier
+      prompt_fused_kernel<T><<<dim3(grid), dim3(kPfThreads), smem, s>>>(g);
+      return pir_check_launch("pir_prompt_gen(fused)");
+    }
+  }
   pir_launch(pool_partial_kernel<T>, dim3(nchunks, d->B), dim3(threads), (size_t)PL * d->C * sizeof(float), s,
              reinterpret_cast<const unsigned short*>(d->x), d->x_pitch, d->x_bstride, HW, d->C, chunk, d->ws);
   if (int e = pir_check_launch("pir_prompt_gen(pool)")) return e;
@@ -328,6 +554,11 @@ extern "C" int pir_prompt_gen(const PirPrompt* d, void* stream) {
   if (d->L < 1 || d->L > pir::kMaxL) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_prompt_gen: 1 <= L <= 8");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   return d->dtype == PIR_DTYPE_BF16 ? pir::launch_prompt<pir::BF16>(d, s) : pir::launch_prompt<pir::FP16>(d, s);
+}
+
+extern "C" int pir_prompt_gen_kernels(const PirPrompt* d) {
+  static const bool two = [] { const char* e = getenv("PIR_PROMPT_FUSED"); return e && e[0] == '0'; }();
+  return (d && d->sync && !two && (d->D % 8) == 0) ? 1 : 2;
 }
 
 extern "C" int pir_patch_embed(const PirPatchEmbed* d, void* stream) {

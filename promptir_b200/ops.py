@@ -199,7 +199,11 @@ def prompt_gen(x: torch.Tensor, prompt: torch.Tensor, lin_w: torch.Tensor, lin_b
     d.out, d.out_pitch, d.out_bstride = po, op, obs
     d.ws, d.weights_out = ws.data_ptr(), _ptr(weights_out)
     d.align_corners = int(align_corners)
-    return _prepared("pir_prompt_gen", d, (x, prompt, lin_w, lin_b, out, ws, weights_out), kernels=2)
+    # two zero-initialised ints owned by this call site: the arrive counters of the single-launch kernel's device-wide barrier
+    sync = torch.zeros(2, dtype=torch.int32, device=x.device)
+    d.sync = sync.data_ptr()
+    return _prepared("pir_prompt_gen", d, (x, prompt, lin_w, lin_b, out, ws, weights_out, sync),
+                     kernels=int(_lib.load().pir_prompt_gen_kernels(C.byref(d))))
 
 
 def patch_embed(img: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> Launch:

@@ -426,9 +426,12 @@ def test_mdta_finalize_fused_equals_two_kernel_path(tmp_path):
 # prompt generation, patch embed, tile blend
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("case", [(2, 16, 16, 384, 320, 16), (1, 64, 64, 192, 128, 32), (2, 8, 24, 96, 64, 64), (1, 40, 24, 96, 64, 64)],
+@pytest.mark.parametrize("case", [(2, 16, 16, 384, 320, 16), (1, 64, 64, 192, 128, 32), (2, 8, 24, 96, 64, 64), (1, 40, 24, 96, 64, 64),
+                                  (16, 32, 32, 384, 320, 16), (16, 128, 128, 96, 64, 64), (3, 136, 72, 96, 64, 64), (16, 64, 64, 192, 128, 32)],
                          ids=lambda c: "B%dH%dW%dC%dD%dS%d" % c)
 def test_prompt_gen(case, dt):
+    """Single-launch PromptGenBlock (device-wide barrier between pool and mix): upsampling x2, identity, downsampling, ragged tiles,
+    more work items than CTAs; launched three times on the same sync counters (CUDA-graph replays re-arm the barrier)."""
     B, H, W, Cc, D, S = case
     torch.manual_seed(D)
     x, _ = rand_act(B, H, W, Cc, dt, Cc + D, 0)
@@ -438,7 +441,11 @@ def test_prompt_gen(case, dt):
     out = torch.zeros(B, H, W, D, device=DEV, dtype=dt)
     ws = torch.zeros(ops.prompt_ws_floats(B, H * W, Cc), device=DEV)
     wts = torch.zeros(B, 5, device=DEV)
-    ops.prompt_gen(x, prm, lw, lb, out, ws, wts)(stream())
+    launch = ops.prompt_gen(x, prm, lw, lb, out, ws, wts)
+    assert launch.kernels == 1
+    for _ in range(3):
+        out.zero_()
+        launch(stream())
     torch.cuda.synchronize()
     ref = torch.zeros_like(out)
     emulator.emu_prompt(dict(x=x, prompt=prm, lin_w=lw, lin_b=lb, out=ref))
