@@ -86,6 +86,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) { }
 }
+// try_wait with a suspend-time hint: the thread is parked by the hardware until the phase completes or the hint (in ns) expires, so a
+// waiting warp retries rarely instead of spinning through issue slots that its scheduler's other warps could use
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+  } while (!ok);
+}
 // for producer / issuer warps that wait most of the time: back off so the spin does not take issue slots from the
 // compute warps sharing the scheduler
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {

@@ -326,16 +326,11 @@ static bool c3_plan(const PirGemm* d, C3Plan* p) {
 
 template <class T, int MT, int NKB, int KSL>
 static int c3_launch(const C3Plan& p, const CUtensorMap& tmA, const CUtensorMap& tmW, cudaStream_t stream) {
-  static bool set[16] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 16 || !set[dev]) {
-    if (cudaFuncSetAttribute(conv3x3_kernel<T, MT, NKB, KSL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
-      return pir_fail(PIR_ERR_CUDA, "pir_gemm (3x3): cannot raise dynamic shared memory limit");
-    if (dev >= 0 && dev < 16) set[dev] = true;
-  }
+  if (!pir_smem_attr_once(reinterpret_cast<const void*>(conv3x3_kernel<T, MT, NKB, KSL>), (int)(227 * 1024 - 1024), "pir_gemm (3x3)")) return PIR_ERR_CUDA;
   static int num_sms = 0;
   if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }

@@ -337,13 +337,9 @@ static int launch_dwconv(const PirDwConv* d, cudaStream_t stream) {
     const uint32_t box[4] = {32, kDwTW + 2, TH + 2, 1};
     if (int e = pir_make_tmap(&tm, dt, 4, d->in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     const size_t smem = (size_t)2 * 2 * (TH + 2) * (kDwTW + 2) * 64 + 128;
-    static bool set[2][2] = {{false, false}, {false, false}};
     const int bw = d->gate == 2 ? 1 : 0;
-    if (!set[T::kFmt][bw]) {
-      if (bw) cudaFuncSetAttribute(dwconv_gate_kernel<T, TH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      else cudaFuncSetAttribute(dwconv_gate_kernel<T, TH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      set[T::kFmt][bw] = true;
-    }
+    if (!pir_smem_attr_once(bw ? reinterpret_cast<const void*>(dwconv_gate_kernel<T, TH, true>) : reinterpret_cast<const void*>(dwconv_gate_kernel<T, TH, false>),
+                            (int)smem, "pir_dwconv3x3")) return PIR_ERR_CUDA;
     const int chunks = (d->C + 31) / 32;
     dim3 grid((unsigned)workers_for(chunks, 2), (unsigned)chunks, 1);
     if (bw) pir_launch(dwconv_gate_kernel<T, TH, true>, grid, dim3(256), smem, stream, tm, a);
@@ -356,12 +352,11 @@ static int launch_dwconv(const PirDwConv* d, cudaStream_t stream) {
     const size_t smem = (size_t)2 * (TH + 2) * (kDwTW + 2) * cc * 2 + 128;
     const int chunks = (d->C + cc - 1) / cc;
     dim3 grid((unsigned)workers_for(chunks, use48 ? 3 : 2), (unsigned)chunks, 1);
-    static bool set[2][2] = {{false, false}, {false, false}};
     if (use48) {
-      if (!set[T::kFmt][0]) { cudaFuncSetAttribute(dwconv_plain_kernel<T, 6, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set[T::kFmt][0] = true; }
+      if (!pir_smem_attr_once(reinterpret_cast<const void*>(dwconv_plain_kernel<T, 6, TH>), (int)smem, "pir_dwconv3x3")) return PIR_ERR_CUDA;
       pir_launch(dwconv_plain_kernel<T, 6, TH>, grid, dim3(6 * 32), smem, stream, tm, a);
     } else {
-      if (!set[T::kFmt][1]) { cudaFuncSetAttribute(dwconv_plain_kernel<T, 8, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); set[T::kFmt][1] = true; }
+      if (!pir_smem_attr_once(reinterpret_cast<const void*>(dwconv_plain_kernel<T, 8, TH>), (int)smem, "pir_dwconv3x3")) return PIR_ERR_CUDA;
       pir_launch(dwconv_plain_kernel<T, 8, TH>, grid, dim3(8 * 32), smem, stream, tm, a);
     }
   }

@@ -407,12 +407,7 @@ static int launch_pw(const PirGemm* d, cudaStream_t stream) {
       if (int e = pir_make_tmap(&tmR, dt, 3, d->res, dims, rstrides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
     }
   }
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[T::kFmt]) {
-    if (cudaFuncSetAttribute(gemm_pw_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512) != cudaSuccess)
-      return pir_fail(PIR_ERR_CUDA, "pir_gemm: cannot raise dynamic shared memory limit");
-    attr_set[T::kFmt] = true;
-  }
+  if (!pir_smem_attr_once(reinterpret_cast<const void*>(gemm_pw_kernel<T>), (int)(227 * 1024 - 512), "pir_gemm")) return PIR_ERR_CUDA;
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -371,12 +371,7 @@ static int launch_gemm(const PirGemm* d, cudaStream_t stream) {
   }
 
   const size_t smem = (size_t)g.stages * (kATileBytes + (size_t)g.block_n * kBlockK * 2) + 1024;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[T::kFmt]) {
-    if (cudaFuncSetAttribute(gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
-      return pir_fail(PIR_ERR_CUDA, "pir_gemm: cannot raise dynamic shared memory limit");
-    attr_set[T::kFmt] = true;
-  }
+  if (!pir_smem_attr_once(reinterpret_cast<const void*>(gemm_kernel<T>), (int)(220 * 1024), "pir_gemm")) return PIR_ERR_CUDA;
   dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)d->B);
   pir_launch(gemm_kernel<T>, grid, dim3(kGemmThreads), smem, stream, tmA, tmB, g);
   return pir_check_launch("pir_gemm");

@@ -6,6 +6,8 @@
 #include <stdlib.h>
 
 #include <mutex>
+#include <set>
+#include <utility>
 
 static thread_local char g_err[512] = "";
 
@@ -63,6 +65,21 @@ int pir_make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void
                     (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
                     rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
   return PIR_OK;
+}
+
+bool pir_smem_attr_once(const void* kernel, int bytes, const char* what) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { pir_fail(PIR_ERR_CUDA, "%s: no current device", what); return false; }
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({kernel, dev})) return true;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+    pir_fail(PIR_ERR_CUDA, "%s: cannot raise the dynamic shared memory limit to %d bytes", what, bytes);
+    return false;
+  }
+  done.insert({kernel, dev});
+  return true;
 }
 
 bool pir_pdl_enabled() {

@@ -28,6 +28,10 @@ namespace pir { int conv3x3_try(const PirGemm* d, cudaStream_t stream); }
 // anyway, and the early-launch bookkeeping costs a little) -> OFF by default; PIR_PDL=1 turns it on.
 bool pir_pdl_enabled();
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, so a process that uses a
+// second GPU must set it there too.  Thread safe.  Returns false (with the error recorded) when the runtime refuses.
+bool pir_smem_attr_once(const void* kernel, int bytes, const char* what);
+
 template <class... KArgs, class... Args>
 inline cudaError_t pir_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -599,12 +599,8 @@ template <class T, int NT>
 static int launch_fin_fused(const PirMdta* d, cudaStream_t s, const float* ws_gram, const float* ws_norm, float* attn) {
   const int c = d->C / d->heads;
   const size_t smem = fin_smem_bytes(c, NT);
-  static size_t raised = 0;
-  if (smem > 48 * 1024 && smem > raised) {
-    if (cudaFuncSetAttribute(mdta_finalize_fused_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return pir_fail(PIR_ERR_CUDA, "pir_mdta_finalize: cannot raise dynamic shared memory limit");
-    raised = smem;
-  }
+  if (smem > 220 * 1024) return pir_fail(PIR_ERR_UNSUPPORTED, "pir_mdta_finalize: head dim %d needs %zu bytes of shared memory", c, smem);
+  if (!pir_smem_attr_once(reinterpret_cast<const void*>(mdta_finalize_fused_kernel<T, NT>), 220 * 1024, "pir_mdta_finalize")) return PIR_ERR_CUDA;
   // one cluster per (head, image); its CTAs share the split-K reduction and take C / size output rows each
   // (a multiple of 8 = one warp's rows).  Enough CTAs to cover the SMs when B * heads alone does not.
   const int pairs = d->B * d->heads;
@@ -669,12 +665,7 @@ static int launch_gram(const PirMdta* d, cudaStream_t stream) {
   const uint32_t box[3] = {64, (uint32_t)kGramPix, 1};
   CUtensorMap tm;
   if (int e = pir_make_tmap(&tm, dt, 3, d->qkv, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
-  static bool set[2] = {false, false};
-  if (!set[T::kFmt]) {
-    if (cudaFuncSetAttribute(mdta_gram_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
-      return pir_fail(PIR_ERR_CUDA, "pir_mdta_gram: cannot raise dynamic shared memory limit");
-    set[T::kFmt] = true;
-  }
+  if (!pir_smem_attr_once(reinterpret_cast<const void*>(mdta_gram_kernel<T>), (int)(220 * 1024), "pir_mdta_gram")) return PIR_ERR_CUDA;
   dim3 grid((unsigned)(gram_nblocks_m(d->C) * g.nblocks_n), (unsigned)d->splits, (unsigned)d->B);
   pir_launch(mdta_gram_kernel<T>, grid, dim3(kGramThreads), smem, stream, tm, g);
   return pir_check_launch("pir_mdta_gram");

@@ -625,14 +625,9 @@ extern "C" int pir_ocab_bwd(const PirOcabBwd* d, void* stream) {
   a.ws_rel = d->ws + (size_t)nparts * kObKV;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const size_t smem = sizeof(float) * (2 * kOcKeys * kOcRow + 2 * kOcRel * kOcDh + 2 * 64 * kOcDh + 2 * 64 * (kOcKeys + 1) + 4 * 64 * kOcOws);
-  static bool set[2] = {false, false};
   const int fi = d->dtype == PIR_DTYPE_BF16 ? 1 : 0;
-  if (!set[fi]) {
-    cudaError_t e = fi ? cudaFuncSetAttribute(ocab_bwd_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                       : cudaFuncSetAttribute(ocab_bwd_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return pir_fail(PIR_ERR_CUDA, "pir_ocab_bwd: cannot raise dynamic shared memory limit");
-    set[fi] = true;
-  }
+  if (!pir_smem_attr_once(fi ? reinterpret_cast<const void*>(ocab_bwd_kernel<BF16>) : reinterpret_cast<const void*>(ocab_bwd_kernel<FP16>), (int)smem,
+                          "pir_ocab_bwd")) return PIR_ERR_CUDA;
   dim3 grid((unsigned)nwin, (unsigned)d->heads, (unsigned)d->B);
   if (fi) ocab_bwd_kernel<BF16><<<grid, 256, smem, s>>>(a); else ocab_bwd_kernel<FP16><<<grid, 256, smem, s>>>(a);
   if (int e = pir_check_launch("pir_ocab_bwd")) return e;

@@ -349,12 +349,7 @@ static int launch_prompt(const PirPrompt* d, cudaStream_t s) {
       if (smem <= 160 * 1024) break;
     }
     if (ts >= 2) {
-      static bool set[2] = {false, false};
-      if (!set[T::kFmt]) {
-        if (cudaFuncSetAttribute(prompt_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
-          return pir_fail(PIR_ERR_CUDA, "pir_prompt_gen: cannot raise dynamic shared memory limit");
-        set[T::kFmt] = true;
-      }
+      if (!pir_smem_attr_once(reinterpret_cast<const void*>(prompt_fused_kernel<T>), (int)(160 * 1024), "pir_prompt_gen")) return PIR_ERR_CUDA;
       static int num_sms = 0;
       if (!num_sms) {
         int dev = 0;

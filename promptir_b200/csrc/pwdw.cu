@@ -670,12 +670,7 @@ static int plan_pwdw(const PirPwDw* d, FwPlan* p) {
 
 template <class T, class Cfg>
 static int launch_cfg(const FwPlan& p, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t stream) {
-  static bool set = false;
-  if (!set) {
-    if (cudaFuncSetAttribute(pwdw_kernel<T, Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
-      return pir_fail(PIR_ERR_CUDA, "pir_pwdw: cannot raise dynamic shared memory limit");
-    set = true;
-  }
+  if (!pir_smem_attr_once(reinterpret_cast<const void*>(pwdw_kernel<T, Cfg>), (int)(227 * 1024 - 1024), "pir_pwdw")) return PIR_ERR_CUDA;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;

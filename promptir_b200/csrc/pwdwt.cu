@@ -569,16 +569,11 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // ---------------------------------------------------------------------------------------------------
 template <class T, int NKB, int KBB, bool GATE, bool GATE32, int PITCH>
 static int tw_launch(const TwArgs& g, uint32_t smem, const CUtensorMap& tmA, const CUtensorMap& tmW, cudaStream_t stream) {
-  static bool set[16] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 16 || !set[dev]) {
-    if (cudaFuncSetAttribute(pwdwt_kernel<T, NKB, KBB, GATE, GATE32, PITCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024) != cudaSuccess)
-      return pir_fail(PIR_ERR_CUDA, "pir_pwdw: cannot raise dynamic shared memory limit");
-    if (dev >= 0 && dev < 16) set[dev] = true;
-  }
+  if (!pir_smem_attr_once(reinterpret_cast<const void*>(pwdwt_kernel<T, NKB, KBB, GATE, GATE32, PITCH>), (int)(227 * 1024 - 1024), "pir_pwdw")) return PIR_ERR_CUDA;
   static int num_sms = 0;
   if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }

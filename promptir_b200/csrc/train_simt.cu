@@ -946,12 +946,7 @@ static int launch_dw_wgrad(const PirDwWgrad* d, cudaStream_t s) {
     if (int e = pir_make_tmap(&tmD, dt, 4, d->dy, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
   }
   const size_t smem = (size_t)2 * ((TH + 2) * 34 + TH * 32) * 128 + 128;
-  static bool set[2] = {false, false};
-  if (!set[T::kFmt]) {
-    if (cudaFuncSetAttribute(dw_wgrad_kernel<T, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return pir_fail(PIR_ERR_CUDA, "pir_dw_wgrad: cannot raise dynamic shared memory limit");
-    set[T::kFmt] = true;
-  }
+  if (!pir_smem_attr_once(reinterpret_cast<const void*>(dw_wgrad_kernel<T, TH>), (int)((int)smem), "pir_dw_wgrad")) return PIR_ERR_CUDA;
   dim3 grid((unsigned)workers, (unsigned)chunks);
   dw_wgrad_kernel<T, TH><<<grid, 256, smem, s>>>(tmX, tmD, a);
   return pir_check_launch("pir_dw_wgrad");

@@ -435,12 +435,7 @@ static int launch_wgrad(const PirWgrad* d, cudaStream_t stream) {
   };
   if (int e = make(&tmA, d->a, d->M, d->a_pitch, d->a_bstride)) return e;
   if (int e = make(&tmB, d->b, d->N, d->b_pitch, d->b_bstride)) return e;
-  static bool set[2] = {false, false};
-  if (!set[T::kFmt]) {
-    if (cudaFuncSetAttribute(wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
-      return pir_fail(PIR_ERR_CUDA, "pir_wgrad: cannot raise dynamic shared memory limit");
-    set[T::kFmt] = true;
-  }
+  if (!pir_smem_attr_once(reinterpret_cast<const void*>(wgrad_kernel<T>), (int)(220 * 1024), "pir_wgrad")) return PIR_ERR_CUDA;
   const int P = d->per_image ? d->B * d->splits : d->splits;
   dim3 grid((unsigned)(p.rblocks * p.cblocks), (unsigned)P, (unsigned)d->taps);
   if (p.swap) wgrad_kernel<T><<<grid, kWgThreads, smem, stream>>>(tmB, tmA, g);

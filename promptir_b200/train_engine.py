@@ -536,6 +536,18 @@ class TrainEngine(Engine):
             raise RuntimeError("promptir_b200.TrainEngine needs a CUDA (sm_100a) device; there is no CPU path")
         self.d_out.copy_(d_out)
         self._run("bwd", self.bwd_launches, use_graph)
+        # fp16 storage runs the backward under a static loss scale (65536): an upstream gradient of order 1 overflows the 16-bit range.
+        # One reduction over the flat buffer leaves a device-side flag (no sync here); overflowed() reads it.
+        # (the 16-bit conversions saturate at +-65504, so an overflow shows up as a clipped dL/d(out) rather than as inf)
+        self._found_inf = None
+        if self.grad_scale != 1.0:
+            self._found_inf = (~torch.isfinite(self.grad_flat)).any() | (self.d_out.abs().amax() * self.grad_scale > 65504.0)
+
+    def overflowed(self) -> bool:
+        """True when the last backward produced a non-finite gradient (fp16 loss scale exceeded): skip the optimizer step and lower
+        `module.grad_scale`, as torch.cuda.amp.GradScaler would.  Always False for bf16 (scale 1).  Synchronises."""
+        f = getattr(self, "_found_inf", None)
+        return bool(f.item()) if f is not None else False
 
     def run_bwd_range(self, a: int, b: int, use_graph: bool = True) -> None:
         """Records [a, b) of the backward program (ddp.OverlappedReducer cuts the backward into a few such pieces); d_out is already set."""

@@ -262,3 +262,25 @@ def test_training_extreme_shapes(shape):
     rel = ((fg - fr).norm() / fr.norm()).item()
     print(f"[train extreme] {shape}: loss {loss.item():.5f} vs {ref_loss:.5f}, flat-gradient rel-L2 {rel:.4f}")
     assert abs(loss.item() - ref_loss) <= 2e-2 * abs(ref_loss) + 1e-4 and rel <= (8e-2 if H * W == 64 else 2e-2)
+
+
+def test_fp16_backward_reports_loss_scale_overflow():
+    """fp16 storage runs the backward under a static loss scale of 65536: an upstream gradient of order 1 (sum-reduced loss) leaves
+    the 16-bit range.  The engine says so (TrainEngine.overflowed) instead of silently handing non-finite / clipped gradients to the
+    optimizer; a mean-reduced loss does not trip it, and bf16 (scale 1) never does."""
+    from promptir_b200 import PromptIR
+    from promptir_b200.train_engine import TrainEngine
+    torch.manual_seed(0)
+    m = PromptIR(decoder=True).to("cuda").train()
+    x = torch.rand(1, 3, 32, 32, device="cuda")
+    eng = TrainEngine(m, 1, 32, 32, "cuda", torch.float16)
+    eng.forward(x)
+    eng.backward(torch.full((1, 3, 32, 32), 1.0 / (3 * 32 * 32), device="cuda"))      # d(mean loss)/d(out)
+    assert not eng.overflowed() and bool(torch.isfinite(eng.grad_flat).all())
+    eng.forward(x)
+    eng.backward(torch.full((1, 3, 32, 32), 4.0, device="cuda"))                        # 4 * 65536 does not fit fp16
+    assert eng.overflowed()
+    eng16 = TrainEngine(m, 1, 32, 32, "cuda", torch.bfloat16)
+    eng16.forward(x)
+    eng16.backward(torch.full((1, 3, 32, 32), 4.0, device="cuda"))
+    assert not eng16.overflowed()
