@@ -217,6 +217,12 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t saddr, uint32_t lb
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Warp index through a shuffle from lane 0: the value is the same as threadIdx.x >> 5, but ptxas can now PROVE it warp-uniform, so the
+// role branches of the warp-specialised kernels become uniform branches and addresses derived from it (tensor-memory columns,
+// mbarriers, the global-memory descriptor) stay in uniform registers.  With the plain shift the fused stencil kernel carried 144
+// R2UR moves (two in front of every store, one per tcgen05.ld), 96 registers and spills; with this 3, 87 and none.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

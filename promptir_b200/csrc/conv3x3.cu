@@ -59,7 +59,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_afull[4], bar_aempty[4], bar_wfull, bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_smem;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr uint32_t x_kb_bytes = X_KB, x_bytes = X_BYTES;
   const uint32_t w_tile = (uint32_t)g.slice_n * 128u;            // one (tap, k-block) tile of the weight slice

@@ -66,7 +66,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_slot_full[kPwMaxSlots], bar_slot_empty[kPwMaxSlots];
   __shared__ uint32_t tmem_base_smem;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));

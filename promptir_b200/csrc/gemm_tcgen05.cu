@@ -62,7 +62,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __shared__ __align__(8) uint64_t bar_accum;
   __shared__ uint32_t tmem_base_smem;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SW128 stages need 1024-B alignment
   const uint32_t b_tile_bytes = (uint32_t)g.block_n * kBlockK * 2;

@@ -42,7 +42,7 @@ mdta_gram_kernel(const __grid_constant__ CUtensorMap tmQKV, const GramArgs g) {
   __shared__ uint32_t tmem_base_smem;
   __shared__ float red[4][6][64];
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const int mb = blockIdx.x / g.nblocks_n;
   const int nb = blockIdx.x % g.nblocks_n;
@@ -294,7 +294,7 @@ mdta_softmax_kernel(const float* __restrict__ ws_gram, const float* __restrict__
                     float* __restrict__ attn, int C, int heads, int splits) {
   pdl_launch_dependents();
   pdl_wait();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;         // global q channel
   const int b = blockIdx.y;
   if (r >= C) return;

@@ -265,7 +265,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __shared__ __align__(8) uint64_t bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_smem;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -481,7 +481,10 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       } else {
         layernorm_tile(x0, y0, it);
       }
-      const bool interior = x0 >= 1 && y0 >= 1 && x0 + TW + 1 <= g.W && y0 + TH + 1 <= g.H;
+      // Border handling is decided per (warp, sub-unit), not per tile: a warp's column patch needs its six input columns inside the
+      // image, a sub-unit its six input rows.  On a 256 x 256 image 20 % of the tiles touch the border but only 6 % of the
+      // (warp, sub-unit) pairs do, and the sub-units of the last tile row that lie wholly below the image are skipped.
+      const bool cols_ok = x0 - 1 + 4 * s >= 0 && x0 + 4 * s + 4 < g.W;
       // validity of this thread's six input columns (halo'd columns 4 s .. 4 s + 5) and its four output columns
       uint32_t col_in = 0;
 #pragma unroll
@@ -503,10 +506,8 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         w2[0] = tw_bcast_hi(tb4.x); w2[1] = tw_bcast_lo(tb4.y); w2[2] = tw_bcast_hi(tb4.y); w2[3] = tw_bcast_lo(tb4.z);
         w2[4] = tw_bcast_hi(tb4.z); w2[5] = tw_bcast_lo(tb4.w); w2[6] = tw_bcast_hi(tb4.w); w2[7] = tw_bcast_lo(tc.x);
         w2[8] = tw_bcast_hi(tc.x);
-        const uint32_t seed1 = interior ? tw_bcast_lo(tc.y) : tw_bcast_lo(tc.z);
-        const uint32_t seed2 = interior ? tw_bcast_hi(tc.y) : tw_bcast_hi(tc.z);
         const float2 tv = svt[ch];
-        const bool add_t = !interior && g.vec_t != nullptr;
+        const bool add_t = g.vec_t != nullptr;
 
         // running output pointer(s) of this thread: (first output row of the sub-unit, first output column, channel)
         unsigned short* orow = out_img + ((size_t)y0 * g.W + xo) * g.out_pitch + ch;
@@ -535,23 +536,29 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t tcol = t_lane + tb * 256u;
           const int yo = y0 + third * kTwRowsPerThird;            // first output row of the sub-unit
-          if (GATE) {
+          const bool interior = cols_ok && yo >= 1 && yo + 4 < g.H;  // all 6 x 6 inputs (hence all 4 x 4 outputs) inside the image
+          // interior: the conv of the constant t is the constant t * sum(taps) and rides on the seed; border: t is added per in-image pixel
+          const uint32_t seed1 = interior ? tw_bcast_lo(tc.y) : tw_bcast_lo(tc.z);
+          const uint32_t seed2 = interior ? tw_bcast_hi(tc.y) : tw_bcast_hi(tc.z);
+          if (yo >= g.H) {
+            // nothing to store (last tile row of an image whose height is not a multiple of the tile): release the accumulators
+          } else if (GATE) {
             if (interior) tw_subunit<T, GATE32, false, PITCH>(tcol, w1, w2, seed1, seed2, tv, 0u, yo, xo, g.H, g.W, orow, pitch, row_stride);
             else tw_subunit<T, GATE32, true, PITCH>(tcol, w1, w2, seed1, seed2, add_t ? tv : make_float2(0.f, 0.f), col_in, yo, xo, g.H, g.W, orow, pitch, row_stride);
-            orow += 4 * row_stride;
           } else {
             // channels past the end of the tensor (last block) are skipped per warp; a partially valid warp masks its stores by
             // pretending the row is outside the image (H = 0 on the border path)
             if (any_a) {
               if (interior && all_a) tw_plain<T, false>(tcol, w1, seed1, 0.f, 0u, yo, xo, g.H, g.W, orow, pitch1, row_stride1);
-              else tw_plain<T, true>(tcol, w1, seed1, add_t ? tv.x : 0.f, interior ? 0x3fu : col_in, yo, xo, va ? g.H : 0, g.W, orow, pitch1, row_stride1);
+              else tw_plain<T, true>(tcol, w1, seed1, (add_t && !interior) ? tv.x : 0.f, interior ? 0x3fu : col_in, yo, xo, va ? g.H : 0, g.W, orow, pitch1, row_stride1);
             }
             if (any_b) {
               if (interior && all_b) tw_plain<T, false>(tcol + 128u, w2, seed2, 0.f, 0u, yo, xo, g.H, g.W, orow2, pitch2, row_stride2);
-              else tw_plain<T, true>(tcol + 128u, w2, seed2, add_t ? tv.y : 0.f, interior ? 0x3fu : col_in, yo, xo, vb ? g.H : 0, g.W, orow2, pitch2, row_stride2);
+              else tw_plain<T, true>(tcol + 128u, w2, seed2, (add_t && !interior) ? tv.y : 0.f, interior ? 0x3fu : col_in, yo, xo, vb ? g.H : 0, g.W, orow2, pitch2, row_stride2);
             }
-            orow += 4 * row_stride1; orow2 += 4 * row_stride2;
           }
+          if (GATE) orow += 4 * row_stride;
+          else { orow += 4 * row_stride1; orow2 += 4 * row_stride2; }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[tb]));

@@ -43,7 +43,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CU
   __shared__ uint32_t tmem_base_smem;
   __shared__ float red[4][4][64];
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
   const int rb = blockIdx.x / g.cblocks;
   const int cb = blockIdx.x % g.cblocks;
