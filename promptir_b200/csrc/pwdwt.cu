@@ -34,6 +34,9 @@ struct TwArgs {
   int n_rows;              // pre-conv channels = weight rows (gate: 2 hp; plain: N)
   int n_cb;                // channel blocks per item: gate hp / 128 (x1 | x2 of 128 gated channels), plain ceil(N / 256) (two 128-channel halves)
   int split;               // plain: channels >= split go to out2 (channel - split); N when there is one output tensor
+  int n_main;              // plain: channels handled in 256-channel blocks (x 3 sub-units); gate: unused
+  int n_rep;               // plain: the last n_rep <= 32 channels, replicated in all four lane quarters (one whole-tile unit per item)
+  int w_rows_main;         // resident weight rows of the block part (the replicated 4 x 32 rows follow)
   int ln_mode;
   int tiles_x, tiles_y, n_items;
   uint32_t mg_per_img, mg_tiles_x;
@@ -180,7 +183,7 @@ __device__ __forceinline__ void tw_subunit(uint32_t tcol, const uint32_t (&w1)[9
 // depthwise conv, stored as 16-bit.  Same structure as tw_subunit.
 template <class T, bool BORDER>
 __device__ __forceinline__ void tw_plain(uint32_t tcol, const uint32_t (&w)[9], uint32_t seed, float tv, uint32_t col_in, int yo, int xo,
-                                         int H, int W, unsigned short* orow, int pitch, size_t row_stride) {
+                                         int H, int W, unsigned short* orow, int pitch, size_t row_stride, bool st_ok = true) {
   constexpr int SW = kTwSW;
   uint32_t a[3][2];
   uint32_t r[8];
@@ -220,10 +223,12 @@ __device__ __forceinline__ void tw_plain(uint32_t tcol, const uint32_t (&w)[9], 
         g0 = pack2<T>(fa.x, fa.y); g1 = pack2<T>(fb.x, fb.y);
       }
       if (!BORDER) {
-        orow[0] = (unsigned short)(g0 & 0xffffu);
-        orow[pitch] = (unsigned short)(g0 >> 16);
-        orow[2 * pitch] = (unsigned short)(g1 & 0xffffu);
-        orow[3 * pitch] = (unsigned short)(g1 >> 16);
+        if (st_ok) {                                          // lanes without a channel (replicated unit with fewer than 32 channels)
+          orow[0] = (unsigned short)(g0 & 0xffffu);
+          orow[pitch] = (unsigned short)(g0 >> 16);
+          orow[2 * pitch] = (unsigned short)(g1 & 0xffffu);
+          orow[3 * pitch] = (unsigned short)(g1 >> 16);
+        }
       } else if (yo + ro < H) {
         if (xo + 0 < W) orow[0] = (unsigned short)(g0 & 0xffffu);
         if (xo + 1 < W) orow[pitch] = (unsigned short)(g0 >> 16);
@@ -248,7 +253,8 @@ __device__ __forceinline__ uint64_t tw_sdesc(uint32_t sbo_bytes, uint32_t layout
 // next item's tile is loaded and LayerNormed while the current one is multiplied).
 template <class T, int NKB, int KBB, bool GATE, bool GATE32, int PITCH>
 __global__ void __launch_bounds__(kTwThreads, 1)
-pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const TwArgs g) {
+pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWr,
+             const TwArgs g) {
   constexpr int TW = kTwTW, TH = kTwTH, SW = kTwSW, NPIX = kTwNPIX;
   constexpr int NA = 2;
   constexpr int KCH = KBB / 2;                                 // channels per k-block
@@ -256,7 +262,8 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr uint32_t X_BYTES = NKB * A_KB;
   constexpr uint32_t SW_LAYOUT = KBB == 128 ? 2u : 4u;
   constexpr uint32_t SBO = 8 * KBB;                            // 8-row swizzle atom
-  const int w_rows = GATE ? 2 * g.hp : g.n_cb * 256;           // resident weight rows (plain: padded to whole blocks, TMA zero fill)
+  const int w_rows_main = GATE ? 2 * g.hp : g.w_rows_main;     // resident weight rows (plain: padded to whole 128-row slabs, TMA zero fill)
+  const int w_rows = w_rows_main + ((!GATE && g.n_rep) ? 128 : 0);   // + the replicated slab: 4 x (the last n_rep channels, zero padded to 32 rows)
   const uint32_t w_kb_bytes = (uint32_t)w_rows * KBB;          // one k-block of the resident weights
 
   extern __shared__ uint8_t smem_raw[];
@@ -273,7 +280,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   float2* svt = reinterpret_cast<float2*>(base_ptr + g.off_vt);          // [hp] (t1, t2)
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmWr);
     for (int i = 0; i < NA; ++i) {
       mbar_init(smem_u32(&bar_afull[i]), 1); mbar_init(smem_u32(&bar_aready[i]), kTwCompute / 32); mbar_init(smem_u32(&bar_aempty[i]), 1);
     }
@@ -290,9 +297,13 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int n_pre = g.n_rows;
     // packed gate: 0.5 p (1 + tanh(.)) q = (p tanh(.) + p) (0.5 q); the 0.5 rides on the x2 branch's taps and bias (exact, a power of two)
     const float qs = (GATE && !GATE32) ? 0.5f : 1.0f;
-    for (int i = threadIdx.x; i < g.n_cb * 128; i += kTwThreads) {
-      const int c1 = GATE ? i : (i >> 7) * 256 + (i & 127), c2 = GATE ? g.hp + i : c1 + 128;
-      const bool v1 = c1 < n_pre, v2 = c2 < n_pre;
+    const int n_slots = g.n_cb * 128 + ((!GATE && g.n_rep) ? 32 : 0);
+    for (int i = threadIdx.x; i < n_slots; i += kTwThreads) {
+      // plain: slots past the blocks belong to the replicated unit (one channel per lane, no second accumulator)
+      const bool rslot = !GATE && i >= g.n_cb * 128;
+      const int c1 = GATE ? i : rslot ? g.n_main + (i - g.n_cb * 128) : (i >> 7) * 256 + (i & 127), c2 = GATE ? g.hp + i : c1 + 128;
+      const bool v1 = GATE ? true : rslot ? (i - g.n_cb * 128) < g.n_rep : c1 < g.n_main;
+      const bool v2 = GATE ? true : (!rslot && c2 < g.n_main);
       float ws1 = 0.f, ws2 = 0.f;
       for (int tap = 0; tap < 9; ++tap) {
         const unsigned short a = v1 ? src[(size_t)tap * n_pre + c1] : (unsigned short)0;
@@ -328,9 +339,13 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (elect_one()) {                               // the whole weight matrix, once
       const uint32_t full = smem_u32(&bar_wfull);
       mbar_expect_tx(full, (uint32_t)NKB * w_kb_bytes);
-      for (int kb = 0; kb < NKB; ++kb)
-        for (int r0 = 0; r0 < w_rows; r0 += 128)
+      for (int kb = 0; kb < NKB; ++kb) {
+        for (int r0 = 0; r0 < w_rows_main; r0 += 128)
           tma_load_2d(base + g.off_w + (uint32_t)kb * w_kb_bytes + (uint32_t)r0 * KBB, &tmW, full, kb * KCH, r0);
+        if (w_rows > w_rows_main)                      // the same 32-row box four times: rows past the tensor are zero filled
+          for (int j = 0; j < 4; ++j)
+            tma_load_2d(base + g.off_w + (uint32_t)kb * w_kb_bytes + (uint32_t)(w_rows_main + 32 * j) * KBB, &tmWr, full, kb * KCH, g.n_main);
+      }
     }
     __syncwarp();
     uint32_t it = 0;
@@ -374,7 +389,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const uint64_t xd = desc_hi | (uint64_t)(x_lo & 0x3fffu);
               const uint64_t w1d = desc_hi | (uint64_t)((w_lo + (((uint32_t)row1 * KBB) >> 4)) & 0x3fffu);
               const uint64_t w2d = desc_hi | (uint64_t)((w_lo + (((uint32_t)row2 * KBB) >> 4)) & 0x3fffu);
-              const bool second = row2 < g.n_rows;                 // plain: the last block may have no second half
+              const bool second = GATE || row2 < g.n_main;         // plain: the last block may have no second half
               for (int k = 0; k < ksteps; ++k) {
                 const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
                 umma_f16(d1, w1d + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idesc, acc);
@@ -382,10 +397,35 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
             umma_commit(smem_u32(&bar_tfull[tb]));
-            if (third == 2 && cb == g.n_cb - 1) umma_commit(smem_u32(&bar_aempty[ab]));
+            if (third == 2 && cb == g.n_cb - 1 && (GATE || g.n_rep == 0)) umma_commit(smem_u32(&bar_aempty[ab]));
           }
           __syncwarp();
         }
+      }
+      if (!GATE && g.n_rep) {
+        // replicated unit: the last <= 32 channels in all four lane quarters against the WHOLE halo'd tile (N = 256 columns of one
+        // buffer); lane quarter q then serves sub-unit q, so the odd channels cost one accumulator pass instead of three
+        const uint32_t tb = tq & 1u;
+        tw_wait_backoff(smem_u32(&bar_tempty[tb]), ((tq >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t idesc_r = make_idesc_f16(T::kFmt, 128, 256, 0, 0);
+          const uint32_t d1 = tmem_base + tb * 256u;
+#pragma unroll
+          for (int kb = 0; kb < NKB; ++kb) {
+            const int rem = g.C - kb * KCH;
+            const int ksteps = rem >= KCH ? KCH / 16 : (rem + 15) >> 4;
+            const uint32_t x_lo = (base + ab * X_BYTES + (uint32_t)kb * A_KB) >> 4;
+            const uint32_t w_lo = (base + g.off_w + (uint32_t)kb * w_kb_bytes + (uint32_t)w_rows_main * KBB) >> 4;
+            const uint64_t xd = desc_hi | (uint64_t)(x_lo & 0x3fffu);
+            const uint64_t wd = desc_hi | (uint64_t)(w_lo & 0x3fffu);
+            for (int k = 0; k < ksteps; ++k) umma_f16(d1, wd + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), idesc_r, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&bar_tfull[tb]));
+          umma_commit(smem_u32(&bar_aempty[ab]));
+        }
+        __syncwarp();
+        ++tq;
       }
     }
   } else {
@@ -518,7 +558,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (!GATE) {
           // plain: two independent channels per thread, each routed to `out` (below split) or `out2`
           const int ca = cb * 256 + q * 32 + lane, cbn = ca + 128;
-          va = ca < g.n_rows; vb = cbn < g.n_rows;
+          va = ca < g.n_main; vb = cbn < g.n_main;
           unsigned short* img2 = reinterpret_cast<unsigned short*>(g.out2) + (size_t)b * g.out2_bstride;
           const size_t pix = (size_t)y0 * g.W + xo;
           orow = ca < g.split ? out_img + pix * g.out_pitch + ca : img2 + pix * g.out2_pitch + (ca - g.split);
@@ -564,6 +604,37 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[tb]));
         }
       }
+      if (!GATE && g.n_rep) {
+        // replicated unit: warp (q, s) runs sub-unit q of the last n_rep channels (lane = channel), quarter 3 has nothing to do
+        const uint32_t tb = tq & 1u;
+        mbar_wait(smem_u32(&bar_tfull[tb]), (tq >> 1) & 1u);
+        tc_fence_after();
+        const int yo = y0 + q * kTwRowsPerThird;
+        if (q < 3 && yo < g.H) {
+          const int slot = g.n_cb * 128 + lane;
+          const uint4 ta = stab[slot * 3], tb4 = stab[slot * 3 + 1], tc = stab[slot * 3 + 2];
+          uint32_t w1[9];
+          w1[0] = tw_bcast_lo(ta.x); w1[1] = tw_bcast_hi(ta.x); w1[2] = tw_bcast_lo(ta.y); w1[3] = tw_bcast_hi(ta.y);
+          w1[4] = tw_bcast_lo(ta.z); w1[5] = tw_bcast_hi(ta.z); w1[6] = tw_bcast_lo(ta.w); w1[7] = tw_bcast_hi(ta.w);
+          w1[8] = tw_bcast_lo(tb4.x);
+          const int c = g.n_main + lane;
+          const bool v = lane < g.n_rep;
+          const bool interior = cols_ok && yo >= 1 && yo + 4 < g.H;
+          const uint32_t seed = interior ? tw_bcast_lo(tc.y) : tw_bcast_lo(tc.z);
+          const float tvx = svt[slot].x;
+          unsigned short* img2 = reinterpret_cast<unsigned short*>(g.out2) + (size_t)b * g.out2_bstride;
+          const size_t pix = (size_t)yo * g.W + xo;
+          const int pr = c < g.split ? pitch : (int)g.out2_pitch;
+          unsigned short* op = c < g.split ? out_img + pix * g.out_pitch + c : img2 + pix * g.out2_pitch + (c - g.split);
+          const uint32_t tcol = t_lane + tb * 256u + (uint32_t)(q * 4 * SW);
+          if (interior) tw_plain<T, false>(tcol, w1, seed, 0.f, 0u, yo, xo, g.H, g.W, op, pr, (size_t)g.W * pr, v);
+          else tw_plain<T, true>(tcol, w1, seed, g.vec_t != nullptr ? tvx : 0.f, col_in, yo, xo, v ? g.H : 0, g.W, op, pr, (size_t)g.W * pr);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[tb]));
+        ++tq;
+      }
       if (item + (int)gridDim.x < g.n_items) item_geo(item + gridDim.x, b, x0, y0);
     }
   }
@@ -575,7 +646,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 // ---------------------------------------------------------------------------------------------------
 template <class T, int NKB, int KBB, bool GATE, bool GATE32, int PITCH>
-static int tw_launch(const TwArgs& g, uint32_t smem, const CUtensorMap& tmA, const CUtensorMap& tmW, cudaStream_t stream) {
+static int tw_launch(const TwArgs& g, uint32_t smem, const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmWr, cudaStream_t stream) {
   if (!pir_smem_attr_once(reinterpret_cast<const void*>(pwdwt_kernel<T, NKB, KBB, GATE, GATE32, PITCH>), (int)(227 * 1024 - 1024), "pir_pwdw")) return PIR_ERR_CUDA;
   static int num_sms = 0;
   if (!num_sms) {
@@ -585,7 +656,7 @@ static int tw_launch(const TwArgs& g, uint32_t smem, const CUtensorMap& tmA, con
     if (num_sms <= 0) num_sms = 148;
   }
   const int grid = g.n_items < num_sms ? g.n_items : num_sms;
-  pwdwt_kernel<T, NKB, KBB, GATE, GATE32, PITCH><<<dim3(grid), dim3(kTwThreads), smem, stream>>>(tmA, tmW, g);
+  pwdwt_kernel<T, NKB, KBB, GATE, GATE32, PITCH><<<dim3(grid), dim3(kTwThreads), smem, stream>>>(tmA, tmW, tmWr, g);
   return pir_check_launch("pir_pwdw (channel-major)");
 }
 
@@ -597,23 +668,36 @@ static bool tw_shape(int C, int* nkb, int* kbb) {
 }
 
 // C <= 64 or C == 96; gate: hidden a multiple of 128; the plan (two x tiles + ALL weights + tables) fits shared memory
+// plain form: the last N % 128 channels, when there are at most 32 of them (qkv: 144 = 128 + 16, 288 = 256 + 32), do not get a
+// 128-row block of their own (three of four lane quarters would idle through three sub-units) but ONE replicated unit per item
+static void tw_plain_split(int N, int* n_main, int* n_rep) {
+  const int r = N % 128;
+  *n_rep = (r > 0 && r <= 32 && N > 128) ? r : 0;
+  *n_main = N - *n_rep;
+}
+
 static uint32_t tw_smem(const PirPwDw* d, int nkb, int kbb, TwArgs* g) {
-  const int n_cb = d->gate ? d->N / 128 : (d->N + 255) / 256;
-  const int w_rows = d->gate ? 2 * d->N : n_cb * 256;
+  int n_main = d->N, n_rep = 0;
+  if (!d->gate) tw_plain_split(d->N, &n_main, &n_rep);
+  const int n_cb = d->gate ? d->N / 128 : (n_main + 255) / 256;
+  const int w_rows_main = d->gate ? 2 * d->N : (n_main + 127) / 128 * 128;
+  const int w_rows = w_rows_main + (n_rep ? 128 : 0);
+  const uint32_t slots = (uint32_t)n_cb * 128u + (n_rep ? 32u : 0u);
+  if (g) { g->n_main = n_main; g->n_rep = n_rep; g->n_cb = n_cb; g->w_rows_main = w_rows_main; }
   uint32_t off = 2u * nkb * 256u * kbb;
   if (g) g->off_w = off;
   off += (uint32_t)nkb * w_rows * kbb;
   if (g) g->off_tab = off;
-  off += (uint32_t)n_cb * 128u * 48u;
+  off += slots * 48u;
   if (g) g->off_vt = off;
-  off += (uint32_t)n_cb * 128u * 8u;
+  off += slots * 8u;
   return off + 1024u;
 }
 
 bool pwdwt_supported(const PirPwDw* d) {
   // bit 0: gate, bit 1: plain.  Default: gate only -- measured on B200 (B = 16, 256 x 256): the plain form leaves lane quarters idle
   // in the last channel block (288 = 256 + 32, 144 = 128 + 16 channels) and runs at 495 / 351 us against 398 / 233 us of pwdw.cu
-  static const int mode = [] { const char* e = getenv("PIR_PWDW_T"); return e ? atoi(e) : 1; }();
+  static const int mode = [] { const char* e = getenv("PIR_PWDW_T"); return e ? atoi(e) : 3; }();
   if (!(mode & (d->gate ? 1 : 2))) return false;
   int nkb, kbb;
   if (!tw_shape(d->C, &nkb, &kbb)) return false;
@@ -627,7 +711,6 @@ static int tw_run(const PirPwDw* d, cudaStream_t stream) {
   const bool gate = d->gate != 0;
   g.B = d->B; g.H = d->H; g.W = d->W; g.C = d->C;
   g.hp = gate ? d->N : 0; g.n_rows = gate ? 2 * d->N : d->N;
-  g.n_cb = gate ? d->N / 128 : (d->N + 255) / 256;
   g.ln_mode = d->ln_mode;
   g.tiles_x = (d->W + kTwTW - 1) / kTwTW; g.tiles_y = (d->H + kTwTH - 1) / kTwTH;
   g.n_items = g.tiles_x * g.tiles_y * d->B;
@@ -663,9 +746,17 @@ static int tw_run(const PirPwDw* d, cudaStream_t stream) {
     const uint32_t box[2] = {(uint32_t)kch, 128};
     if (int e = pir_make_tmap(&tmW, dt, 2, d->w, dims, strides, box, sw)) return e;
   }
+  CUtensorMap tmWr = tmW;
+  if (g.n_rep) {                                                        // 32-row boxes for the replicated slab
+    const uint64_t kpad = (uint64_t)((d->C + 63) / 64) * 64;
+    const uint64_t dims[2] = {kpad, (uint64_t)g.n_rows};
+    const uint64_t strides[1] = {kpad * 2};
+    const uint32_t box[2] = {(uint32_t)kch, 32};
+    if (int e = pir_make_tmap(&tmWr, dt, 2, d->w, dims, strides, box, sw)) return e;
+  }
   if (!gate) {
-    if (nkb == 1) return tw_launch<T, 1, 128, false, false, 0>(g, smem, tmA, tmW, stream);
-    return tw_launch<T, 3, 64, false, false, 0>(g, smem, tmA, tmW, stream);
+    if (nkb == 1) return tw_launch<T, 1, 128, false, false, 0>(g, smem, tmA, tmW, tmWr, stream);
+    return tw_launch<T, 3, 64, false, false, 0>(g, smem, tmA, tmW, tmWr, stream);
   }
   // fp32 erf-GELU gate for fp16 storage only on request (PIR_PWDW_GATE32=1, A/B): the packed fp16 gate measured 8.3e-4 against
   // 9.0e-4 max-abs on the cfg2 forward and is 0.75 ms per step faster
@@ -673,11 +764,11 @@ static int tw_run(const PirPwDw* d, cudaStream_t stream) {
   const bool g32 = T::kFmt == 0 && gate32;
   // the networks write a dense gated tensor (pitch == hidden): those two pitches are compiled in
   if (nkb == 1) {
-    if (d->out_pitch == 128) return g32 ? tw_launch<T, 1, 128, true, true, 128>(g, smem, tmA, tmW, stream) : tw_launch<T, 1, 128, true, false, 128>(g, smem, tmA, tmW, stream);
-    return g32 ? tw_launch<T, 1, 128, true, true, 0>(g, smem, tmA, tmW, stream) : tw_launch<T, 1, 128, true, false, 0>(g, smem, tmA, tmW, stream);
+    if (d->out_pitch == 128) return g32 ? tw_launch<T, 1, 128, true, true, 128>(g, smem, tmA, tmW, tmWr, stream) : tw_launch<T, 1, 128, true, false, 128>(g, smem, tmA, tmW, tmWr, stream);
+    return g32 ? tw_launch<T, 1, 128, true, true, 0>(g, smem, tmA, tmW, tmWr, stream) : tw_launch<T, 1, 128, true, false, 0>(g, smem, tmA, tmW, tmWr, stream);
   }
-  if (d->out_pitch == 256) return g32 ? tw_launch<T, 3, 64, true, true, 256>(g, smem, tmA, tmW, stream) : tw_launch<T, 3, 64, true, false, 256>(g, smem, tmA, tmW, stream);
-  return g32 ? tw_launch<T, 3, 64, true, true, 0>(g, smem, tmA, tmW, stream) : tw_launch<T, 3, 64, true, false, 0>(g, smem, tmA, tmW, stream);
+  if (d->out_pitch == 256) return g32 ? tw_launch<T, 3, 64, true, true, 256>(g, smem, tmA, tmW, tmWr, stream) : tw_launch<T, 3, 64, true, false, 256>(g, smem, tmA, tmW, tmWr, stream);
+  return g32 ? tw_launch<T, 3, 64, true, true, 0>(g, smem, tmA, tmW, tmWr, stream) : tw_launch<T, 3, 64, true, false, 0>(g, smem, tmA, tmW, tmWr, stream);
 }
 
 int pwdwt_run(const PirPwDw* d, cudaStream_t stream) {
