@@ -22,8 +22,9 @@
 
 namespace pir {
 
-constexpr int kTwThreads = 576;
-constexpr int kTwCompute = 512;
+constexpr int kTwThreads = 704;
+constexpr int kTwCompute = 512;                                            // stencil warps 2-17
+constexpr int kTwLn = 128;                                                 // LayerNorm warps 18-21
 constexpr int kTwTW = 16, kTwTH = 12, kTwSW = 18, kTwNPIX = 14 * 18;     // output tile, halo'd width, halo'd pixels
 constexpr int kTwN = 112;                                                  // UMMA N of a sub-unit (6 x 18 = 108 columns used)
 constexpr int kTwRowsPerThird = 4;
@@ -82,8 +83,25 @@ __device__ __forceinline__ uint32_t tw_gate2(uint32_t p, uint32_t q) {
   return tw_max2(tw_min2(tw_mul2(tw_fma2(p, th, p), q), kMax), kMin);
 }
 __device__ __forceinline__ float2 tw_h2f2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+#ifndef PIR_TW_PARK
+#define PIR_TW_PARK 1
+#endif
+// Waits of the producer / issuer / LayerNorm warps (mostly idle) and of the stencil warps on a full accumulator: parked in the
+// mbarrier unit (try_wait with a suspend-time hint) instead of polling, so a waiting warp costs no issue slots and wakes when the
+// phase completes rather than at the next poll.
 __device__ __forceinline__ void tw_wait_backoff(uint32_t bar, uint32_t parity) {
+#if PIR_TW_PARK
+  mbar_wait_parked(bar, parity);
+#else
   while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+#endif
+}
+__device__ __forceinline__ void tw_wait_full(uint32_t bar, uint32_t parity) {
+#if PIR_TW_PARK
+  mbar_wait_parked(bar, parity);
+#else
+  mbar_wait(bar, parity);
+#endif
 }
 // 32 lanes x 8 consecutive fp32 columns
 __device__ __forceinline__ void tw_ld8(uint32_t taddr, uint32_t (&v)[8]) {
@@ -282,7 +300,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmWr);
     for (int i = 0; i < NA; ++i) {
-      mbar_init(smem_u32(&bar_afull[i]), 1); mbar_init(smem_u32(&bar_aready[i]), kTwCompute / 32); mbar_init(smem_u32(&bar_aempty[i]), 1);
+      mbar_init(smem_u32(&bar_afull[i]), 1); mbar_init(smem_u32(&bar_aready[i]), kTwLn / 32); mbar_init(smem_u32(&bar_aempty[i]), 1);
     }
     mbar_init(smem_u32(&bar_wfull), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bar_tfull[i]), 1); mbar_init(smem_u32(&bar_tempty[i]), kTwCompute / 32); }
@@ -353,7 +371,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int b, x0, y0;
       item_geo(item, b, x0, y0);
       const uint32_t ab = it % NA;
-      mbar_wait_sleep(smem_u32(&bar_aempty[ab]), ((it / NA) & 1u) ^ 1u);
+      tw_wait_backoff(smem_u32(&bar_aempty[ab]), ((it / NA) & 1u) ^ 1u);
       if (elect_one()) {
         const uint32_t full = smem_u32(&bar_afull[ab]);
         mbar_expect_tx(full, (uint32_t)NKB * (uint32_t)(NPIX * KBB));
@@ -366,7 +384,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ========================================= MMA issuer ============================================
     const uint64_t desc_hi = tw_sdesc(SBO, SW_LAYOUT);
     const uint32_t idesc = make_idesc_f16(T::kFmt, 128, kTwN, 0, 0);
-    mbar_wait_sleep(smem_u32(&bar_wfull), 0);
+    tw_wait_backoff(smem_u32(&bar_wfull), 0);
     uint32_t it = 0, tq = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
       const uint32_t ab = it % NA;
@@ -428,21 +446,21 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         ++tq;
       }
     }
-  } else {
-    // ============================ LayerNorm in place, then stencil + gate + store from TMEM ============================
-    const int ct = threadIdx.x - 64;                 // 0..511
-    const int q = warp & 3;                          // TMEM lane quarter of this warp
-    const int s = (warp - 2) >> 2;                   // column patch: output columns 4 s .. 4 s + 3
-    constexpr int LNR = (NPIX * 4 + kTwCompute - 1) / kTwCompute;
+  } else if (warp >= 2 + kTwCompute / 32) {
+    // ============================ LayerNorm warps: normalise the halo'd x tile in place ============================
+    // Four warps of their own instead of a phase of the stencil warps: their LDS / fp32-FMA / shuffle stream fills issue slots the
+    // stencil warps (bound by the fp16 FMA pipe) leave empty, and the stencil warps never stop for a tile's LayerNorm.
+    const int ct = threadIdx.x - (64 + kTwCompute);  // 0..127
+    constexpr int LNR = (NPIX * 4 + kTwLn - 1) / kTwLn;
     const float inv_k = 1.0f / (float)g.C;
     auto layernorm_tile = [&](int x0, int y0, uint32_t itn) {
       const uint32_t ab = itn % NA;
       uint8_t* a_tile = base_ptr + (size_t)ab * X_BYTES;
-      mbar_wait(smem_u32(&bar_afull[ab]), (itn / NA) & 1u);
+      tw_wait_backoff(smem_u32(&bar_afull[ab]), (itn / NA) & 1u);     // sleeps between polls: these warps run two tiles ahead and mostly wait
       if (g.ln_mode) {
-#pragma unroll
+#pragma unroll 2
         for (int r = 0; r < LNR; ++r) {
-          const int task = r * kTwCompute + ct;
+          const int task = r * kTwLn + ct;
           const int m = task >> 2, part = task & 3;
           const int my = m / SW;
           const int py = y0 - 1 + my, px = x0 - 1 + (m - my * SW);
@@ -503,24 +521,21 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bar_aready[ab]));
     };
-
-    uint32_t it = 0, tq = 0;
-    int b = 0, x0 = 0, y0 = 0;
-    if ((int)blockIdx.x < g.n_items) {
-      item_geo(blockIdx.x, b, x0, y0);
-      if (NA == 2) layernorm_tile(x0, y0, 0);
-    }
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(4 * s);
+    uint32_t it = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++it) {
-      if (NA == 2) {
-        if (item + (int)gridDim.x < g.n_items) {
-          int nb_, nx0, ny0;
-          item_geo(item + gridDim.x, nb_, nx0, ny0);
-          layernorm_tile(nx0, ny0, it + 1);
-        }
-      } else {
-        layernorm_tile(x0, y0, it);
-      }
+      int b, x0, y0;
+      item_geo(item, b, x0, y0);
+      layernorm_tile(x0, y0, it);
+    }
+  } else {
+    // ============================ stencil + gate + store from TMEM ============================
+    const int q = warp & 3;                          // TMEM lane quarter of this warp
+    const int s = (warp - 2) >> 2;                   // column patch: output columns 4 s .. 4 s + 3
+    uint32_t tq = 0;
+    int b = 0, x0 = 0, y0 = 0;
+    if ((int)blockIdx.x < g.n_items) item_geo(blockIdx.x, b, x0, y0);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(4 * s);
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
       // Border handling is decided per (warp, sub-unit), not per tile: a warp's column patch needs its six input columns inside the
       // image, a sub-unit its six input rows.  On a 256 x 256 image 20 % of the tiles touch the border but only 6 % of the
       // (warp, sub-unit) pairs do, and the sub-units of the last tile row that lie wholly below the image are skipped.
@@ -572,7 +587,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const bool all_a = GATE || __all_sync(0xffffffffu, va), all_b = GATE || __all_sync(0xffffffffu, vb);   // tcgen05.ld is warp-collective: branch per warp only
         for (int third = 0; third < 3; ++third, ++tq) {
           const uint32_t tb = tq & 1u;
-          mbar_wait(smem_u32(&bar_tfull[tb]), (tq >> 1) & 1u);
+          tw_wait_full(smem_u32(&bar_tfull[tb]), (tq >> 1) & 1u);
           tc_fence_after();
           const uint32_t tcol = t_lane + tb * 256u;
           const int yo = y0 + third * kTwRowsPerThird;            // first output row of the sub-unit
@@ -607,7 +622,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (!GATE && g.n_rep) {
         // replicated unit: warp (q, s) runs sub-unit q of the last n_rep channels (lane = channel), quarter 3 has nothing to do
         const uint32_t tb = tq & 1u;
-        mbar_wait(smem_u32(&bar_tfull[tb]), (tq >> 1) & 1u);
+        tw_wait_full(smem_u32(&bar_tfull[tb]), (tq >> 1) & 1u);
         tc_fence_after();
         const int yo = y0 + q * kTwRowsPerThird;
         if (q < 3 && yo < g.H) {
