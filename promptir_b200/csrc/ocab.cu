@@ -505,6 +505,340 @@ ocab_bwd_kernel(const ObArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Backward on warp-level tensor-core MMA (default; the fp32 SIMT kernel above stays selectable with PIR_OCAB_BWD_SIMT=1).
+// One CTA of 4 warps per (window, head); warp w owns queries 16w .. 16w+15 like the forward kernel.
+//   phase A (per warp, accumulators in registers):
+//       S = Qs K^T + bias -> P (18 mma);  dP = dO V^T (18 mma);  dS = P (dP - <P, dP>);  dQs = dS K (18 mma)
+//       P and dS are staged as 16-bit [query][key] tiles; dS carries a power-of-two scale in the fp16 build (its values sit near
+//       the fp16 subnormal range otherwise).  Column / row sums of dS (C_i[kc], R_i[kr]) and the relative-position part of dQs
+//       are SIMT work on the warp's own 16 queries (a query's 144 keys all belong to one warp: no block barrier).
+//   phase B (all warps): dK = dS^T Qs and dV = P^T dO, 9 key tiles each, A operand by ldmatrix.trans from the staged tiles (72 + 72 mma);
+//       d rel_w = Cs^T Qs, d rel_h = Rs^T Qs with the shifted tables Cs[i][r] = C_i[r + y_i - 11]: one (table, 16-row tile) per warp.
+// Workspace layout and the gather / table-reduce kernels are those of the SIMT version; fp32 accumulation, deterministic.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kObPs = 152;                 // 16-bit row stride of the staged P / dS tiles (304 B: ldmatrix rows on distinct banks)
+constexpr int kObCs = 40;                  // 16-bit row stride of the shifted column / row sum tables
+constexpr size_t kObMmaSmem = 2 * (2 * 64 * kOcRowH + 2 * kOcKeys * kOcRowH) + 4 * (2 * kOcRel * kOcDh + 2 * 64 * kOcTs) + 2 * (2 * 64 * kObPs) +
+                              4 * (2 * 64 * kOcOws + 64 * 17) + 2 * (2 * 64 * kObCs);
+
+template <class T>
+__global__ void __launch_bounds__(128)
+ocab_bwd_mma_kernel(const ObArgs a) {
+  typedef unsigned short u16;
+  extern __shared__ __align__(16) uint8_t obm[];
+  u16 (*sQ)[kOcRowH] = reinterpret_cast<u16 (*)[kOcRowH]>(obm);                              // [64] scaled queries
+  u16 (*sdO)[kOcRowH] = sQ + 64;                                                             // [64]
+  u16 (*sK)[kOcRowH] = sdO + 64;                                                             // [144]
+  u16 (*sV)[kOcRowH] = sK + kOcKeys;                                                         // [144]
+  float (*sRel)[kOcRel][kOcDh] = reinterpret_cast<float (*)[kOcRel][kOcDh]>(sV + kOcKeys);   // [2]: rel_w, rel_h
+  float (*sT)[64][kOcTs] = reinterpret_cast<float (*)[64][kOcTs]>(&sRel[2][0][0]);           // [2]: Tw, Th
+  u16 (*sP)[kObPs] = reinterpret_cast<u16 (*)[kObPs]>(&sT[2][0][0]);                         // [64][144]
+  u16 (*sdS)[kObPs] = sP + 64;                                                               // [64][144], scaled
+  float (*sC)[kOcOws] = reinterpret_cast<float (*)[kOcOws]>(sdS + 64);                       // [64][12]
+  float (*sR)[kOcOws] = sC + 64;                                                             // [64][12]
+  float (*sdQ)[17] = reinterpret_cast<float (*)[17]>(sR + 64);                               // [64][16] tensor-core part of dQs
+  u16 (*sCs)[64][kObCs] = reinterpret_cast<u16 (*)[64][kObCs]>(sdQ + 64);                    // [2][64][32]: shifted C / R, scaled
+  constexpr float kS = T::kFmt == 0 ? 256.0f : 1.0f, kInvS = 1.0f / kS;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nw = a.W / kOcWs, nwin = (a.H / kOcWs) * nw;
+  const int wy = blockIdx.x / nw, wx = blockIdx.x % nw;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const unsigned short* base = a.qkv + (size_t)b * a.qbs;
+
+  // ---- gather (as the forward kernel) + the 64 output gradients ----
+  for (int e = tid; e < kOcKeys * 4; e += 128) {
+    const int j = e >> 2, which = (e >> 1) & 1, half = e & 1;
+    const int py = wy * kOcWs - (kOcOws - kOcWs) / 2 + j / kOcOws, px = wx * kOcWs - (kOcOws - kOcWs) / 2 + j % kOcOws;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (py >= 0 && py < a.H && px >= 0 && px < a.W)
+      v = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)py * a.W + px) * a.qpitch + (size_t)(1 + which) * a.inner + h * kOcDh + half * 8));
+    *reinterpret_cast<uint4*>((which ? sV[j] : sK[j]) + half * 8) = v;
+  }
+  {
+    const int i = tid >> 1, half = tid & 1;
+    const size_t qpix = (size_t)(wy * kOcWs + (i >> 3)) * a.W + wx * kOcWs + (i & 7);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + qpix * a.qpitch + h * kOcDh + half * 8));
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+    uint4 o;
+    o.x = pack2<T>(unpack_lo<T>(w4[0]) * 0.25f, unpack_hi<T>(w4[0]) * 0.25f);
+    o.y = pack2<T>(unpack_lo<T>(w4[1]) * 0.25f, unpack_hi<T>(w4[1]) * 0.25f);
+    o.z = pack2<T>(unpack_lo<T>(w4[2]) * 0.25f, unpack_hi<T>(w4[2]) * 0.25f);
+    o.w = pack2<T>(unpack_lo<T>(w4[3]) * 0.25f, unpack_hi<T>(w4[3]) * 0.25f);
+    *reinterpret_cast<uint4*>(sQ[i] + half * 8) = o;
+    *reinterpret_cast<uint4*>(sdO[i] + half * 8) =
+        __ldg(reinterpret_cast<const uint4*>(a.dout + (size_t)b * a.dbs + qpix * a.dpitch + h * kOcDh + half * 8));
+  }
+  for (int e = tid; e < kOcRel * kOcDh; e += 128) {
+    sRel[0][e / kOcDh][e % kOcDh] = __ldg(a.rel_w + e);
+    sRel[1][e / kOcDh][e % kOcDh] = __ldg(a.rel_h + e);
+  }
+  __syncthreads();
+  {
+    const int i = tid >> 1, which = tid & 1;
+    float q[16];
+#pragma unroll
+    for (int d2 = 0; d2 < 8; ++d2) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(&sQ[i][2 * d2]);
+      q[2 * d2] = unpack_lo<T>(w);
+      q[2 * d2 + 1] = unpack_hi<T>(w);
+    }
+#pragma unroll
+    for (int r = 4; r < kOcRel; ++r) {
+      const float* rr = sRel[which][r];
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; d += 2) { t0 = fmaf(q[d], rr[d], t0); t1 = fmaf(q[d + 1], rr[d + 1], t1); }
+      sT[which][i][r] = t0 + t1;
+    }
+  }
+  __syncthreads();
+
+  // =============================== phase A: this warp's 16 queries ===============================
+  const int g = lane >> 2, q4 = lane & 3;
+  const int row0 = warp * 16 + g, row1 = row0 + 8;
+  float c[18][4];
+  {
+    uint32_t af[4];
+    ldsm_x4(af, smem_u32(&sQ[warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]));
+#pragma unroll
+    for (int n = 0; n < 18; ++n) { c[n][0] = c[n][1] = c[n][2] = c[n][3] = 0.f; }
+#pragma unroll
+    for (int n2 = 0; n2 < 9; ++n2) {
+      uint32_t bf[4];
+      ldsm_x4(bf, smem_u32(&sK[n2 * 16 + (lane & 7) + 8 * (lane >> 4)][8 * ((lane >> 3) & 1)]));
+      mma16816<T>(c[2 * n2], af, bf[0], bf[1]);
+      mma16816<T>(c[2 * n2 + 1], af, bf[2], bf[3]);
+    }
+  }
+  {
+    const float* tw0 = sT[0][row0] + (kOcOws - 1 - g);
+    const float* tw1 = sT[0][row1] + (kOcOws - 1 - g);
+    const float* th0 = sT[1][row0] + (kOcOws - 1 - 2 * warp);
+    const float* th1 = sT[1][row1] + (kOcOws - 1 - (2 * warp + 1));
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 18; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int v = (8 * n) % 12 + 2 * q4 + e;
+        const int wrap = v >= 12 ? 1 : 0;
+        const int kc = v - 12 * wrap, kr = (8 * n) / 12 + wrap;
+        c[n][e] += tw0[kc] + th0[kr];
+        c[n][2 + e] += tw1[kc] + th1[kr];
+        m0 = fmaxf(m0, c[n][e]);
+        m1 = fmaxf(m1, c[n][2 + e]);
+      }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+    const float L2E = 1.4426950408889634f;
+#pragma unroll
+    for (int n = 0; n < 18; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        c[n][e] = exp2f((c[n][e] - m0) * L2E); s0 += c[n][e];
+        c[n][2 + e] = exp2f((c[n][2 + e] - m1) * L2E); s1 += c[n][2 + e];
+      }
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float r0 = 1.0f / s0, r1 = 1.0f / s1;
+#pragma unroll
+    for (int n = 0; n < 18; ++n) { c[n][0] *= r0; c[n][1] *= r0; c[n][2] *= r1; c[n][3] *= r1; }
+  }
+  // dP = dO V^T, <P, dP>, dS
+  float dp[18][4];
+  {
+    uint32_t df[4];
+    ldsm_x4(df, smem_u32(&sdO[warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]));
+#pragma unroll
+    for (int n = 0; n < 18; ++n) { dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f; }
+#pragma unroll
+    for (int n2 = 0; n2 < 9; ++n2) {
+      uint32_t bf[4];
+      ldsm_x4(bf, smem_u32(&sV[n2 * 16 + (lane & 7) + 8 * (lane >> 4)][8 * ((lane >> 3) & 1)]));
+      mma16816<T>(dp[2 * n2], df, bf[0], bf[1]);
+      mma16816<T>(dp[2 * n2 + 1], df, bf[2], bf[3]);
+    }
+    float rd0 = 0.f, rd1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 18; ++n) {
+      rd0 = fmaf(c[n][0], dp[n][0], fmaf(c[n][1], dp[n][1], rd0));
+      rd1 = fmaf(c[n][2], dp[n][2], fmaf(c[n][3], dp[n][3], rd1));
+    }
+    rd0 += __shfl_xor_sync(0xffffffffu, rd0, 1); rd0 += __shfl_xor_sync(0xffffffffu, rd0, 2);
+    rd1 += __shfl_xor_sync(0xffffffffu, rd1, 1); rd1 += __shfl_xor_sync(0xffffffffu, rd1, 2);
+#pragma unroll
+    for (int n = 0; n < 18; ++n) {
+      dp[n][0] = c[n][0] * (dp[n][0] - rd0) * kS; dp[n][1] = c[n][1] * (dp[n][1] - rd0) * kS;
+      dp[n][2] = c[n][2] * (dp[n][2] - rd1) * kS; dp[n][3] = c[n][3] * (dp[n][3] - rd1) * kS;
+    }
+  }
+  // stage P and dS (16-bit), dQs = dS K on the tensor cores
+  {
+    float dq[2][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) { dq[t][0] = dq[t][1] = dq[t][2] = dq[t][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 9; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack2<T>(dp[2 * kk][0], dp[2 * kk][1]);
+      pa[1] = pack2<T>(dp[2 * kk][2], dp[2 * kk][3]);
+      pa[2] = pack2<T>(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+      pa[3] = pack2<T>(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+      *reinterpret_cast<uint32_t*>(&sdS[row0][16 * kk + 2 * q4]) = pa[0];
+      *reinterpret_cast<uint32_t*>(&sdS[row1][16 * kk + 2 * q4]) = pa[1];
+      *reinterpret_cast<uint32_t*>(&sdS[row0][16 * kk + 8 + 2 * q4]) = pa[2];
+      *reinterpret_cast<uint32_t*>(&sdS[row1][16 * kk + 8 + 2 * q4]) = pa[3];
+      *reinterpret_cast<uint32_t*>(&sP[row0][16 * kk + 2 * q4]) = pack2<T>(c[2 * kk][0], c[2 * kk][1]);
+      *reinterpret_cast<uint32_t*>(&sP[row1][16 * kk + 2 * q4]) = pack2<T>(c[2 * kk][2], c[2 * kk][3]);
+      *reinterpret_cast<uint32_t*>(&sP[row0][16 * kk + 8 + 2 * q4]) = pack2<T>(c[2 * kk + 1][0], c[2 * kk + 1][1]);
+      *reinterpret_cast<uint32_t*>(&sP[row1][16 * kk + 8 + 2 * q4]) = pack2<T>(c[2 * kk + 1][2], c[2 * kk + 1][3]);
+      uint32_t kf[4];
+      ldsm_x4_trans(kf, smem_u32(&sK[kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]));
+      mma16816<T>(dq[0], pa, kf[0], kf[1]);
+      mma16816<T>(dq[1], pa, kf[2], kf[3]);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      sdQ[row0][8 * t + 2 * q4] = dq[t][0] * kInvS; sdQ[row0][8 * t + 2 * q4 + 1] = dq[t][1] * kInvS;
+      sdQ[row1][8 * t + 2 * q4] = dq[t][2] * kInvS; sdQ[row1][8 * t + 2 * q4 + 1] = dq[t][3] * kInvS;
+    }
+  }
+  __syncwarp();
+  {
+    // column sums C_i[kc] (even lanes) / row sums R_i[kr] (odd lanes) of dS for query i = 16 warp + lane / 2
+    const int i = warp * 16 + (lane >> 1), which = lane & 1;
+    const int x = i >> 3, y = i & 7;
+    const u16* ds = sdS[i];
+    if (which == 0) {
+#pragma unroll
+      for (int kc2 = 0; kc2 < kOcOws; kc2 += 2) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int kr = 0; kr < kOcOws; ++kr) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(ds + kr * kOcOws + kc2);
+          s0 += unpack_lo<T>(w); s1 += unpack_hi<T>(w);
+        }
+        sC[i][kc2] = s0 * kInvS; sC[i][kc2 + 1] = s1 * kInvS;
+      }
+    } else {
+#pragma unroll
+      for (int kr = 0; kr < kOcOws; ++kr) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int kc2 = 0; kc2 < kOcOws; kc2 += 2) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(ds + kr * kOcOws + kc2);
+          s0 += unpack_lo<T>(w); s1 += unpack_hi<T>(w);
+        }
+        sR[i][kr] = (s0 + s1) * kInvS;
+      }
+    }
+    __syncwarp();
+    // shifted 16-bit tables for the table gradients: Cs[i][r] = C_i[r + y - 11], Rs[i][r] = R_i[r + x - 11] (zero outside 0..11)
+    {
+      const float* src = which ? sR[i] : sC[i];
+      const int pos = which ? x : y;
+#pragma unroll
+      for (int r2 = 0; r2 < 32; r2 += 2) {
+        const int k0 = r2 + pos - (kOcOws - 1), k1 = k0 + 1;
+        const float v0 = (k0 >= 0 && k0 < kOcOws) ? src[k0] * kS : 0.f;
+        const float v1 = (k1 >= 0 && k1 < kOcOws) ? src[k1] * kS : 0.f;
+        *reinterpret_cast<uint32_t*>(&sCs[which][i][r2]) = pack2<T>(v0, v1);
+      }
+    }
+    // relative-position part of dQs, then dq = dQs / 4 -> global: lane = (query, half of the 16 channels)
+    const int d0 = which * 8;
+    float acc[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[d] = sdQ[i][d0 + d];
+#pragma unroll
+    for (int kk = 0; kk < kOcOws; ++kk) {
+      const float cv = sC[i][kk], rv = sR[i][kk];
+      const float* rw = sRel[0][kk - y + kOcOws - 1] + d0;
+      const float* rh = sRel[1][kk - x + kOcOws - 1] + d0;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) acc[d] = fmaf(cv, rw[d], fmaf(rv, rh[d], acc[d]));
+    }
+    const size_t qpix = (size_t)(wy * kOcWs + x) * a.W + wx * kOcWs + y;
+    uint4 o;
+    o.x = pack2<T>(acc[0] * 0.25f, acc[1] * 0.25f); o.y = pack2<T>(acc[2] * 0.25f, acc[3] * 0.25f);
+    o.z = pack2<T>(acc[4] * 0.25f, acc[5] * 0.25f); o.w = pack2<T>(acc[6] * 0.25f, acc[7] * 0.25f);
+    *reinterpret_cast<uint4*>(a.dqkv + (size_t)b * a.gbs + qpix * a.gpitch + h * kOcDh + d0) = o;
+  }
+  __syncthreads();
+
+  // =============================== phase B: contractions over the 64 queries ===============================
+  const size_t cta = ((size_t)b * nwin + blockIdx.x) * a.heads + h;
+  float* okv = a.ws_kv + cta * kObKV;
+  uint32_t qf[4][4], of[4][4];                       // B operands: Qs / dO as [k = query][n = channel]
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    ldsm_x4_trans(qf[ks], smem_u32(&sQ[ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]));
+    ldsm_x4_trans(of[ks], smem_u32(&sdO[ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]));
+  }
+  for (int mt = warp; mt < 9; mt += 4) {             // dK rows 16 mt .. 16 mt + 15
+    float acc[2][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t af[4];
+      ldsm_x4_trans(af, smem_u32(&sdS[ks * 16 + (lane & 7) + 8 * (lane >> 4)][mt * 16 + 8 * ((lane >> 3) & 1)]));
+      mma16816<T>(acc[0], af, qf[ks][0], qf[ks][1]);
+      mma16816<T>(acc[1], af, qf[ks][2], qf[ks][3]);
+    }
+    float* o0 = okv + (size_t)(mt * 16 + g) * 32 + 2 * q4;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      *reinterpret_cast<float2*>(o0 + 8 * t) = make_float2(acc[t][0] * kInvS, acc[t][1] * kInvS);
+      *reinterpret_cast<float2*>(o0 + 8 * 32 + 8 * t) = make_float2(acc[t][2] * kInvS, acc[t][3] * kInvS);
+    }
+  }
+  for (int mt = (warp + 2) & 3; mt < 9; mt += 4) {   // dV rows (the other warps' turn: 5 / 4 / 5 / 4 tiles per warp)
+    float acc[2][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t af[4];
+      ldsm_x4_trans(af, smem_u32(&sP[ks * 16 + (lane & 7) + 8 * (lane >> 4)][mt * 16 + 8 * ((lane >> 3) & 1)]));
+      mma16816<T>(acc[0], af, of[ks][0], of[ks][1]);
+      mma16816<T>(acc[1], af, of[ks][2], of[ks][3]);
+    }
+    float* o0 = okv + (size_t)(mt * 16 + g) * 32 + 16 + 2 * q4;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      *reinterpret_cast<float2*>(o0 + 8 * t) = make_float2(acc[t][0], acc[t][1]);
+      *reinterpret_cast<float2*>(o0 + 8 * 32 + 8 * t) = make_float2(acc[t][2], acc[t][3]);
+    }
+  }
+  {
+    // table gradients: warp = (table, 16-row tile); rows r >= 23 are padding
+    const int tbl = warp >> 1, mt = warp & 1;
+    float acc[2][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t af[4];
+      ldsm_x4_trans(af, smem_u32(&sCs[tbl][ks * 16 + (lane & 7) + 8 * (lane >> 4)][mt * 16 + 8 * ((lane >> 3) & 1)]));
+      mma16816<T>(acc[0], af, qf[ks][0], qf[ks][1]);
+      mma16816<T>(acc[1], af, qf[ks][2], qf[ks][3]);
+    }
+    float* orel = a.ws_rel + cta * kObRel + (size_t)tbl * kOcRel * kOcDh;
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (r0 < kOcRel) *reinterpret_cast<float2*>(orel + r0 * kOcDh + 8 * t + 2 * q4) = make_float2(acc[t][0] * kInvS, acc[t][1] * kInvS);
+      if (r1 < kOcRel) *reinterpret_cast<float2*>(orel + r1 * kOcDh + 8 * t + 2 * q4) = make_float2(acc[t][2] * kInvS, acc[t][3] * kInvS);
+    }
+  }
+}
+
 // gather: dk, dv of pixel (y, x), head h = sum over the key windows containing it.  one thread per (pixel, head, dk|dv)
 template <class T>
 __global__ void __launch_bounds__(256)
@@ -629,7 +963,14 @@ extern "C" int pir_ocab_bwd(const PirOcabBwd* d, void* stream) {
   if (!pir_smem_attr_once(fi ? reinterpret_cast<const void*>(ocab_bwd_kernel<BF16>) : reinterpret_cast<const void*>(ocab_bwd_kernel<FP16>), (int)smem,
                           "pir_ocab_bwd")) return PIR_ERR_CUDA;
   dim3 grid((unsigned)nwin, (unsigned)d->heads, (unsigned)d->B);
-  if (fi) ocab_bwd_kernel<BF16><<<grid, 256, smem, s>>>(a); else ocab_bwd_kernel<FP16><<<grid, 256, smem, s>>>(a);
+  static const bool simt = getenv("PIR_OCAB_BWD_SIMT") != nullptr;   // A/B: the fp32 SIMT version
+  if (simt) {
+    if (fi) ocab_bwd_kernel<BF16><<<grid, 256, smem, s>>>(a); else ocab_bwd_kernel<FP16><<<grid, 256, smem, s>>>(a);
+  } else {
+    if (!pir_smem_attr_once(fi ? reinterpret_cast<const void*>(ocab_bwd_mma_kernel<BF16>) : reinterpret_cast<const void*>(ocab_bwd_mma_kernel<FP16>),
+                            (int)kObMmaSmem, "pir_ocab_bwd")) return PIR_ERR_CUDA;
+    if (fi) ocab_bwd_mma_kernel<BF16><<<grid, 128, kObMmaSmem, s>>>(a); else ocab_bwd_mma_kernel<FP16><<<grid, 128, kObMmaSmem, s>>>(a);
+  }
   if (int e = pir_check_launch("pir_ocab_bwd")) return e;
   const long long total = (long long)d->B * d->H * d->W * d->heads * 2;
   long long blocks = (total + 255) / 256;

@@ -1,14 +1,13 @@
-export PIR_TIME_DTYPE=fp16
-python -m pytest tests/test_gpu_kernels.py -x -q -k "pwdw" 2>&1 | tail -3
-for L in libbase_r2c.so libpromptir_b200.so; do
-  export PROMPTIR_B200_LIB=$PWD/promptir_b200/$L
-  echo "== $L" >> gpurun_out/r2_ab11.txt
-  python tools/time_pwdw.py 16 256 256 96 256 1 20 >> gpurun_out/r2_ab11.txt
-  python tools/time_pwdw.py 16 256 256 96 288 0 20 >> gpurun_out/r2_ab11.txt
-  python tools/time_pwdw.py 16 256 256 48 128 1 20 >> gpurun_out/r2_ab11.txt
-  python tools/time_pwdw.py 16 256 256 48 144 0 20 >> gpurun_out/r2_ab11.txt
-  python tools/time_pwdw.py 16 128 128 96 256 1 20 >> gpurun_out/r2_ab11.txt
-  python tools/time_forward.py 16 256 256 fp16 > gpurun_out/r2_fwd11_$L.txt 2>&1
-  tail -2 gpurun_out/r2_fwd11_$L.txt >> gpurun_out/r2_ab11.txt
+python -m pytest tests/test_gpu_xrestormer.py -x -q 2>&1 | tail -5
+for V in "PIR_OCAB_BWD_SIMT=1" "PIR_X=1"; do
+  echo "== $V" >> gpurun_out/r2_ab15.txt
+  env $V python tools/bench_train.py --model xrestormer --steps 5 --warmup 3 > gpurun_out/tmp_xtrain_$V.json 2> gpurun_out/tmp_xtrain.err
+  python - "gpurun_out/tmp_xtrain_$V.json" >> gpurun_out/r2_ab15.txt <<'P'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print({k:d.get(k) for k in ('value','ms_per_step','unit')})
+k=d.get('kernels') or {}
+for n,v in sorted(k.items(), key=lambda t:-t[1].get('ms',0))[:8]: print('  ',n,v.get('launches'),v.get('ms'))
+P
 done
-cat gpurun_out/r2_ab11.txt
+cat gpurun_out/r2_ab15.txt; tail -3 gpurun_out/tmp_xtrain.err
