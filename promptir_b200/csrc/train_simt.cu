@@ -2,6 +2,8 @@
 // Reference: autograd of net/model.py (LayerNorm :39-41,60-63; GDFN gate :96-97; MDTA :123-137; PixelShuffle/Unshuffle
 // :165,175; PromptGenBlock :226-232) as driven by train.py:37-46.  All of them are HBM/L2-bound: 16-byte vector loads and
 // stores on NHWC 16-bit tensors, fp32 arithmetic, deterministic reductions (no atomics).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -566,6 +568,99 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const SgMulti mp) {
   }
 }
 
+// Tensor-core form of the same strided batched GEMM (default): fp32 operands are split into TF32 high and low parts at fragment
+// load and every product is three mma.m16n8k8 (lo x hi, hi x lo, hi x hi: "3xTF32", fp32-level accuracy, error ~2^-21 relative).
+// 128 threads, 64 x 64 tile, warp w owns the 32 x 32 quadrant (w >> 1, w & 1); K chunks of 16 staged through shared memory with the
+// next chunk's global loads in flight, rows padded to 72 floats so the fragment reads (lane = (g, q4) -> word 8 q4 + g) are
+// conflict free.  PIR_SGEMM_SIMT=1 selects the FFMA kernel above (A/B).
+__device__ __forceinline__ uint32_t f2tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <class T>
+__global__ void __launch_bounds__(128, 4) tgemm_strided_kernel(const SgMulti mp) {
+  constexpr int LD = 72;
+  __shared__ __align__(16) float As[16][LD];
+  __shared__ __align__(16) float Bs[16][LD];
+  const int which = (int)blockIdx.x < mp.bend[0] ? 0 : ((int)blockIdx.x < mp.bend[1] ? 1 : 2);
+  const SgArgs& g = mp.g[which];
+  const int idx = (int)blockIdx.x - (which ? mp.bend[which - 1] : 0);
+  const int tiles = mp.nt_m[which] * mp.nt_n[which];
+  const int z = idx / tiles, tile = idx % tiles, b = z / g.heads, h = z % g.heads;
+  const int m0 = (tile / mp.nt_n[which]) * 64, n0 = (tile % mp.nt_n[which]) * 64;
+  const float* A = g.A + (size_t)b * g.a_sb + (size_t)h * g.a_sh;
+  const float* Bm = g.B + (size_t)b * g.b_sb + (size_t)h * g.b_sh;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, gq = lane >> 2, q4 = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f; }
+  // tile coordinates of the eight A and eight B elements this thread stages per K chunk: the unit-stride axis goes across lanes
+  const bool a_mfast = g.a_sm == 1, b_nfast = g.b_sn == 1;
+  auto a_m = [&](int i) { return a_mfast ? (t & 63) : (t >> 4) + 8 * i; };
+  auto a_k = [&](int i) { return a_mfast ? (t >> 6) + 2 * i : (t & 15); };
+  auto b_n = [&](int i) { return b_nfast ? (t & 63) : (t >> 4) + 8 * i; };
+  auto b_k = [&](int i) { return b_nfast ? (t >> 6) + 2 * i : (t & 15); };
+  float ra[8], rb[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int am = a_m(i), ak = a_k(i), bn = b_n(i), bk = b_k(i);
+      ra[i] = (m0 + am < g.M && k0 + ak < g.K) ? A[(size_t)(m0 + am) * g.a_sm + (size_t)(k0 + ak) * g.a_sk] : 0.f;
+      rb[i] = (n0 + bn < g.N && k0 + bk < g.K) ? Bm[(size_t)(k0 + bk) * g.b_sk + (size_t)(n0 + bn) * g.b_sn] : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < g.K; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { As[a_k(i)][a_m(i)] = ra[i]; Bs[b_k(i)][b_n(i)] = rb[i]; }
+    __syncthreads();
+    if (k0 + 16 < g.K) fetch(k0 + 16);              // next chunk's loads fly while this one is multiplied
+#pragma unroll
+    for (int ks = 0; ks < 16; ks += 8) {
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float v[4] = {As[ks + q4][wm + 16 * mt + gq], As[ks + q4][wm + 16 * mt + gq + 8], As[ks + q4 + 4][wm + 16 * mt + gq],
+                            As[ks + q4 + 4][wm + 16 * mt + gq + 8]};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { ah[mt][e] = f2tf32(v[e]); al[mt][e] = f2tf32(v[e] - __uint_as_float(ah[mt][e])); }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float v[2] = {Bs[ks + q4][wn + 8 * nt + gq], Bs[ks + q4 + 4][wn + 8 * nt + gq]};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { bh[nt][e] = f2tf32(v[e]); bl[nt][e] = f2tf32(v[e] - __uint_as_float(bh[nt][e])); }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          mma_tf32(acc[mt][nt], al[mt], bh[nt]);
+          mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
+          mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int m = m0 + wm + 16 * mt + gq + 8 * (e >> 1), n = n0 + wn + 8 * nt + 2 * q4 + (e & 1);
+        if (m >= g.M || n >= g.N) continue;
+        const size_t o = (size_t)b * g.o_sb + (size_t)h * g.o_sh + (size_t)m * g.o_sm + (size_t)n * g.o_sn;
+        if (g.out16) g.out16[o] = to16<T>(acc[mt][nt][e]);
+        else g.out[o] = acc[mt][nt][e];
+      }
+}
+
 // k2: one warp per attention row (b, r = h*c + i): softmax backward of dA (in place -> dcos), cos, rq, temperature partial.  c <= 32 NT
 template <int NT>
 __global__ void __launch_bounds__(256) mdta_bwd_rows_kernel(const MbArgs a) {
@@ -1033,7 +1128,12 @@ extern "C" int pir_mdta_bwd(const PirMdtaBwd* d, void* stream) {
       total += mp.nt_m[i] * mp.nt_n[i] * B * heads;
       mp.bend[i] = total;
     }
-    if (bf) sgemm_strided_kernel<BF16><<<total, 256, 0, s>>>(mp); else sgemm_strided_kernel<FP16><<<total, 256, 0, s>>>(mp);
+    static const bool simt = getenv("PIR_SGEMM_SIMT") != nullptr;      // A/B: the FFMA kernel
+    if (simt) {
+      if (bf) sgemm_strided_kernel<BF16><<<total, 256, 0, s>>>(mp); else sgemm_strided_kernel<FP16><<<total, 256, 0, s>>>(mp);
+    } else {
+      if (bf) tgemm_strided_kernel<BF16><<<total, 128, 0, s>>>(mp); else tgemm_strided_kernel<FP16><<<total, 128, 0, s>>>(mp);
+    }
     if (int e = pir_check_launch("pir_mdta_bwd(dA, fold, dwo part)")) return e;
   }
   if (c <= 256) mdta_bwd_rows_kernel<8><<<dim3((C + 7) / 8, B), 256, 0, s>>>(a);
