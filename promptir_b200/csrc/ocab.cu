@@ -518,12 +518,14 @@ ocab_bwd_kernel(const ObArgs a) {
 // Workspace layout and the gather / table-reduce kernels are those of the SIMT version; fp32 accumulation, deterministic.
 // ------------------------------------------------------------------------------------------------------
 constexpr int kObPs = 152;                 // 16-bit row stride of the staged P / dS tiles (304 B: ldmatrix rows on distinct banks)
-constexpr int kObCs = 40;                  // 16-bit row stride of the shifted column / row sum tables
-constexpr size_t kObMmaSmem = 2 * (2 * 64 * kOcRowH + 2 * kOcKeys * kOcRowH) + 4 * (2 * kOcRel * kOcDh + 2 * 64 * kOcTs) + 2 * (2 * 64 * kObPs) +
-                              4 * (2 * 64 * kOcOws + 64 * 17) + 2 * (2 * 64 * kObCs);
+constexpr int kObCs = 24;                  // 16-bit row stride of the shifted column / row sum tables (23 used)
+// 74.6 KB: three CTAs per SM.  The per-warp scratch (column / row sums, shifted tables) lives in the warp's own rows of the bias tables,
+// which are dead once the warp has added the bias to its logits.
+constexpr size_t kObMmaSmem = 2 * (2 * 64 * kOcRowH + 2 * kOcKeys * kOcRowH) + 4 * (2 * kOcRel * kOcDh + 2 * 64 * kOcTs) + 2 * (2 * 64 * kObPs);
+static_assert(2 * 16 * kOcOws * 4 <= 16 * kOcTs * 4 && 2 * 16 * kObCs * 2 <= 16 * kOcTs * 4, "per-warp scratch must fit the warp's bias-table rows");
 
 template <class T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 3)
 ocab_bwd_mma_kernel(const ObArgs a) {
   typedef unsigned short u16;
   extern __shared__ __align__(16) uint8_t obm[];
@@ -535,10 +537,10 @@ ocab_bwd_mma_kernel(const ObArgs a) {
   float (*sT)[64][kOcTs] = reinterpret_cast<float (*)[64][kOcTs]>(&sRel[2][0][0]);           // [2]: Tw, Th
   u16 (*sP)[kObPs] = reinterpret_cast<u16 (*)[kObPs]>(&sT[2][0][0]);                         // [64][144]
   u16 (*sdS)[kObPs] = sP + 64;                                                               // [64][144], scaled
-  float (*sC)[kOcOws] = reinterpret_cast<float (*)[kOcOws]>(sdS + 64);                       // [64][12]
-  float (*sR)[kOcOws] = sC + 64;                                                             // [64][12]
-  float (*sdQ)[17] = reinterpret_cast<float (*)[17]>(sR + 64);                               // [64][16] tensor-core part of dQs
-  u16 (*sCs)[64][kObCs] = reinterpret_cast<u16 (*)[64][kObCs]>(sdQ + 64);                    // [2][64][32]: shifted C / R, scaled
+  // per-warp scratch inside the bias tables (see kObMmaSmem): warp w' keeps C | R of its 16 queries ([16][12] fp32 each) in its rows of
+  // Tw and the shifted 16-bit tables Cs | Rs ([2][16][24]) in its rows of Th
+  auto wC = [&](int w2) { return &sT[0][w2 * 16][0]; };
+  auto wCs = [&](int w2) { return reinterpret_cast<u16*>(&sT[1][w2 * 16][0]); };
   constexpr float kS = T::kFmt == 0 ? 256.0f : 1.0f, kInvS = 1.0f / kS;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -678,42 +680,36 @@ ocab_bwd_mma_kernel(const ObArgs a) {
     }
   }
   // stage P and dS (16-bit), dQs = dS K on the tensor cores
-  {
-    float dq[2][4];
+  float dq[2][4];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) { dq[t][0] = dq[t][1] = dq[t][2] = dq[t][3] = 0.f; }
+  for (int t = 0; t < 2; ++t) { dq[t][0] = dq[t][1] = dq[t][2] = dq[t][3] = 0.f; }
 #pragma unroll
-    for (int kk = 0; kk < 9; ++kk) {
-      uint32_t pa[4];
-      pa[0] = pack2<T>(dp[2 * kk][0], dp[2 * kk][1]);
-      pa[1] = pack2<T>(dp[2 * kk][2], dp[2 * kk][3]);
-      pa[2] = pack2<T>(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
-      pa[3] = pack2<T>(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
-      *reinterpret_cast<uint32_t*>(&sdS[row0][16 * kk + 2 * q4]) = pa[0];
-      *reinterpret_cast<uint32_t*>(&sdS[row1][16 * kk + 2 * q4]) = pa[1];
-      *reinterpret_cast<uint32_t*>(&sdS[row0][16 * kk + 8 + 2 * q4]) = pa[2];
-      *reinterpret_cast<uint32_t*>(&sdS[row1][16 * kk + 8 + 2 * q4]) = pa[3];
-      *reinterpret_cast<uint32_t*>(&sP[row0][16 * kk + 2 * q4]) = pack2<T>(c[2 * kk][0], c[2 * kk][1]);
-      *reinterpret_cast<uint32_t*>(&sP[row1][16 * kk + 2 * q4]) = pack2<T>(c[2 * kk][2], c[2 * kk][3]);
-      *reinterpret_cast<uint32_t*>(&sP[row0][16 * kk + 8 + 2 * q4]) = pack2<T>(c[2 * kk + 1][0], c[2 * kk + 1][1]);
-      *reinterpret_cast<uint32_t*>(&sP[row1][16 * kk + 8 + 2 * q4]) = pack2<T>(c[2 * kk + 1][2], c[2 * kk + 1][3]);
-      uint32_t kf[4];
-      ldsm_x4_trans(kf, smem_u32(&sK[kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]));
-      mma16816<T>(dq[0], pa, kf[0], kf[1]);
-      mma16816<T>(dq[1], pa, kf[2], kf[3]);
-    }
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      sdQ[row0][8 * t + 2 * q4] = dq[t][0] * kInvS; sdQ[row0][8 * t + 2 * q4 + 1] = dq[t][1] * kInvS;
-      sdQ[row1][8 * t + 2 * q4] = dq[t][2] * kInvS; sdQ[row1][8 * t + 2 * q4 + 1] = dq[t][3] * kInvS;
-    }
+  for (int kk = 0; kk < 9; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack2<T>(dp[2 * kk][0], dp[2 * kk][1]);
+    pa[1] = pack2<T>(dp[2 * kk][2], dp[2 * kk][3]);
+    pa[2] = pack2<T>(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+    pa[3] = pack2<T>(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+    *reinterpret_cast<uint32_t*>(&sdS[row0][16 * kk + 2 * q4]) = pa[0];
+    *reinterpret_cast<uint32_t*>(&sdS[row1][16 * kk + 2 * q4]) = pa[1];
+    *reinterpret_cast<uint32_t*>(&sdS[row0][16 * kk + 8 + 2 * q4]) = pa[2];
+    *reinterpret_cast<uint32_t*>(&sdS[row1][16 * kk + 8 + 2 * q4]) = pa[3];
+    *reinterpret_cast<uint32_t*>(&sP[row0][16 * kk + 2 * q4]) = pack2<T>(c[2 * kk][0], c[2 * kk][1]);
+    *reinterpret_cast<uint32_t*>(&sP[row1][16 * kk + 2 * q4]) = pack2<T>(c[2 * kk][2], c[2 * kk][3]);
+    *reinterpret_cast<uint32_t*>(&sP[row0][16 * kk + 8 + 2 * q4]) = pack2<T>(c[2 * kk + 1][0], c[2 * kk + 1][1]);
+    *reinterpret_cast<uint32_t*>(&sP[row1][16 * kk + 8 + 2 * q4]) = pack2<T>(c[2 * kk + 1][2], c[2 * kk + 1][3]);
+    uint32_t kf[4];
+    ldsm_x4_trans(kf, smem_u32(&sK[kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)][8 * (lane >> 4)]));
+    mma16816<T>(dq[0], pa, kf[0], kf[1]);
+    mma16816<T>(dq[1], pa, kf[2], kf[3]);
   }
-  __syncwarp();
+  __syncwarp();                                        // the warp's dS rows are complete; its bias-table rows are dead
   {
     // column sums C_i[kc] (even lanes) / row sums R_i[kr] (odd lanes) of dS for query i = 16 warp + lane / 2
-    const int i = warp * 16 + (lane >> 1), which = lane & 1;
+    const int il = lane >> 1, i = warp * 16 + il, which = lane & 1;
     const int x = i >> 3, y = i & 7;
     const u16* ds = sdS[i];
+    float* mine = wC(warp) + which * (16 * kOcOws) + il * kOcOws;          // C rows, then R rows
     if (which == 0) {
 #pragma unroll
       for (int kc2 = 0; kc2 < kOcOws; kc2 += 2) {
@@ -723,7 +719,7 @@ ocab_bwd_mma_kernel(const ObArgs a) {
           const uint32_t w = *reinterpret_cast<const uint32_t*>(ds + kr * kOcOws + kc2);
           s0 += unpack_lo<T>(w); s1 += unpack_hi<T>(w);
         }
-        sC[i][kc2] = s0 * kInvS; sC[i][kc2 + 1] = s1 * kInvS;
+        mine[kc2] = s0 * kInvS; mine[kc2 + 1] = s1 * kInvS;
       }
     } else {
 #pragma unroll
@@ -734,40 +730,53 @@ ocab_bwd_mma_kernel(const ObArgs a) {
           const uint32_t w = *reinterpret_cast<const uint32_t*>(ds + kr * kOcOws + kc2);
           s0 += unpack_lo<T>(w); s1 += unpack_hi<T>(w);
         }
-        sR[i][kr] = (s0 + s1) * kInvS;
+        mine[kr] = (s0 + s1) * kInvS;
       }
     }
-    __syncwarp();
     // shifted 16-bit tables for the table gradients: Cs[i][r] = C_i[r + y - 11], Rs[i][r] = R_i[r + x - 11] (zero outside 0..11)
     {
-      const float* src = which ? sR[i] : sC[i];
       const int pos = which ? x : y;
+      u16* dst = wCs(warp) + which * (16 * kObCs) + il * kObCs;
 #pragma unroll
-      for (int r2 = 0; r2 < 32; r2 += 2) {
+      for (int r2 = 0; r2 < kObCs; r2 += 2) {
         const int k0 = r2 + pos - (kOcOws - 1), k1 = k0 + 1;
-        const float v0 = (k0 >= 0 && k0 < kOcOws) ? src[k0] * kS : 0.f;
-        const float v1 = (k1 >= 0 && k1 < kOcOws) ? src[k1] * kS : 0.f;
-        *reinterpret_cast<uint32_t*>(&sCs[which][i][r2]) = pack2<T>(v0, v1);
+        const float v0 = (k0 >= 0 && k0 < kOcOws) ? mine[k0] * kS : 0.f;
+        const float v1 = (k1 >= 0 && k1 < kOcOws) ? mine[k1] * kS : 0.f;
+        *reinterpret_cast<uint32_t*>(dst + r2) = pack2<T>(v0, v1);
       }
     }
-    // relative-position part of dQs, then dq = dQs / 4 -> global: lane = (query, half of the 16 channels)
-    const int d0 = which * 8;
-    float acc[8];
-#pragma unroll
-    for (int d = 0; d < 8; ++d) acc[d] = sdQ[i][d0 + d];
+  }
+  __syncwarp();
+  {
+    // relative-position part of dQs in the accumulator layout: rows row0 / row1 (window rows 2 warp / 2 warp + 1, column g),
+    // channels 8 t + 2 q4 + {0, 1};  dQs_i += sum_kk C_i[kk] rel_w[kk - y + 11] + R_i[kk] rel_h[kk - x + 11]
+    const float* c0p = wC(warp) + g * kOcOws;                 // query row0: il = g
+    const float* c1p = c0p + 8 * kOcOws;                      // query row1: il = g + 8
+    const float* r0p = c0p + 16 * kOcOws;
+    const float* r1p = c1p + 16 * kOcOws;
 #pragma unroll
     for (int kk = 0; kk < kOcOws; ++kk) {
-      const float cv = sC[i][kk], rv = sR[i][kk];
-      const float* rw = sRel[0][kk - y + kOcOws - 1] + d0;
-      const float* rh = sRel[1][kk - x + kOcOws - 1] + d0;
+      const float cv0 = c0p[kk], cv1 = c1p[kk], rv0 = r0p[kk], rv1 = r1p[kk];
+      const float* rw = sRel[0][kk - g + kOcOws - 1] + 2 * q4;
+      const float* rh0 = sRel[1][kk - 2 * warp + kOcOws - 1] + 2 * q4;
+      const float* rh1 = sRel[1][kk - (2 * warp + 1) + kOcOws - 1] + 2 * q4;
 #pragma unroll
-      for (int d = 0; d < 8; ++d) acc[d] = fmaf(cv, rw[d], fmaf(rv, rh[d], acc[d]));
+      for (int t = 0; t < 2; ++t) {
+        const float2 w2 = *reinterpret_cast<const float2*>(rw + 8 * t);
+        const float2 h0 = *reinterpret_cast<const float2*>(rh0 + 8 * t), h1 = *reinterpret_cast<const float2*>(rh1 + 8 * t);
+        dq[t][0] = fmaf(cv0 * kS, w2.x, fmaf(rv0 * kS, h0.x, dq[t][0])); dq[t][1] = fmaf(cv0 * kS, w2.y, fmaf(rv0 * kS, h0.y, dq[t][1]));
+        dq[t][2] = fmaf(cv1 * kS, w2.x, fmaf(rv1 * kS, h1.x, dq[t][2])); dq[t][3] = fmaf(cv1 * kS, w2.y, fmaf(rv1 * kS, h1.y, dq[t][3]));
+      }
     }
-    const size_t qpix = (size_t)(wy * kOcWs + x) * a.W + wx * kOcWs + y;
-    uint4 o;
-    o.x = pack2<T>(acc[0] * 0.25f, acc[1] * 0.25f); o.y = pack2<T>(acc[2] * 0.25f, acc[3] * 0.25f);
-    o.z = pack2<T>(acc[4] * 0.25f, acc[5] * 0.25f); o.w = pack2<T>(acc[6] * 0.25f, acc[7] * 0.25f);
-    *reinterpret_cast<uint4*>(a.dqkv + (size_t)b * a.gbs + qpix * a.gpitch + h * kOcDh + d0) = o;
+    // dq = dQs / 4 (qs = q / 4), unscaled
+    const float sc = 0.25f * kInvS;
+    const size_t pix0 = (size_t)(wy * kOcWs + 2 * warp) * a.W + wx * kOcWs + g;
+    unsigned short* op = a.dqkv + (size_t)b * a.gbs + h * kOcDh + 2 * q4;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      *reinterpret_cast<uint32_t*>(op + pix0 * a.gpitch + 8 * t) = pack2<T>(dq[t][0] * sc, dq[t][1] * sc);
+      *reinterpret_cast<uint32_t*>(op + (pix0 + a.W) * a.gpitch + 8 * t) = pack2<T>(dq[t][2] * sc, dq[t][3] * sc);
+    }
   }
   __syncthreads();
 
@@ -825,7 +834,8 @@ ocab_bwd_mma_kernel(const ObArgs a) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       uint32_t af[4];
-      ldsm_x4_trans(af, smem_u32(&sCs[tbl][ks * 16 + (lane & 7) + 8 * (lane >> 4)][mt * 16 + 8 * ((lane >> 3) & 1)]));
+      // rows 16 ks .. 16 ks + 15 are warp ks' scratch; columns >= 23 are padding (they reach rows of the output that are not stored)
+      ldsm_x4_trans(af, smem_u32(wCs(ks) + tbl * (16 * kObCs) + ((lane & 7) + 8 * (lane >> 4)) * kObCs + mt * 16 + 8 * ((lane >> 3) & 1)));
       mma16816<T>(acc[0], af, qf[ks][0], qf[ks][1]);
       mma16816<T>(acc[1], af, qf[ks][2], qf[ks][3]);
     }
