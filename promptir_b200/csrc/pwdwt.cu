@@ -8,13 +8,18 @@
 // GELU gate and the store from registers -- no shared-memory tile, no LDS, no group barriers.  x1 and x2 of the gate (channels c and
 // hidden + c) are two accumulators of the SAME lane (two MMA chains against the two 128-row weight slabs).
 //
-// Per CTA (persistent, one per SM, 576 threads): warp 0 TMA producer | warp 1 MMA issuer | warps 2-17 compute.
-// Item = (image, 12 x 16 output tile); halo'd tile 14 x 18 = 252 pixels (256 rows in shared memory), LayerNorm in place as in pwdw.cu.
+// Per CTA (persistent, one per SM, 704 threads): warp 0 TMA producer | warp 1 MMA issuer | warps 2-17 stencil | warps 18-21 LayerNorm.
+// Item = (image, 12 x 16 output tile); halo'd tile 14 x 18 = 252 pixels (256 rows in shared memory), two tile buffers: the LayerNorm
+// warps normalise tile i + 1 in place (as in pwdw.cu) while tile i is multiplied and filtered.
 // Per item, per block of 128 gated channels, three sub-units of 6 halo'd rows (4 output rows): N = 112 columns (6 x 18 = 108 used)
 // per accumulator, two accumulators (x1 | x2) per TMEM buffer, two buffers (512 columns).  The B operand of a sub-unit is the x
 // tile at row offset 72 * third (9 KiB: swizzle-atom aligned), so the overlapping rows are never copied.
-// Compute warp w: lane quarter q = w & 3 (channels 32 q .. 32 q + 31 of the block), column patch s = (w - 2) >> 2 (output columns
-// 4 s .. 4 s + 3); per sub-unit a thread produces 4 x 4 gated outputs of one channel.
+// Stencil warp w: lane quarter q = w & 3 (channels 32 q .. 32 q + 31 of the block), column patch s = (w - 2) >> 2 (output columns
+// 4 s .. 4 s + 3); per sub-unit a thread produces 4 x 4 gated outputs of one channel.  Whether a (warp, sub-unit) needs the border
+// path (t added per in-image pixel, bounds-checked stores) is decided per warp and sub-unit, not per tile.
+// Plain form (qkv, no gate): 256-channel blocks (two independent accumulators per lane); the last N % 128 <= 32 channels form ONE
+// replicated unit per item (the same 32 weight rows in all four lane quarters against the whole tile, quarter q serving sub-unit q).
+// What bounds it: the packed-fp16 FMA pipe of the CUDA cores (one HFMA2 per two cycles per scheduler), see DESIGN.md 3.2b.
 #include <stdlib.h>
 
 #include "common.cuh"
