@@ -279,6 +279,13 @@ PWDW_CASES = [
     (3, 20, 28, 48, 144, False, LN_BIASFREE, None, 0, False, True),
     (2, 128, 128, 96, 288, False, LN_WITHBIAS, None, 0, False, False),
     (1, 8, 8, 48, 144, False, LN_NONE, None, 0, True, False),
+    # plain form, other channel splits: 192 = 128 + 64 (a half block, no replicated unit), 96 <= 128 (one block), 160 = 128 + 32 at
+    # C = 48 (replicated unit of a full 32), 272 = 256 + 16 at C = 64, image height a multiple of neither 12 nor 4
+    (2, 30, 40, 64, 192, False, LN_WITHBIAS, None, 0, True, True),
+    (1, 24, 16, 32, 96, False, LN_BIASFREE, None, 0, False, False),
+    (2, 26, 20, 48, 160, False, LN_WITHBIAS, None, 0, False, True),
+    (1, 18, 50, 64, 272, False, LN_WITHBIAS, None, 0, True, False),
+    (1, 22, 34, 64, 128, True, LN_WITHBIAS, None, 0, True, True),
 ]
 
 
