@@ -16,6 +16,8 @@
 // Warp roles (480 threads): 0 TMA producer | 1 TMEM alloc + MMA issue | 2-5 LN statistics |
 //   6-9 and 10-13 two independent epilogue warpgroups (alternate 64-column slabs, own staging slots) |
 //   14 residual prefetch.  (One warpgroup alone is latency bound: TMEM load -> FMA -> pack -> STS chains.)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 
@@ -38,6 +40,7 @@ struct PwArgs {
   int w_batched;
   int ln_mode;
   int has_res;
+  int rotate;         // streamed weights: per-CTA rotation of the column-chunk order (PIR_GEMM_ROTATE=0 turns it off)
   int m_tiles;        // per image
   int n_alloc;        // weight rows held per k-block: ceil(N16 / 64) * 64
   uint32_t off_ring, off_slots, off_vec, off_stats;   // byte offsets from the 1024-aligned smem base
@@ -77,6 +80,11 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t b_chunk_bytes = (uint32_t)((g.NC + 63) / 64) * 8192u;   // whole 64-row boxes
   const uint32_t stage_bytes = kPwATile + (g.resident ? 0u : b_chunk_bytes);
   const int total_tiles = g.B * g.m_tiles;
+  // Streamed (non-resident) weights: every CTA walks the column chunks of a tile in its own rotation, so at any moment the CTAs
+  // pull DIFFERENT parts of the weight matrix out of L2 instead of all 128-148 of them hammering the same lines (the level-4
+  // GEMMs stream a 0.9-1.6 MB matrix per CTA and ran at ~35 GB/s per SM).  All roles use the same order.
+  const int rot = (g.resident || g.rotate == 0) ? 0 : (int)(blockIdx.x % (unsigned)g.n_chunks);
+  auto chunk_of = [&](int c) { const int cc = c + rot; return cc >= g.n_chunks ? cc - g.n_chunks : cc; };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmO);
@@ -116,7 +124,8 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int b = t / g.m_tiles, m0 = (t % g.m_tiles) * kPwBlockM;
       const int reps = g.resident ? 1 : g.n_chunks;
-      for (int c = 0; c < reps; ++c) {
+      for (int ci = 0; ci < reps; ++ci) {
+        const int c = chunk_of(ci);
         const int ncols = min(g.NC, ((g.N + 15) / 16 * 16) - c * g.NC);
         const int bboxes = g.resident ? 0 : (ncols + 63) / 64;
         for (int kb = 0; kb < g.nkb; ++kb) {
@@ -140,7 +149,8 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0; uint32_t phase = 0;      // ring position of the current tile's first k-block
     uint32_t q = 0;                          // accumulator chunk counter
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      for (int c = 0; c < g.n_chunks; ++c, ++q) {
+      for (int ci = 0; ci < g.n_chunks; ++ci, ++q) {
+        const int c = chunk_of(ci);
         const uint32_t buf = q & 1u;
         const int ncols = min(g.NC, ((g.N + 15) / 16 * 16) - c * g.NC);
         const uint32_t idesc = make_idesc_f16(T::kFmt, kPwBlockM, ncols, 0, 0);
@@ -158,13 +168,13 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int k = 0; k < ksteps; ++k)
               umma_f16(tmem_base + buf * 256u, make_sdesc_sw128(a_src + k * 32, 16, 1024), make_sdesc_sw128(b_src + k * 32, 16, 1024),
                        idesc, (kb | k) != 0 ? 1u : 0u);
-            if (!g.resident || c == g.n_chunks - 1) umma_commit(smem_u32(&bar_empty[st]));   // stage no longer needed
+            if (!g.resident || ci == g.n_chunks - 1) umma_commit(smem_u32(&bar_empty[st]));   // stage no longer needed
             if (kb == g.nkb - 1) umma_commit(smem_u32(&bar_tfull[buf]));
           }
           __syncwarp();
           if (++st == g.stages) { st = 0; ph ^= 1u; }
         }
-        if (!g.resident || c == g.n_chunks - 1) { stage = st; phase = ph; }     // resident: chunks re-walk the same stages
+        if (!g.resident || ci == g.n_chunks - 1) { stage = st; phase = ph; }     // resident: chunks re-walk the same stages
       }
     }
   } else if (warp < 6) {
@@ -229,7 +239,8 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         a_shift = st.x; a_scale = st.y;
         mbar_arrive(smem_u32(&bar_sempty[mb]));
       }
-      for (int c = 0; c < g.n_chunks; ++c, ++q) {
+      for (int ci = 0; ci < g.n_chunks; ++ci, ++q) {
+        const int c = chunk_of(ci);
         const uint32_t buf = q & 1u;
         const int ncols = min(g.NC, n16 - c * g.NC);
         // both groups observe every chunk (even one whose slabs all belong to the other group) so neither can run
@@ -313,7 +324,8 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t u = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int b = t / g.m_tiles, m0 = (t % g.m_tiles) * kPwBlockM;
-        for (int c = 0; c < g.n_chunks; ++c) {
+        for (int ci = 0; ci < g.n_chunks; ++ci) {
+          const int c = chunk_of(ci);
           const int ncols = min(g.NC, n16 - c * g.NC);
           for (int s0 = 0; s0 < ncols; s0 += 64, ++u) {
             const uint32_t grp = u & 1u, j = u >> 1;
@@ -349,6 +361,10 @@ static int launch_pw(const PirGemm* d, cudaStream_t stream) {
   if (n16 <= 256) { g.NC = n16; g.n_chunks = 1; } else { g.NC = 256; g.n_chunks = (n16 + 255) / 256; }
   g.n_alloc = (n16 + 63) / 64 * 64;
   g.w_batched = d->w_batched; g.ln_mode = d->ln_mode; g.has_res = d->res ? 1 : 0;
+  {
+    static const int rot_env = [] { const char* e = getenv("PIR_GEMM_ROTATE"); return e ? atoi(e) : 1; }();
+    g.rotate = rot_env;
+  }
   g.m_tiles = (g.hw + kPwBlockM - 1) / kPwBlockM;
   g.ln_s = d->ln_s; g.vec_t = d->vec_t;
 
