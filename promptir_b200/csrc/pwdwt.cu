@@ -120,7 +120,8 @@ __device__ __forceinline__ void tw_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 // gated outputs.  BORDER: the tile touches the image border -- t is added to in-image pixels only (the zero padding of the depthwise
 // conv must stay zero) and stores are bounds-checked; interior tiles take the straight-line path.
 template <class T, bool GATE32, bool BORDER, int PITCH>
-__device__ __forceinline__ void tw_subunit(uint32_t tcol, const uint32_t (&w1)[9], const uint32_t (&w2)[9], uint32_t seed1, uint32_t seed2,
+__device__ __forceinline__ void tw_subunit(uint32_t tcol, const uint32_t (&w1)[9], const uint32_t (&w2)[9], uint32_t seed1a, uint32_t seed1b,
+                                           uint32_t seed2a, uint32_t seed2b,
                                            float2 tv, uint32_t col_in, int yo, int xo, int H, int W, unsigned short* orow, int pitch_rt,
                                            size_t row_stride) {
   constexpr int SW = kTwSW;
@@ -156,7 +157,7 @@ __device__ __forceinline__ void tw_subunit(uint32_t tcol, const uint32_t (&w1)[9
       o2[j] = tw_pack_sat(__uint_as_float(r2[2 * j + 1]), __uint_as_float(r2[2 * j + 2]));
     }
     if (ri < 5) { tw_ld8(tcol + (uint32_t)((ri + 1) * SW), r1); tw_ld8(tcol + 128u + (uint32_t)((ri + 1) * SW), r2); }
-    if (ri < 4) { a1[ri % 3][0] = seed1; a1[ri % 3][1] = seed1; a2[ri % 3][0] = seed2; a2[ri % 3][1] = seed2; }
+    if (ri < 4) { a1[ri % 3][0] = seed1a; a1[ri % 3][1] = seed1b; a2[ri % 3][0] = seed2a; a2[ri % 3][1] = seed2b; }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int ro = ri - ky;
@@ -205,7 +206,7 @@ __device__ __forceinline__ void tw_subunit(uint32_t tcol, const uint32_t (&w1)[9
 // Plain (no gate) sub-unit of one thread and ONE accumulator: 6 halo'd rows x 6 columns of its channel -> 4 x 4 outputs of the
 // depthwise conv, stored as 16-bit.  Same structure as tw_subunit.
 template <class T, bool BORDER>
-__device__ __forceinline__ void tw_plain(uint32_t tcol, const uint32_t (&w)[9], uint32_t seed, float tv, uint32_t col_in, int yo, int xo,
+__device__ __forceinline__ void tw_plain(uint32_t tcol, const uint32_t (&w)[9], uint32_t seeda, uint32_t seedb, float tv, uint32_t col_in, int yo, int xo,
                                          int H, int W, unsigned short* orow, int pitch, size_t row_stride, bool st_ok = true) {
   constexpr int SW = kTwSW;
   uint32_t a[3][2];
@@ -228,7 +229,7 @@ __device__ __forceinline__ void tw_plain(uint32_t tcol, const uint32_t (&w)[9], 
 #pragma unroll
     for (int j = 0; j < 2; ++j) o[j] = tw_pack_sat(__uint_as_float(r[2 * j + 1]), __uint_as_float(r[2 * j + 2]));
     if (ri < 5) tw_ld8(tcol + (uint32_t)((ri + 1) * SW), r);
-    if (ri < 4) { a[ri % 3][0] = seed; a[ri % 3][1] = seed; }
+    if (ri < 4) { a[ri % 3][0] = seeda; a[ri % 3][1] = seedb; }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int ro = ri - ky;
@@ -270,7 +271,7 @@ __device__ __forceinline__ uint64_t tw_sdesc(uint32_t sbo_bytes, uint32_t layout
 }
 
 // Shared-memory plan (bytes from the 1024-aligned base):
-//   [x tile: 2 x NKB k-blocks x 256 rows x KBB B] [weights, resident: NKB k-blocks x 2 hp rows x KBB B] [tap table: hp x 48 B] [t: hp x 8 B]
+//   [x tile: 2 x NKB k-blocks x 256 rows x KBB B] [weights, resident: NKB k-blocks x 2 hp rows x KBB B] [tap table: hp x 64 B] [t: hp x 8 B]
 // KBB = bytes of a k-block row: 128 (64 channels, 128-byte swizzle; C = 48) or 64 (32 channels, 64-byte swizzle; C = 96 = 3 x 32, so
 // nothing is padded, two x tiles and the WHOLE weight matrix fit next to each other: the weights are fetched once per CTA and the
 // next item's tile is loaded and LayerNormed while the current one is multiplied).
@@ -299,7 +300,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  uint4* stab = reinterpret_cast<uint4*>(base_ptr + g.off_tab);          // [hp][3] x 16 B: w1[9] w2[9] seed1i seed2i bias1 bias2 0 0 (fp16)
+  uint4* stab = reinterpret_cast<uint4*>(base_ptr + g.off_tab);          // [hp][4] x 16 B: w1[9] w2[9] seed1i seed2i bias1 bias2 0 0 | seed1L seed2L seed1R seed2R 0 0 0 0 (fp16)
   float2* svt = reinterpret_cast<float2*>(base_ptr + g.off_vt);          // [hp] (t1, t2)
 
   if (threadIdx.x == 0) {
@@ -327,20 +328,29 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int c1 = GATE ? i : rslot ? g.n_main + (i - g.n_cb * 128) : (i >> 7) * 256 + (i & 127), c2 = GATE ? g.hp + i : c1 + 128;
       const bool v1 = GATE ? true : rslot ? (i - g.n_cb * 128) < g.n_rep : c1 < g.n_main;
       const bool v2 = GATE ? true : (!rslot && c2 < g.n_main);
-      float ws1 = 0.f, ws2 = 0.f;
+      float ws1 = 0.f, ws2 = 0.f, cl1 = 0.f, cl2 = 0.f, cr1 = 0.f, cr2 = 0.f;
       for (int tap = 0; tap < 9; ++tap) {
         const unsigned short a = v1 ? src[(size_t)tap * n_pre + c1] : (unsigned short)0;
         const float bf = v2 ? __half2float(__ushort_as_half(src[(size_t)tap * n_pre + c2])) * qs : 0.f;
-        tab[i * 24 + tap] = a; tab[i * 24 + 9 + tap] = __half_as_ushort(__float2half_rn(bf));
+        tab[i * 32 + tap] = a; tab[i * 32 + 9 + tap] = __half_as_ushort(__float2half_rn(bf));
         ws1 += __half2float(__ushort_as_half(a)); ws2 += bf;
+        if (tap % 3 == 0) { cl1 += __half2float(__ushort_as_half(a)); cl2 += bf; }      // left column of taps (dx = -1)
+        if (tap % 3 == 2) { cr1 += __half2float(__ushort_as_half(a)); cr2 += bf; }      // right column (dx = +1)
       }
       const float b1 = (g.dw_bias && v1) ? g.dw_bias[c1] : 0.f, b2 = ((g.dw_bias && v2) ? g.dw_bias[c2] : 0.f) * qs;
       const float t1 = (g.vec_t && v1) ? g.vec_t[c1] : 0.f, t2 = (g.vec_t && v2) ? g.vec_t[c2] : 0.f;
-      tab[i * 24 + 18] = __half_as_ushort(__float2half_rn(b1 + t1 * ws1));      // interior tiles: the conv of the constant t is a constant
-      tab[i * 24 + 19] = __half_as_ushort(__float2half_rn(b2 + t2 * ws2));
-      tab[i * 24 + 20] = __half_as_ushort(__float2half_rn(b1));
-      tab[i * 24 + 21] = __half_as_ushort(__float2half_rn(b2));
-      tab[i * 24 + 22] = 0; tab[i * 24 + 23] = 0;
+      tab[i * 32 + 18] = __half_as_ushort(__float2half_rn(b1 + t1 * ws1));      // interior tiles: the conv of the constant t is a constant
+      tab[i * 32 + 19] = __half_as_ushort(__float2half_rn(b2 + t2 * ws2));
+      tab[i * 32 + 20] = __half_as_ushort(__float2half_rn(b1));
+      tab[i * 32 + 21] = __half_as_ushort(__float2half_rn(b2));
+      tab[i * 32 + 22] = 0; tab[i * 32 + 23] = 0;
+      // output columns whose left / right neighbour column lies outside the image (its pixels are zero padding and get no t): the
+      // constant loses that column of taps.  With these seeds an x-edge patch runs the straight-line path like an interior one.
+      tab[i * 32 + 24] = __half_as_ushort(__float2half_rn(b1 + t1 * (ws1 - cl1)));
+      tab[i * 32 + 25] = __half_as_ushort(__float2half_rn(b2 + t2 * (ws2 - cl2)));
+      tab[i * 32 + 26] = __half_as_ushort(__float2half_rn(b1 + t1 * (ws1 - cr1)));
+      tab[i * 32 + 27] = __half_as_ushort(__float2half_rn(b2 + t2 * (ws2 - cr2)));
+      tab[i * 32 + 28] = 0; tab[i * 32 + 29] = 0; tab[i * 32 + 30] = 0; tab[i * 32 + 31] = 0;
       svt[i] = make_float2(t1, t2);
     }
   }
@@ -545,6 +555,11 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // image, a sub-unit its six input rows.  On a 256 x 256 image 20 % of the tiles touch the border but only 6 % of the
       // (warp, sub-unit) pairs do, and the sub-units of the last tile row that lie wholly below the image are skipped.
       const bool cols_ok = x0 - 1 + 4 * s >= 0 && x0 + 4 * s + 4 < g.W;
+      // x-edge patches: exactly the left-most (right-most) input column is outside the image and all four output columns are inside.
+      // They would make ONE of the four column patches 1.5x slower than the other three for every sub-unit of an edge tile, and the
+      // other twelve warps wait for it at every accumulator hand-over; edge seeds (see the table) put them on the straight-line path.
+      const bool left_edge = x0 - 1 + 4 * s == -1 && x0 + 4 * s + 4 < g.W;
+      const bool right_edge = x0 + 4 * s + 4 == g.W && x0 - 1 + 4 * s >= 0;
       // validity of this thread's six input columns (halo'd columns 4 s .. 4 s + 5) and its four output columns
       uint32_t col_in = 0;
 #pragma unroll
@@ -557,7 +572,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int cb = 0; cb < g.n_cb; ++cb) {
         const int ch = cb * 128 + q * 32 + lane;       // table slot of this thread = its gated channel (gate)
         // taps (packed pairs), seeds
-        const uint4 ta = stab[ch * 3], tb4 = stab[ch * 3 + 1], tc = stab[ch * 3 + 2];
+        const uint4 ta = stab[ch * 4], tb4 = stab[ch * 4 + 1], tc = stab[ch * 4 + 2];
         // halves: ta = w1[0..7]; tb4 = w1[8] w2[0..6]; tc = w2[7] w2[8] s1i s2i b1 b2 0 0
         uint32_t w1[9], w2[9];
         w1[0] = tw_bcast_lo(ta.x); w1[1] = tw_bcast_hi(ta.x); w1[2] = tw_bcast_lo(ta.y); w1[3] = tw_bcast_hi(ta.y);
@@ -596,25 +611,33 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t tcol = t_lane + tb * 256u;
           const int yo = y0 + third * kTwRowsPerThird;            // first output row of the sub-unit
-          const bool interior = cols_ok && yo >= 1 && yo + 4 < g.H;  // all 6 x 6 inputs (hence all 4 x 4 outputs) inside the image
+          const bool rows_ok = yo >= 1 && yo + 4 < g.H;
+          const bool xl = rows_ok && left_edge, xr = rows_ok && right_edge;
+          const bool interior = (cols_ok && rows_ok) || xl || xr;   // straight-line path: no per-pixel t, no bounds checks
           // interior: the conv of the constant t is the constant t * sum(taps) and rides on the seed; border: t is added per in-image pixel
           const uint32_t seed1 = interior ? tw_bcast_lo(tc.y) : tw_bcast_lo(tc.z);
           const uint32_t seed2 = interior ? tw_bcast_hi(tc.y) : tw_bcast_hi(tc.z);
+          uint32_t seed1a = seed1, seed1b = seed1, seed2a = seed2, seed2b = seed2;   // per accumulator: output pairs (0, 1) and (2, 3)
+          if (xl || xr) {                                           // rare: fetched here so nothing stays live across the loop
+            const uint4 td = stab[ch * 4 + 3];
+            if (xl) { seed1a = __byte_perm(td.x, tc.y, 0x5410); seed2a = __byte_perm(td.x, tc.y, 0x7632); }    // (edge, interior)
+            if (xr) { seed1b = __byte_perm(tc.y, td.y, 0x5410); seed2b = __byte_perm(tc.y, td.y, 0x7632); }    // (interior, edge)
+          }
           if (yo >= g.H) {
             // nothing to store (last tile row of an image whose height is not a multiple of the tile): release the accumulators
           } else if (GATE) {
-            if (interior) tw_subunit<T, GATE32, false, PITCH>(tcol, w1, w2, seed1, seed2, tv, 0u, yo, xo, g.H, g.W, orow, pitch, row_stride);
-            else tw_subunit<T, GATE32, true, PITCH>(tcol, w1, w2, seed1, seed2, add_t ? tv : make_float2(0.f, 0.f), col_in, yo, xo, g.H, g.W, orow, pitch, row_stride);
+            if (interior) tw_subunit<T, GATE32, false, PITCH>(tcol, w1, w2, seed1a, seed1b, seed2a, seed2b, tv, 0u, yo, xo, g.H, g.W, orow, pitch, row_stride);
+            else tw_subunit<T, GATE32, true, PITCH>(tcol, w1, w2, seed1a, seed1b, seed2a, seed2b, add_t ? tv : make_float2(0.f, 0.f), col_in, yo, xo, g.H, g.W, orow, pitch, row_stride);
           } else {
             // channels past the end of the tensor (last block) are skipped per warp; a partially valid warp masks its stores by
             // pretending the row is outside the image (H = 0 on the border path)
             if (any_a) {
-              if (interior && all_a) tw_plain<T, false>(tcol, w1, seed1, 0.f, 0u, yo, xo, g.H, g.W, orow, pitch1, row_stride1);
-              else tw_plain<T, true>(tcol, w1, seed1, (add_t && !interior) ? tv.x : 0.f, interior ? 0x3fu : col_in, yo, xo, va ? g.H : 0, g.W, orow, pitch1, row_stride1);
+              if (interior && all_a) tw_plain<T, false>(tcol, w1, seed1a, seed1b, 0.f, 0u, yo, xo, g.H, g.W, orow, pitch1, row_stride1);
+              else tw_plain<T, true>(tcol, w1, seed1a, seed1b, (add_t && !interior) ? tv.x : 0.f, interior ? 0x3fu : col_in, yo, xo, va ? g.H : 0, g.W, orow, pitch1, row_stride1);
             }
             if (any_b) {
-              if (interior && all_b) tw_plain<T, false>(tcol + 128u, w2, seed2, 0.f, 0u, yo, xo, g.H, g.W, orow2, pitch2, row_stride2);
-              else tw_plain<T, true>(tcol + 128u, w2, seed2, (add_t && !interior) ? tv.y : 0.f, interior ? 0x3fu : col_in, yo, xo, vb ? g.H : 0, g.W, orow2, pitch2, row_stride2);
+              if (interior && all_b) tw_plain<T, false>(tcol + 128u, w2, seed2a, seed2b, 0.f, 0u, yo, xo, g.H, g.W, orow2, pitch2, row_stride2);
+              else tw_plain<T, true>(tcol + 128u, w2, seed2a, seed2b, (add_t && !interior) ? tv.y : 0.f, interior ? 0x3fu : col_in, yo, xo, vb ? g.H : 0, g.W, orow2, pitch2, row_stride2);
             }
           }
           if (GATE) orow += 4 * row_stride;
@@ -632,23 +655,28 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int yo = y0 + q * kTwRowsPerThird;
         if (q < 3 && yo < g.H) {
           const int slot = g.n_cb * 128 + lane;
-          const uint4 ta = stab[slot * 3], tb4 = stab[slot * 3 + 1], tc = stab[slot * 3 + 2];
+          const uint4 ta = stab[slot * 4], tb4 = stab[slot * 4 + 1], tc = stab[slot * 4 + 2], td = stab[slot * 4 + 3];
           uint32_t w1[9];
           w1[0] = tw_bcast_lo(ta.x); w1[1] = tw_bcast_hi(ta.x); w1[2] = tw_bcast_lo(ta.y); w1[3] = tw_bcast_hi(ta.y);
           w1[4] = tw_bcast_lo(ta.z); w1[5] = tw_bcast_hi(ta.z); w1[6] = tw_bcast_lo(ta.w); w1[7] = tw_bcast_hi(ta.w);
           w1[8] = tw_bcast_lo(tb4.x);
           const int c = g.n_main + lane;
           const bool v = lane < g.n_rep;
-          const bool interior = cols_ok && yo >= 1 && yo + 4 < g.H;
-          const uint32_t seed = interior ? tw_bcast_lo(tc.y) : tw_bcast_lo(tc.z);
+          const bool rows_ok = yo >= 1 && yo + 4 < g.H;
+          const bool xl = rows_ok && left_edge, xr = rows_ok && right_edge;
+          const bool interior = (cols_ok && rows_ok) || xl || xr;
+          uint32_t seeda, seedb;
+          seeda = seedb = interior ? tw_bcast_lo(tc.y) : tw_bcast_lo(tc.z);
+          if (xl) seeda = __byte_perm(td.x, tc.y, 0x5410);
+          if (xr) seedb = __byte_perm(tc.y, td.y, 0x5410);
           const float tvx = svt[slot].x;
           unsigned short* img2 = reinterpret_cast<unsigned short*>(g.out2) + (size_t)b * g.out2_bstride;
           const size_t pix = (size_t)yo * g.W + xo;
           const int pr = c < g.split ? pitch : (int)g.out2_pitch;
           unsigned short* op = c < g.split ? out_img + pix * g.out_pitch + c : img2 + pix * g.out2_pitch + (c - g.split);
           const uint32_t tcol = t_lane + tb * 256u + (uint32_t)(q * 4 * SW);
-          if (interior) tw_plain<T, false>(tcol, w1, seed, 0.f, 0u, yo, xo, g.H, g.W, op, pr, (size_t)g.W * pr, v);
-          else tw_plain<T, true>(tcol, w1, seed, g.vec_t != nullptr ? tvx : 0.f, col_in, yo, xo, v ? g.H : 0, g.W, op, pr, (size_t)g.W * pr);
+          if (interior) tw_plain<T, false>(tcol, w1, seeda, seedb, 0.f, 0u, yo, xo, g.H, g.W, op, pr, (size_t)g.W * pr, v);
+          else tw_plain<T, true>(tcol, w1, seeda, seedb, g.vec_t != nullptr ? tvx : 0.f, col_in, yo, xo, v ? g.H : 0, g.W, op, pr, (size_t)g.W * pr);
         }
         tc_fence_before();
         __syncwarp();
@@ -708,7 +736,7 @@ static uint32_t tw_smem(const PirPwDw* d, int nkb, int kbb, TwArgs* g) {
   if (g) g->off_w = off;
   off += (uint32_t)nkb * w_rows * kbb;
   if (g) g->off_tab = off;
-  off += slots * 48u;
+  off += slots * 64u;
   if (g) g->off_vt = off;
   off += slots * 8u;
   return off + 1024u;
