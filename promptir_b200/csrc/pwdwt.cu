@@ -271,7 +271,7 @@ __device__ __forceinline__ uint64_t tw_sdesc(uint32_t sbo_bytes, uint32_t layout
 }
 
 // Shared-memory plan (bytes from the 1024-aligned base):
-//   [x tile: 2 x NKB k-blocks x 256 rows x KBB B] [weights, resident: NKB k-blocks x 2 hp rows x KBB B] [tap table: hp x 64 B] [t: hp x 8 B]
+//   [x tile: 2 x NKB k-blocks x 256 rows x KBB B] [weights, resident: NKB k-blocks x 2 hp rows x KBB B] [tap table: hp x 80 B] [t: hp x 8 B]
 // KBB = bytes of a k-block row: 128 (64 channels, 128-byte swizzle; C = 48) or 64 (32 channels, 64-byte swizzle; C = 96 = 3 x 32, so
 // nothing is padded, two x tiles and the WHOLE weight matrix fit next to each other: the weights are fetched once per CTA and the
 // next item's tile is loaded and LayerNormed while the current one is multiplied).
@@ -300,7 +300,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int lane = threadIdx.x & 31;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  uint4* stab = reinterpret_cast<uint4*>(base_ptr + g.off_tab);          // [hp][4] x 16 B: w1[9] w2[9] seed1i seed2i bias1 bias2 0 0 | seed1L seed2L seed1R seed2R 0 0 0 0 (fp16)
+  uint4* stab = reinterpret_cast<uint4*>(base_ptr + g.off_tab);          // [hp][5] x 16 B: w1[9] w2[9] seed1i seed2i bias1 bias2 0 0 | seed1L seed2L seed1R seed2R 0 0 0 0 (fp16)
   float2* svt = reinterpret_cast<float2*>(base_ptr + g.off_vt);          // [hp] (t1, t2)
 
   if (threadIdx.x == 0) {
@@ -332,25 +332,26 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int tap = 0; tap < 9; ++tap) {
         const unsigned short a = v1 ? src[(size_t)tap * n_pre + c1] : (unsigned short)0;
         const float bf = v2 ? __half2float(__ushort_as_half(src[(size_t)tap * n_pre + c2])) * qs : 0.f;
-        tab[i * 32 + tap] = a; tab[i * 32 + 9 + tap] = __half_as_ushort(__float2half_rn(bf));
+        tab[i * 40 + tap] = a; tab[i * 40 + 9 + tap] = __half_as_ushort(__float2half_rn(bf));
         ws1 += __half2float(__ushort_as_half(a)); ws2 += bf;
         if (tap % 3 == 0) { cl1 += __half2float(__ushort_as_half(a)); cl2 += bf; }      // left column of taps (dx = -1)
         if (tap % 3 == 2) { cr1 += __half2float(__ushort_as_half(a)); cr2 += bf; }      // right column (dx = +1)
       }
       const float b1 = (g.dw_bias && v1) ? g.dw_bias[c1] : 0.f, b2 = ((g.dw_bias && v2) ? g.dw_bias[c2] : 0.f) * qs;
       const float t1 = (g.vec_t && v1) ? g.vec_t[c1] : 0.f, t2 = (g.vec_t && v2) ? g.vec_t[c2] : 0.f;
-      tab[i * 32 + 18] = __half_as_ushort(__float2half_rn(b1 + t1 * ws1));      // interior tiles: the conv of the constant t is a constant
-      tab[i * 32 + 19] = __half_as_ushort(__float2half_rn(b2 + t2 * ws2));
-      tab[i * 32 + 20] = __half_as_ushort(__float2half_rn(b1));
-      tab[i * 32 + 21] = __half_as_ushort(__float2half_rn(b2));
-      tab[i * 32 + 22] = 0; tab[i * 32 + 23] = 0;
+      tab[i * 40 + 18] = __half_as_ushort(__float2half_rn(b1 + t1 * ws1));      // interior tiles: the conv of the constant t is a constant
+      tab[i * 40 + 19] = __half_as_ushort(__float2half_rn(b2 + t2 * ws2));
+      tab[i * 40 + 20] = __half_as_ushort(__float2half_rn(b1));
+      tab[i * 40 + 21] = __half_as_ushort(__float2half_rn(b2));
+      tab[i * 40 + 22] = 0; tab[i * 40 + 23] = 0;
       // output columns whose left / right neighbour column lies outside the image (its pixels are zero padding and get no t): the
       // constant loses that column of taps.  With these seeds an x-edge patch runs the straight-line path like an interior one.
-      tab[i * 32 + 24] = __half_as_ushort(__float2half_rn(b1 + t1 * (ws1 - cl1)));
-      tab[i * 32 + 25] = __half_as_ushort(__float2half_rn(b2 + t2 * (ws2 - cl2)));
-      tab[i * 32 + 26] = __half_as_ushort(__float2half_rn(b1 + t1 * (ws1 - cr1)));
-      tab[i * 32 + 27] = __half_as_ushort(__float2half_rn(b2 + t2 * (ws2 - cr2)));
-      tab[i * 32 + 28] = 0; tab[i * 32 + 29] = 0; tab[i * 32 + 30] = 0; tab[i * 32 + 31] = 0;
+      tab[i * 40 + 24] = __half_as_ushort(__float2half_rn(b1 + t1 * (ws1 - cl1)));
+      tab[i * 40 + 25] = __half_as_ushort(__float2half_rn(b2 + t2 * (ws2 - cl2)));
+      tab[i * 40 + 26] = __half_as_ushort(__float2half_rn(b1 + t1 * (ws1 - cr1)));
+      tab[i * 40 + 27] = __half_as_ushort(__float2half_rn(b2 + t2 * (ws2 - cr2)));
+      // (slots are 80 bytes apart: with 64 the 16-byte reads of eight consecutive channels fall on two bank groups, a 4-way conflict)
+      for (int z = 28; z < 40; ++z) tab[i * 40 + z] = 0;
       svt[i] = make_float2(t1, t2);
     }
   }
@@ -572,7 +573,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int cb = 0; cb < g.n_cb; ++cb) {
         const int ch = cb * 128 + q * 32 + lane;       // table slot of this thread = its gated channel (gate)
         // taps (packed pairs), seeds
-        const uint4 ta = stab[ch * 4], tb4 = stab[ch * 4 + 1], tc = stab[ch * 4 + 2];
+        const uint4 ta = stab[ch * 5], tb4 = stab[ch * 5 + 1], tc = stab[ch * 5 + 2];
         // halves: ta = w1[0..7]; tb4 = w1[8] w2[0..6]; tc = w2[7] w2[8] s1i s2i b1 b2 0 0
         uint32_t w1[9], w2[9];
         w1[0] = tw_bcast_lo(ta.x); w1[1] = tw_bcast_hi(ta.x); w1[2] = tw_bcast_lo(ta.y); w1[3] = tw_bcast_hi(ta.y);
@@ -619,7 +620,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t seed2 = interior ? tw_bcast_hi(tc.y) : tw_bcast_hi(tc.z);
           uint32_t seed1a = seed1, seed1b = seed1, seed2a = seed2, seed2b = seed2;   // per accumulator: output pairs (0, 1) and (2, 3)
           if (xl || xr) {                                           // rare: fetched here so nothing stays live across the loop
-            const uint4 td = stab[ch * 4 + 3];
+            const uint4 td = stab[ch * 5 + 3];
             if (xl) { seed1a = __byte_perm(td.x, tc.y, 0x5410); seed2a = __byte_perm(td.x, tc.y, 0x7632); }    // (edge, interior)
             if (xr) { seed1b = __byte_perm(tc.y, td.y, 0x5410); seed2b = __byte_perm(tc.y, td.y, 0x7632); }    // (interior, edge)
           }
@@ -655,7 +656,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int yo = y0 + q * kTwRowsPerThird;
         if (q < 3 && yo < g.H) {
           const int slot = g.n_cb * 128 + lane;
-          const uint4 ta = stab[slot * 4], tb4 = stab[slot * 4 + 1], tc = stab[slot * 4 + 2], td = stab[slot * 4 + 3];
+          const uint4 ta = stab[slot * 5], tb4 = stab[slot * 5 + 1], tc = stab[slot * 5 + 2], td = stab[slot * 5 + 3];
           uint32_t w1[9];
           w1[0] = tw_bcast_lo(ta.x); w1[1] = tw_bcast_hi(ta.x); w1[2] = tw_bcast_lo(ta.y); w1[3] = tw_bcast_hi(ta.y);
           w1[4] = tw_bcast_lo(ta.z); w1[5] = tw_bcast_hi(ta.z); w1[6] = tw_bcast_lo(ta.w); w1[7] = tw_bcast_hi(ta.w);
@@ -736,7 +737,7 @@ static uint32_t tw_smem(const PirPwDw* d, int nkb, int kbb, TwArgs* g) {
   if (g) g->off_w = off;
   off += (uint32_t)nkb * w_rows * kbb;
   if (g) g->off_tab = off;
-  off += slots * 64u;
+  off += slots * 80u;
   if (g) g->off_vt = off;
   off += slots * 8u;
   return off + 1024u;
