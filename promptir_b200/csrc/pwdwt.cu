@@ -474,59 +474,78 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint8_t* a_tile = base_ptr + (size_t)ab * X_BYTES;
       tw_wait_backoff(smem_u32(&bar_afull[ab]), (itn / NA) & 1u);     // sleeps between polls: these warps run two tiles ahead and mostly wait
       if (g.ln_mode) {
-#pragma unroll 2
-        for (int r = 0; r < LNR; ++r) {
-          const int task = r * kTwLn + ct;
-          const int m = task >> 2, part = task & 3;
-          const int my = m / SW;
-          const int py = y0 - 1 + my, px = x0 - 1 + (m - my * SW);
-          const bool act = m < NPIX && py >= 0 && py < g.H && px >= 0 && px < g.W;
-          // a thread owns CPT physical 16-byte chunks of every k-block row: 2 part + (e ^ (m & 1)) of 8 (128-byte rows; the row parity
-          // keeps the quarter-warp's LDS.128 conflict free) or chunk `part` of 4 (64-byte rows)
-          constexpr int CPT = KBB / 64;
-          const int sw = KBB == 128 ? (m & 7) : ((m >> 1) & 3);               // logical chunk = physical chunk ^ sw
-          float s1 = 0.f, s2 = 0.f, s1b = 0.f, s2b = 0.f;
+        // Two tasks per thread at a time, their rows held in registers between the statistics and the normalisation: the loads of
+        // both are in flight together (in place, the compiler cannot move a task's loads above the previous task's stores) and
+        // every value is read from shared memory once.  A LayerNorm warp is latency bound (~0.1 IPC); with one task at a time the
+        // four warps needed ~12 K cycles per tile and paced the plain (qkv) kernel and the C = 48 gate.
+        constexpr int CPT = KBB / 64;                      // 16-byte chunks of a k-block row per thread
+        constexpr int NV = NKB * CPT;
+        constexpr int LNP = 2;                             // tasks in flight per thread
+#pragma unroll 1
+        for (int r = 0; r < LNR; r += LNP) {
+          uint4 v[LNP][NV];
+          int mrow[LNP], part_[LNP];
+          bool act[LNP];
 #pragma unroll
-          for (int kb = 0; kb < NKB; ++kb) {
-            if (act) {
-              const uint8_t* a_row = a_tile + (size_t)kb * A_KB + (size_t)m * KBB;
+          for (int u = 0; u < LNP; ++u) {
+            const int task = (r + u) * kTwLn + ct;
+            const int m = task >> 2, part = task & 3;
+            const int my = m / SW;
+            const int py = y0 - 1 + my, px = x0 - 1 + (m - my * SW);
+            mrow[u] = m; part_[u] = part;
+            act[u] = (r + u) < LNR && m < NPIX && py >= 0 && py < g.H && px >= 0 && px < g.W;
+            // a thread owns CPT physical 16-byte chunks of every k-block row: 2 part + (e ^ (m & 1)) of 8 (128-byte rows; the row parity
+            // keeps the quarter-warp's LDS.128 conflict free) or chunk `part` of 4 (64-byte rows)
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb)
 #pragma unroll
               for (int e = 0; e < CPT; ++e) {
                 const int j = KBB == 128 ? 2 * part + (e ^ (m & 1)) : part;
-                const uint4 v = *reinterpret_cast<const uint4*>(a_row + (j << 4));
-                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+                v[u][kb * CPT + e] = act[u] ? *reinterpret_cast<const uint4*>(a_tile + (size_t)kb * A_KB + (size_t)m * KBB + (j << 4))
+                                            : make_uint4(0u, 0u, 0u, 0u);
+              }
+          }
+          float rstd[LNP], shift[LNP];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const unsigned short lo = lo16(w4[i]), hi = hi16(w4[i]);
-                  s1 = fma16<T>(lo, T::kOne, s1);
-                  s1b = fma16<T>(hi, T::kOne, s1b);
-                  s2 = fma16<T>(lo, lo, s2);
-                  s2b = fma16<T>(hi, hi, s2b);
-                }
+          for (int u = 0; u < LNP; ++u) {
+            float s1 = 0.f, s2 = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+              const uint32_t w4[4] = {v[u][q].x, v[u][q].y, v[u][q].z, v[u][q].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const unsigned short lo = lo16(w4[i]), hi = hi16(w4[i]);
+                s1 = fma16<T>(lo, T::kOne, s1);
+                s1b = fma16<T>(hi, T::kOne, s1b);
+                s2 = fma16<T>(lo, lo, s2);
+                s2b = fma16<T>(hi, hi, s2b);
               }
             }
+            s1 += s1b; s2 += s2b;
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+            const float mu = s1 * inv_k;
+            rstd[u] = rsqrtf(fmaxf(fmaf(s2, inv_k, -mu * mu), 0.f) + 1e-5f);
+            shift[u] = g.ln_mode == 2 ? 0.f : -rstd[u] * mu;
           }
-          s1 += s1b; s2 += s2b;
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-          const float mu = s1 * inv_k;
-          const float rstd = rsqrtf(fmaxf(fmaf(s2, inv_k, -mu * mu), 0.f) + 1e-5f);
-          const float shift = g.ln_mode == 2 ? 0.f : -rstd * mu;
 #pragma unroll
-          for (int kb = 0; kb < NKB; ++kb) {
-            if (act) {
-              uint8_t* a_row = a_tile + (size_t)kb * A_KB + (size_t)m * KBB;
-              const int valid = g.C - kb * KCH;                               // the zero padding above C (last k-block) must stay zero
+          for (int u = 0; u < LNP; ++u) {
+            if (!act[u]) continue;
+            const int m = mrow[u], part = part_[u];
+            const int sw = KBB == 128 ? (m & 7) : ((m >> 1) & 3);               // logical chunk = physical chunk ^ sw
+#pragma unroll
+            for (int kb = 0; kb < NKB; ++kb) {
+              const int valid = g.C - kb * KCH;                                 // the zero padding above C (last k-block) must stay zero
 #pragma unroll
               for (int e = 0; e < CPT; ++e) {
                 const int j = KBB == 128 ? 2 * part + (e ^ (m & 1)) : part;
                 if ((j ^ sw) * 8 < valid) {
-                  uint4 v = *reinterpret_cast<const uint4*>(a_row + (j << 4));
-                  uint32_t* w4 = &v.x;
+                  uint4 o = v[u][kb * CPT + e];
+                  uint32_t* w4 = &o.x;
 #pragma unroll
                   for (int i = 0; i < 4; ++i)
-                    w4[i] = pack2<T>(fmaf(unpack_lo<T>(w4[i]), rstd, shift), fmaf(unpack_hi<T>(w4[i]), rstd, shift));
-                  *reinterpret_cast<uint4*>(a_row + (j << 4)) = v;
+                    w4[i] = pack2<T>(fmaf(unpack_lo<T>(w4[i]), rstd[u], shift[u]), fmaf(unpack_hi<T>(w4[i]), rstd[u], shift[u]));
+                  *reinterpret_cast<uint4*>(a_tile + (size_t)kb * A_KB + (size_t)m * KBB + (j << 4)) = o;
                 }
               }
             }
