@@ -480,7 +480,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // four warps needed ~12 K cycles per tile and paced the plain (qkv) kernel and the C = 48 gate.
         constexpr int CPT = KBB / 64;                      // 16-byte chunks of a k-block row per thread
         constexpr int NV = NKB * CPT;
-        constexpr int LNP = 2;                             // tasks in flight per thread
+        constexpr int LNP = KBB == 128 ? 4 : 2;              // tasks in flight per thread (C = 96: three 16-byte chunks each; four would spill)
 #pragma unroll 1
         for (int r = 0; r < LNR; r += LNP) {
           uint4 v[LNP][NV];
