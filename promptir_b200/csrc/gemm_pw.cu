@@ -40,6 +40,7 @@ struct PwArgs {
   int w_batched;
   int ln_mode;
   int has_res;
+  int res_pf;         // residual tiles prefetched into L2 ahead of the slot loads (0 = off; PIR_GEMM_RESPF)
   int rotate;         // streamed weights: per-CTA rotation of the column-chunk order (PIR_GEMM_ROTATE=0 turns it off)
   int m_tiles;        // per image
   int n_alloc;        // weight rows held per k-block: ceil(N16 / 64) * 64
@@ -51,6 +52,10 @@ struct PwArgs {
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(m), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// L2 prefetch of a tensor box (no shared memory, no completion): used to pull a residual tile towards L2 a few tiles ahead
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(m), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -322,8 +327,20 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (g.has_res) {
       const int n16 = (g.N + 15) / 16 * 16;
       uint32_t u = 0;
+      // A slab can only be requested when its staging slot is free again (two slots per epilogue group), so with ~4 us of loaded
+      // DRAM latency per request each group turned one slab around per ~5 K cycles whatever the ring depth.  The tiles this CTA will
+      // need g.res_pf iterations from now are pulled into L2 here; the slot loads then see L2 latency.  Measured (cfg2 forward): K4
+      // 2.41 -> 2.10 ms and K7 3.08 -> 3.01 ms with one tile ahead; two or more ahead, or prefetching the activation tiles as well,
+      // is slower (K7 already runs at ~90 % of the copy bandwidth: extra requests only add DRAM contention).
+      auto prefetch_tile = [&](int tp) {
+        if (tp >= total_tiles || !elect_one()) return;
+        const int b2 = tp / g.m_tiles, m2 = (tp % g.m_tiles) * kPwBlockM;
+        for (int c0 = 0; c0 < n16; c0 += 64) tma_prefetch_3d(&tmR, c0, m2, b2);
+      };
+      for (int k = 0; k < g.res_pf; ++k) prefetch_tile((int)blockIdx.x + k * (int)gridDim.x);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int b = t / g.m_tiles, m0 = (t % g.m_tiles) * kPwBlockM;
+        if (g.res_pf) prefetch_tile(t + g.res_pf * (int)gridDim.x);
         for (int ci = 0; ci < g.n_chunks; ++ci) {
           const int c = chunk_of(ci);
           const int ncols = min(g.NC, n16 - c * g.NC);
@@ -364,6 +381,8 @@ static int launch_pw(const PirGemm* d, cudaStream_t stream) {
   {
     static const int rot_env = [] { const char* e = getenv("PIR_GEMM_ROTATE"); return e ? atoi(e) : 1; }();
     g.rotate = rot_env;
+    static const int pf_env = [] { const char* e = getenv("PIR_GEMM_RESPF"); const int v = e ? atoi(e) : 1; return v < 0 ? 0 : (v > 8 ? 8 : v); }();
+    g.res_pf = g.has_res ? pf_env : 0;
   }
   g.m_tiles = (g.hw + kPwBlockM - 1) / kPwBlockM;
   g.ln_s = d->ln_s; g.vec_t = d->vec_t;
