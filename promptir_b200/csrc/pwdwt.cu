@@ -205,10 +205,11 @@ __device__ __forceinline__ void tw_subunit(uint32_t tcol, const uint32_t (&w1)[9
 
 // Plain (no gate) sub-unit of one thread and ONE accumulator: 6 halo'd rows x 6 columns of its channel -> 4 x 4 outputs of the
 // depthwise conv, stored as 16-bit.  Same structure as tw_subunit.
-template <class T, bool BORDER>
+template <class T, bool BORDER, int PITCH = 0>
 __device__ __forceinline__ void tw_plain(uint32_t tcol, const uint32_t (&w)[9], uint32_t seeda, uint32_t seedb, float tv, uint32_t col_in, int yo, int xo,
-                                         int H, int W, unsigned short* orow, int pitch, size_t row_stride, bool st_ok = true) {
+                                         int H, int W, unsigned short* orow, int pitch_rt, size_t row_stride, bool st_ok = true) {
   constexpr int SW = kTwSW;
+  const int pitch = PITCH ? PITCH : pitch_rt;           // compile-time pixel pitch: the four pixel stores of a row share one address
   uint32_t a[3][2];
   uint32_t r[8];
   tw_ld8(tcol, r);
@@ -652,11 +653,26 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             // channels past the end of the tensor (last block) are skipped per warp; a partially valid warp masks its stores by
             // pretending the row is outside the image (H = 0 on the border path)
             if (any_a) {
-              if (interior && all_a) tw_plain<T, false>(tcol, w1, seed1a, seed1b, 0.f, 0u, yo, xo, g.H, g.W, orow, pitch1, row_stride1);
+              if (interior && all_a) {
+                // the networks' two output tensors have pixel pitches PITCH (q|k) and PITCH / 2 (v), a warp's channels go to one of them
+                if constexpr (PITCH != 0) {
+                  if (cb * 256 + q * 32 < g.split) tw_plain<T, false, PITCH>(tcol, w1, seed1a, seed1b, 0.f, 0u, yo, xo, g.H, g.W, orow, pitch1, row_stride1);
+                  else tw_plain<T, false, PITCH / 2>(tcol, w1, seed1a, seed1b, 0.f, 0u, yo, xo, g.H, g.W, orow, pitch1, row_stride1);
+                } else {
+                  tw_plain<T, false>(tcol, w1, seed1a, seed1b, 0.f, 0u, yo, xo, g.H, g.W, orow, pitch1, row_stride1);
+                }
+              }
               else tw_plain<T, true>(tcol, w1, seed1a, seed1b, (add_t && !interior) ? tv.x : 0.f, interior ? 0x3fu : col_in, yo, xo, va ? g.H : 0, g.W, orow, pitch1, row_stride1);
             }
             if (any_b) {
-              if (interior && all_b) tw_plain<T, false>(tcol + 128u, w2, seed2a, seed2b, 0.f, 0u, yo, xo, g.H, g.W, orow2, pitch2, row_stride2);
+              if (interior && all_b) {
+                if constexpr (PITCH != 0) {
+                  if (cb * 256 + 128 + q * 32 < g.split) tw_plain<T, false, PITCH>(tcol + 128u, w2, seed2a, seed2b, 0.f, 0u, yo, xo, g.H, g.W, orow2, pitch2, row_stride2);
+                  else tw_plain<T, false, PITCH / 2>(tcol + 128u, w2, seed2a, seed2b, 0.f, 0u, yo, xo, g.H, g.W, orow2, pitch2, row_stride2);
+                } else {
+                  tw_plain<T, false>(tcol + 128u, w2, seed2a, seed2b, 0.f, 0u, yo, xo, g.H, g.W, orow2, pitch2, row_stride2);
+                }
+              }
               else tw_plain<T, true>(tcol + 128u, w2, seed2a, seed2b, (add_t && !interior) ? tv.y : 0.f, interior ? 0x3fu : col_in, yo, xo, vb ? g.H : 0, g.W, orow2, pitch2, row_stride2);
             }
           }
@@ -695,7 +711,11 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int pr = c < g.split ? pitch : (int)g.out2_pitch;
           unsigned short* op = c < g.split ? out_img + pix * g.out_pitch + c : img2 + pix * g.out2_pitch + (c - g.split);
           const uint32_t tcol = t_lane + tb * 256u + (uint32_t)(q * 4 * SW);
-          if (interior) tw_plain<T, false>(tcol, w1, seeda, seedb, 0.f, 0u, yo, xo, g.H, g.W, op, pr, (size_t)g.W * pr, v);
+          if (interior) {
+            // dense outputs: the replicated channels (the last of the 3 C) all belong to v
+            if constexpr (PITCH != 0) tw_plain<T, false, PITCH / 2>(tcol, w1, seeda, seedb, 0.f, 0u, yo, xo, g.H, g.W, op, pr, (size_t)g.W * pr, v);
+            else tw_plain<T, false>(tcol, w1, seeda, seedb, 0.f, 0u, yo, xo, g.H, g.W, op, pr, (size_t)g.W * pr, v);
+          }
           else tw_plain<T, true>(tcol, w1, seeda, seedb, g.vec_t != nullptr ? tvx : 0.f, col_in, yo, xo, v ? g.H : 0, g.W, op, pr, (size_t)g.W * pr);
         }
         tc_fence_before();
@@ -823,8 +843,12 @@ static int tw_run(const PirPwDw* d, cudaStream_t stream) {
     if (int e = pir_make_tmap(&tmWr, dt, 2, d->w, dims, strides, box, sw)) return e;
   }
   if (!gate) {
-    if (nkb == 1) return tw_launch<T, 1, 128, false, false, 0>(g, smem, tmA, tmW, tmWr, stream);
-    return tw_launch<T, 3, 64, false, false, 0>(g, smem, tmA, tmW, tmWr, stream);
+    // dense q|k (pitch 2 C) and v (pitch C) tensors: those pitches are compiled in (store addresses become immediates)
+    const bool dense2 = two && d->split == 2 * d->C && d->out_pitch == 2 * d->C && d->out2_pitch == d->C && d->N == 3 * d->C;
+    if (nkb == 1) return dense2 && d->C == 48 ? tw_launch<T, 1, 128, false, false, 96>(g, smem, tmA, tmW, tmWr, stream)
+                                              : tw_launch<T, 1, 128, false, false, 0>(g, smem, tmA, tmW, tmWr, stream);
+    return dense2 && d->C == 96 ? tw_launch<T, 3, 64, false, false, 192>(g, smem, tmA, tmW, tmWr, stream)
+                                : tw_launch<T, 3, 64, false, false, 0>(g, smem, tmA, tmW, tmWr, stream);
   }
   // fp32 erf-GELU gate for fp16 storage only on request (PIR_PWDW_GATE32=1, A/B): the packed fp16 gate measured 8.3e-4 against
   // 9.0e-4 max-abs on the cfg2 forward and is 0.75 ms per step faster
