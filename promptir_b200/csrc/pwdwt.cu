@@ -91,6 +91,9 @@ __device__ __forceinline__ float2 tw_h2f2(uint32_t v) { return __half22float2(*r
 #ifndef PIR_TW_PARK
 #define PIR_TW_PARK 1
 #endif
+#ifndef PIR_TW_LAZY_NS
+#define PIR_TW_LAZY_NS 400
+#endif
 // Waits of the producer / issuer / LayerNorm warps (mostly idle) and of the stencil warps on a full accumulator: parked in the
 // mbarrier unit (try_wait with a suspend-time hint) instead of polling, so a waiting warp costs no issue slots and wakes when the
 // phase completes rather than at the next poll.
@@ -100,6 +103,10 @@ __device__ __forceinline__ void tw_wait_backoff(uint32_t bar, uint32_t parity) {
 #else
   while (!mbar_try_wait(bar, parity)) __nanosleep(40);
 #endif
+}
+// latency-tolerant waits (TMA producer on a free tile buffer, LayerNorm warps on an arrived tile): poll rarely
+__device__ __forceinline__ void tw_wait_lazy(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(PIR_TW_LAZY_NS);
 }
 __device__ __forceinline__ void tw_wait_full(uint32_t bar, uint32_t parity) {
 #if PIR_TW_PARK
@@ -388,7 +395,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int b, x0, y0;
       item_geo(item, b, x0, y0);
       const uint32_t ab = it % NA;
-      tw_wait_backoff(smem_u32(&bar_aempty[ab]), ((it / NA) & 1u) ^ 1u);
+      tw_wait_lazy(smem_u32(&bar_aempty[ab]), ((it / NA) & 1u) ^ 1u);
       if (elect_one()) {
         const uint32_t full = smem_u32(&bar_afull[ab]);
         mbar_expect_tx(full, (uint32_t)NKB * (uint32_t)(NPIX * KBB));
@@ -473,7 +480,7 @@ pwdwt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     auto layernorm_tile = [&](int x0, int y0, uint32_t itn) {
       const uint32_t ab = itn % NA;
       uint8_t* a_tile = base_ptr + (size_t)ab * X_BYTES;
-      tw_wait_backoff(smem_u32(&bar_afull[ab]), (itn / NA) & 1u);     // sleeps between polls: these warps run two tiles ahead and mostly wait
+      tw_wait_lazy(smem_u32(&bar_afull[ab]), (itn / NA) & 1u);        // sleeps between polls: these warps run a tile ahead and mostly wait
       if (g.ln_mode) {
         // Two tasks per thread at a time, their rows held in registers between the statistics and the normalisation: the loads of
         // both are in flight together (in place, the compiler cannot move a task's loads above the previous task's stores) and
