@@ -62,6 +62,11 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// This kernel is memory bound: its warps mostly wait, and a polling loop is pure power (the cfg2 step runs into the software power
+// cap).  Latency-tolerant waits (TMA producer, residual prefetch) poll every 256 ns, the others every 32 ns.
+__device__ __forceinline__ void pw_wait_lazy(uint32_t bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) __nanosleep(256); }
+__device__ __forceinline__ void pw_wait_nap(uint32_t bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) __nanosleep(32); }
+
 template <class T>
 __global__ void __launch_bounds__(kPwThreads, 1)
 gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -134,7 +139,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ncols = min(g.NC, ((g.N + 15) / 16 * 16) - c * g.NC);
         const int bboxes = g.resident ? 0 : (ncols + 63) / 64;
         for (int kb = 0; kb < g.nkb; ++kb) {
-          mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
+          pw_wait_lazy(smem_u32(&bar_empty[stage]), phase ^ 1u);
           if (elect_one()) {
             const uint32_t full = smem_u32(&bar_full[stage]);
             const uint32_t dst = ring + (uint32_t)stage * stage_bytes;
@@ -159,11 +164,11 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t buf = q & 1u;
         const int ncols = min(g.NC, ((g.N + 15) / 16 * 16) - c * g.NC);
         const uint32_t idesc = make_idesc_f16(T::kFmt, kPwBlockM, ncols, 0, 0);
-        mbar_wait(smem_u32(&bar_tempty[buf]), ((q >> 1) & 1u) ^ 1u);
+        pw_wait_nap(smem_u32(&bar_tempty[buf]), ((q >> 1) & 1u) ^ 1u);
         tc_fence_after();
         int st = stage; uint32_t ph = phase;
         for (int kb = 0; kb < g.nkb; ++kb) {
-          mbar_wait(smem_u32(&bar_full[st]), ph);
+          pw_wait_nap(smem_u32(&bar_full[st]), ph);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_src = ring + (uint32_t)st * stage_bytes;
@@ -194,7 +199,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int reps = g.resident ? 1 : g.n_chunks;
         for (int c = 0; c < reps; ++c) {
           for (int kb = 0; kb < g.nkb; ++kb) {
-            mbar_wait(smem_u32(&bar_full[stage]), phase);
+            pw_wait_nap(smem_u32(&bar_full[stage]), phase);
             if (c == 0) {
               const uint8_t* a_src = base_ptr + g.off_ring + (size_t)stage * stage_bytes + (size_t)row * 128;
 #pragma unroll
@@ -218,7 +223,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float mu = s1 * inv_k;
             const float rstd = rsqrtf(fmaxf(fmaf(s2, inv_k, -mu * mu), 0.f) + 1e-5f);
             const uint32_t mb = ti & 1u;
-            mbar_wait(smem_u32(&bar_sempty[mb]), ((ti >> 1) & 1u) ^ 1u);
+            pw_wait_nap(smem_u32(&bar_sempty[mb]), ((ti >> 1) & 1u) ^ 1u);
             sstats[mb * 128 + row] = make_float2(g.ln_mode == 2 ? 0.f : -rstd * mu, rstd);
             mbar_arrive(smem_u32(&bar_sfull[mb]));          // release semantics order the store above
           }
@@ -239,7 +244,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float a_scale = 1.f, a_shift = 0.f;
       if (g.ln_mode) {
         const uint32_t mb = ti & 1u;
-        mbar_wait(smem_u32(&bar_sfull[mb]), (ti >> 1) & 1u);
+        pw_wait_nap(smem_u32(&bar_sfull[mb]), (ti >> 1) & 1u);
         const float2 st = sstats[mb * 128 + row];
         a_shift = st.x; a_scale = st.y;
         mbar_arrive(smem_u32(&bar_sempty[mb]));
@@ -250,7 +255,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ncols = min(g.NC, n16 - c * g.NC);
         // both groups observe every chunk (even one whose slabs all belong to the other group) so neither can run
         // more than one mbarrier phase ahead on bar_tempty
-        mbar_wait(smem_u32(&bar_tfull[buf]), (q >> 1) & 1u);
+        pw_wait_nap(smem_u32(&bar_tfull[buf]), (q >> 1) & 1u);
         tc_fence_after();
         for (int s0 = 0; s0 < ncols; s0 += 64, ++u) {
           if ((int)(u & 1u) != grp) continue;
@@ -275,8 +280,8 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          if (g.has_res) mbar_wait(smem_u32(&bar_slot_full[slot]), sph);
-          else mbar_wait(smem_u32(&bar_slot_empty[slot]), sph ^ 1u);
+          if (g.has_res) pw_wait_nap(smem_u32(&bar_slot_full[slot]), sph);
+          else pw_wait_nap(smem_u32(&bar_slot_empty[slot]), sph ^ 1u);
           tmem_ld_wait();
           uint8_t* srow = base_ptr + g.off_slots + (size_t)slot * kPwSlab + (size_t)row * 128;
           const float4* sv4 = reinterpret_cast<const float4*>(svec + ncol0);
@@ -347,7 +352,7 @@ gemm_pw_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int s0 = 0; s0 < ncols; s0 += 64, ++u) {
             const uint32_t grp = u & 1u, j = u >> 1;
             const uint32_t slot = grp * 2u + (j & 1u), sph = (j >> 1) & 1u;
-            mbar_wait(smem_u32(&bar_slot_empty[slot]), sph ^ 1u);
+            pw_wait_lazy(smem_u32(&bar_slot_empty[slot]), sph ^ 1u);
             if (elect_one()) {
               const uint32_t full = smem_u32(&bar_slot_full[slot]);
               mbar_expect_tx(full, kPwSlab);
