@@ -13,7 +13,8 @@ Workload (config.workload): BASELINE.json configs[1] -- all-in-one inference on 
   cpu_baseline : the reference's own fp32 PyTorch forward (unmodified net/model.py from baseline/_ref; oracle port if absent) on the
                  host cores over the SAME 16 images; its outputs are the parity reference of every image that was timed
   parity / alt : both 16-bit storage types are timed and checked; `dtype` is the one that meets the 2e-3 / 0.02 dB contract
-  configs : sub-records for BASELINE configs[2..4]: 4K tiles, the training step (AdamW + NCCL all-reduce inside), PromptXRestormer
+  configs : sub-records for BASELINE configs[2..4]: 4K tiles, the training step (AdamW + NCCL all-reduce inside), PromptXRestormer;
+            reference_eager_b200 = the unmodified reference module as PyTorch eager (cuDNN / cuBLAS) on the same B200, headline workload
 `--impl reference` times that CPU path alone (rank 0 only under torchrun) and prints the reference-arm line.
 Multi-GPU: images are independent, so the batch is sharded by rank with no data-path collective (weak scaling).
 """
@@ -352,7 +353,8 @@ def run_ours(args):
         import subbench
         for name, fn in (("tiles_4k", lambda: subbench.bench_tiles(dev, world, rank, DT[head])),
                          ("train_step", lambda: subbench.bench_train(dev, world, rank, torch.bfloat16)),
-                         ("xrestormer", lambda: subbench.bench_xrestormer(dev, world, rank, DT[head]))):
+                         ("xrestormer", lambda: subbench.bench_xrestormer(dev, world, rank, DT[head])),
+                         ("reference_eager_b200", lambda: subbench.bench_reference_eager(dev, world, rank))):
             try:
                 subs[name] = fn()
             except Exception as e:                       # a sub-record must never take the headline line down
@@ -423,7 +425,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-configs", action="store_true", help="skip the tiles_4k / train_step / xrestormer sub-records")
+    ap.add_argument("--no-configs", action="store_true", help="skip the tiles_4k / train_step / xrestormer / reference_eager_b200 sub-records")
     args = ap.parse_args()
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.gpus == 1:
         quiet_stdout()

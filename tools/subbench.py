@@ -6,6 +6,8 @@
                             + torch.optim.AdamW(fused=True).step() + the pir_repack refresh of the 16-bit weight caches;
                             128x128 patches, batch 32 per GPU
     xrestormer  configs[4]  PromptXRestormer inference at 512x512, one image per GPU
+    reference_eager_b200    the unmodified reference module as PyTorch eager on the same B200, headline workload (BASELINE.md section 3;
+                            rank 0, none of this library's kernels on that path)
 Every function returns a dict with ms_per_step (CUDA events, max over ranks), the whole-job value and a parity field measured
 against the CPU oracle on a bounded input (rank 0).  They are also what tools/bench_*.py print on their own.
 """
@@ -230,3 +232,164 @@ def bench_xrestormer(dev, world: int, rank: int, dtype: torch.dtype, steps: int 
             "metric": "xrestormer_fwd_megapixels_per_sec", "value": world * batch * side * side / 1e6 / ms * 1e3, "unit": "MP/s", "ms_per_step": ms,
             "steps": steps, "warmup": warmup, "dtype": str(dtype).split(".")[-1], "collective": "none", "gpu_launches_per_step": launches,
             "kernels": kernels, "parity": parity}
+
+
+# ----------------------------------------------------------------------------------------------------
+def bench_reference_eager(dev, world: int, rank: int, steps: int = 3, warmup: int = 2, batch: int = 16, side: int = 256) -> dict:
+    """BASELINE.md section 3 "same-box GPU comparison": the UNMODIFIED reference module (net/model.py, copied to the git-ignored
+    baseline/_ref/ by __graft_entry__.build(); it travels with the gpurun snapshot) run as PyTorch eager ops -- cuDNN / cuBLAS / ATen --
+    on the same B200 on the headline workload (BASELINE.json configs[1]), CUDA-event timed.  None of this library's kernels are on that
+    path.  Rank 0 only (the comparison is per GPU).  Also reports how far the reference's own bf16 run lands from its own fp32 run on
+    this batch: the context for the 2e-3 contract of the 16-bit builds."""
+    if rank != 0:
+        return {"skipped": "rank 0 only"}
+    path = os.path.join(ROOT, "baseline", "_ref", "net", "model.py")
+    if not os.path.exists(path):
+        return {"unavailable": "baseline/_ref/net/model.py absent (__graft_entry__.build() copies it where /root/reference exists)"}
+    import importlib.util
+    from promptir_b200 import synth
+    spec = importlib.util.spec_from_file_location("_promptir_reference_model_gpu", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(0)
+    ref = mod.PromptIR(decoder=True).eval().to(dev)
+    x = synth.synthetic_batch(batch, side, side, seed=1)[0].to(dev)
+    mp = batch * side * side / 1e6
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"ms_per_step": round(ms, 3), "MP_per_s": round(mp / ms * 1e3, 3)}
+
+    out = {"workload": f"unmodified reference net/model.py PromptIR(decoder=True), PyTorch {torch.__version__} eager on the same B200, batch {batch} of "
+                       f"{side}x{side} (BASELINE.json configs[1]), {warmup} warm-up + {steps} timed forwards per variant, CUDA events",
+           "unit": "MP/s", "variants": {}}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        with torch.no_grad():
+            out["variants"]["fp32_torch_defaults"] = timed(lambda: ref(x))         # the stock code path: what `python demo.py` runs
+            y32 = ref(x).clamp(0, 1)
+            torch.backends.cudnn.allow_tf32 = True
+            torch.backends.cuda.matmul.allow_tf32 = True
+            out["variants"]["fp32_tf32"] = timed(lambda: ref(x))
+            ref = ref.bfloat16()
+            xb = x.bfloat16()
+            out["variants"]["bf16"] = timed(lambda: ref(xb))
+            y16 = ref(xb).float().clamp(0, 1)
+            out["reference_bf16_vs_its_fp32"] = {"max_abs_clamped": float((y16 - y32).abs().max()), "images": batch,
+                                                 "note": "the reference's own bf16 eager run against its own fp32 run, same weights and inputs"}
+            try:                                         # optional variant: must not take the record down
+                for p in ref.parameters():
+                    if p.dim() == 4:                     # (prompt_param is 5-D: Module.to(memory_format=...) would reject it)
+                        p.data = p.data.contiguous(memory_format=torch.channels_last)
+                xcl = xb.contiguous(memory_format=torch.channels_last)
+                out["variants"]["bf16_channels_last"] = timed(lambda: ref(xcl))
+            except Exception as e:
+                out["bf16_channels_last_error"] = f"{type(e).__name__}: {e}"
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    best = max(out["variants"].items(), key=lambda kv: kv[1]["MP_per_s"])
+    out["best_variant"], out["value"], out["ms_per_step"] = best[0], best[1]["MP_per_s"], best[1]["ms_per_step"]
+    del ref
+    torch.cuda.empty_cache()
+    for name, fn in (("train_step", lambda: _reference_eager_train(mod, dev)), ("xrestormer", lambda: _reference_eager_x(dev))):
+        try:                                             # comparators for the train_step / xrestormer sub-records; optional
+            out[name] = fn()
+        except Exception as e:
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+    return out
+
+
+def _timed_eager(fn, steps: int, warmup: int) -> float:
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def _reference_eager_train(mod, dev, steps: int = 2, warmup: int = 1, batch: int = 32, side: int = 128) -> dict:
+    """train.py:37-56 with the unmodified reference module on the same B200: forward + L1 + autograd backward + AdamW step
+    (BASELINE.json configs[3] per-GPU work; one GPU, so no all-reduce)."""
+    from promptir_b200 import synth
+    torch.manual_seed(0)
+    ref = mod.PromptIR(decoder=True).train().to(dev)
+    opt = torch.optim.AdamW(ref.parameters(), lr=2e-4)
+    x, y = synth.synthetic_batch(batch, side, side, seed=1)
+    x, y = x.to(dev), y.to(dev)
+    mp = batch * side * side / 1e6
+
+    def step(autocast: bool = False):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out = ref(x)
+        F.l1_loss(out.float(), y).backward()
+        opt.step()
+    res = {"workload": f"unmodified reference PromptIR(decoder=True): forward + L1 + autograd backward + torch.optim.AdamW.step(), batch {batch} of "
+                       f"{side}x{side}, one B200, {warmup} warm-up + {steps} timed steps per variant", "unit": "MP/s", "variants": {}}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, tf32, ac in (("fp32_torch_defaults", None, False), ("fp32_tf32", True, False), ("bf16_autocast", True, True)):
+            if tf32:
+                torch.backends.cudnn.allow_tf32 = True
+                torch.backends.cuda.matmul.allow_tf32 = True
+            ms = _timed_eager(lambda: step(ac), steps, warmup)
+            res["variants"][name] = {"ms_per_step": round(ms, 3), "MP_per_s": round(mp / ms * 1e3, 3)}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    best = max(res["variants"].items(), key=lambda kv: kv[1]["MP_per_s"])
+    res["best_variant"], res["value"], res["ms_per_step"] = best[0], best[1]["MP_per_s"], best[1]["ms_per_step"]
+    return res
+
+
+def _reference_eager_x(dev, steps: int = 3, warmup: int = 2, batch: int = 1, side: int = 512) -> dict:
+    """The unmodified reference net/prompt_xrestormer.py (torchstat, an import-only dependency, stubbed) on the same B200:
+    BASELINE.json configs[4] per-GPU work (one 512x512 image)."""
+    import importlib.util
+    import types
+    from promptir_b200 import synth
+    path = os.path.join(ROOT, "baseline", "_ref", "net", "prompt_xrestormer.py")
+    if not os.path.exists(path):
+        return {"unavailable": "baseline/_ref/net/prompt_xrestormer.py absent"}
+    sys.modules.setdefault("torchstat", types.SimpleNamespace(stat=None))
+    spec = importlib.util.spec_from_file_location("_promptir_reference_xrestormer_gpu", path)
+    xmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(xmod)
+    torch.manual_seed(0)
+    ref = xmod.PromptXRestormer().eval().to(dev)
+    x = synth.synthetic_batch(batch, side, side, seed=1)[0].to(dev)
+    mp = batch * side * side / 1e6
+    res = {"workload": f"unmodified reference PromptXRestormer() forward, batch {batch} of {side}x{side}, one B200, {warmup} warm-up + {steps} timed "
+                       "forwards per variant", "unit": "MP/s", "variants": {}}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        with torch.no_grad():
+            ms = _timed_eager(lambda: ref(x), steps, warmup)
+            res["variants"]["fp32_torch_defaults"] = {"ms_per_step": round(ms, 3), "MP_per_s": round(mp / ms * 1e3, 3)}
+            torch.backends.cudnn.allow_tf32 = True
+            torch.backends.cuda.matmul.allow_tf32 = True
+            ms = _timed_eager(lambda: ref(x), steps, warmup)
+            res["variants"]["fp32_tf32"] = {"ms_per_step": round(ms, 3), "MP_per_s": round(mp / ms * 1e3, 3)}
+            ref = ref.bfloat16()
+            xb = x.bfloat16()
+            ms = _timed_eager(lambda: ref(xb), steps, warmup)
+            res["variants"]["bf16"] = {"ms_per_step": round(ms, 3), "MP_per_s": round(mp / ms * 1e3, 3)}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    best = max(res["variants"].items(), key=lambda kv: kv[1]["MP_per_s"])
+    res["best_variant"], res["value"], res["ms_per_step"] = best[0], best[1]["MP_per_s"], best[1]["ms_per_step"]
+    return res
