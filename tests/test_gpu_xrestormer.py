@@ -3,7 +3,9 @@ specification, the XEngine program op by op, and the whole forward against the g
 Tolerances, stated here (the north star fixes 2e-3 / 0.02 dB for PromptIR only): this network has 200 residual sub-layers against
 PromptIR's 94 (four per block, plus three 160/320/704-wide prompt blocks), so 16-bit rounding accumulates further:
 fp16 max-abs <= 4e-3 on clamp(out,0,1) vs the fp32 reference (measured 2.2e-3..2.8e-3), bf16 <= 3e-2 (measured 1.8e-2..1.9e-2),
-dPSNR <= 0.02 dB for both (measured <= 0.0023 dB)."""
+dPSNR <= 0.02 dB for both (measured <= 0.0023 dB).  The limits are justified by the 16-bit-reference test below: the reference
+network itself, executed by PyTorch eager in fp16 / bf16 on the same GPU, is 4.3e-3..1.8e-2 / 1.8e-2..2.2e-2 from its fp32 result, and
+this build has to be at least that close (test_16bit_build_is_as_close_to_fp32_as_the_reference_run_in_16bit)."""
 from __future__ import annotations
 
 import os
@@ -106,6 +108,43 @@ def test_forward_matches_reference_golden(model, golden_dir, dt, case, seed):
     dpsnr = abs(O.psnr(y.cpu(), clean) - O.psnr(yref.cpu(), clean))
     print(f"[x parity] {case} {dt}: max-abs(clamped) {err:.3e} raw {(y - yref).abs().max().item():.3e} dPSNR {dpsnr:.4f} dB")
     assert err <= MAXABS[dt] and dpsnr <= 0.02
+
+
+def _errors_vs_16bit_reference(model, dt, x):
+    """-> (max-abs, rms) of this build and of the reference algorithm executed with `dt` tensors by PyTorch eager on the same GPU,
+    both against the fp32 run of the reference algorithm (clamped max-abs, raw rms)."""
+    from oracle import xrestormer_oracle as XO
+    sd32 = {k: v.detach().to(DEV) for k, v in model.state_dict().items()}
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref32 = XO.xrestormer_forward(sd32, x.to(DEV)).float()
+            ref16 = XO.xrestormer_forward({k: v.to(dt) for k, v in sd32.items()}, x.to(DEV).to(dt)).float()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    model.compute_dtype = dt
+    with torch.no_grad():
+        got = model(x.to(DEV)).float()
+    ours = float((got.clamp(0, 1) - ref32.clamp(0, 1)).abs().max()), float((got - ref32).pow(2).mean().sqrt())
+    eager = float((ref16.clamp(0, 1) - ref32.clamp(0, 1)).abs().max()), float((ref16 - ref32).pow(2).mean().sqrt())
+    return ours, eager
+
+
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_16bit_build_is_as_close_to_fp32_as_the_reference_run_in_16bit(model, dt):
+    """Why the limits above are 4e-3 / 3e-2 and not PromptIR's 2e-3 (the fair oracle for a 16-bit build is the
+    reference executed in that type on the same GPU): the reference network itself, run by PyTorch eager with fp16 / bf16 tensors,
+    lands this far from its own fp32 result.  This build (16-bit storage, fp32 accumulation, fp32 LayerNorm / softmax statistics) must
+    not be further away than that, in rms over the image (5 % slack for the eager side's algorithm choices) and in max-abs
+    (single-pixel statistic: 25 % slack).  Measured on B200: fp16 this build 2.3e-3 / 2.6e-3 max-abs (rms 5.6e-4 / 5.9e-4) against
+    1.8e-2 / 4.3e-3 (rms 3.6e-3 / 1.0e-3) for the reference in fp16 eager; bf16 1.6e-2 / 1.9e-2 (rms 4.7e-3 / 4.8e-3) against
+    1.8e-2 / 2.2e-2 (rms 5.1e-3 / 5.2e-3)."""
+    for shape, seed in (((2, 64, 64), 5), ((1, 128, 128), 6)):
+        x, _ = O.synthetic_batch(*shape, seed=seed)
+        (err_ours, rms_ours), (err_eager, rms_eager) = _errors_vs_16bit_reference(model, dt, x)
+        print(f"[x 16-bit] {dt} {shape}: this build max-abs {err_ours:.3e} rms {rms_ours:.3e}; reference in {dt} eager max-abs {err_eager:.3e} rms {rms_eager:.3e}")
+        assert rms_ours <= 1.05 * rms_eager and err_ours <= 1.25 * err_eager
 
 
 def test_errors_are_loud(model):
