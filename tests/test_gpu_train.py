@@ -192,6 +192,49 @@ def test_loss_backward_matches_oracle_autograd(dt, per_lim, cos_lim):
         assert cos >= cos_lim and worst[0] <= per_lim, (cos, worst)
 
 
+def _grad_errors(grads, ref):
+    """flat relative L2 error, cosine and the worst non-negligible tensor of {name: gradient} against the fp32 reference gradients."""
+    big = 1e-3 * max(t.norm().item() for t in ref.values() if t is not None)
+    flat_g, flat_r, worst = [], [], (0.0, "")
+    for n, r in ref.items():
+        if r is None or grads.get(n) is None:
+            continue
+        g = grads[n].detach().cpu().float()
+        if r.norm().item() > big:
+            worst = max(worst, (((g - r).norm() / r.norm()).item(), n))
+        flat_g.append(g.reshape(-1))
+        flat_r.append(r.reshape(-1))
+    fg, fr = torch.cat(flat_g), torch.cat(flat_r)
+    return ((fg - fr).norm() / fr.norm()).item(), torch.nn.functional.cosine_similarity(fg, fr, dim=0).item(), worst
+
+
+def test_bf16_gradients_are_as_close_to_fp32_as_the_reference_trained_in_bf16():
+    """The limits of the test above (worst tensor 8 %) against what the reference itself delivers when its training step runs in bf16
+    on the same GPU: autograd of the reference algorithm with bf16 parameters and activations, and under
+    torch.autocast(bfloat16) with fp32 parameters, both compared with fp32 autograd.  This library's bf16 training path (bf16 storage,
+    fp32 accumulation, fp32 weight gradients) must not be further from fp32 than either of them."""
+    m = perturbed_model(seed=1).to(DEV).train()
+    m.compute_dtype = torch.bfloat16
+    x, clean = O.synthetic_batch(2, 64, 64, seed=7)
+    _, ref = _oracle_grads(m, x, clean)
+    xd, cd = x.to(DEV), clean.to(DEV)
+    m.zero_grad(set_to_none=True)
+    torch.nn.functional.l1_loss(m(xd), cd).backward()
+    ours = _grad_errors({n: p.grad for n, p in m.named_parameters()}, ref)
+    sd16 = {k: v.detach().to(torch.bfloat16).requires_grad_(True) for k, v in m.state_dict().items()}
+    torch.nn.functional.l1_loss(O.promptir_forward(sd16, xd.bfloat16()).float(), cd).backward()
+    eager16 = _grad_errors({k: v.grad for k, v in sd16.items()}, ref)
+    sd32 = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = O.promptir_forward(sd32, xd)
+    torch.nn.functional.l1_loss(out.float(), cd).backward()
+    autocast = _grad_errors({k: v.grad for k, v in sd32.items()}, ref)
+    for name, (rel, cos, worst) in (("this build bf16", ours), ("reference all-bf16 autograd", eager16), ("reference bf16 autocast", autocast)):
+        print(f"[train 16-bit] {name}: flat-grad rel-L2 {rel:.4f} cos {cos:.6f} worst tensor {worst[1]} {worst[0]:.4f}")
+    # measured on B200: this build rel-L2 0.53 % (worst tensor 4.7 %), all-bf16 autograd 1.34 % (6.2 %), bf16 autocast 0.99 % (7.3 %)
+    assert ours[0] <= eager16[0] and ours[0] <= autocast[0] and ours[2][0] <= 1.25 * eager16[2][0]
+
+
 def test_optimizer_step_refreshes_packed_weights():
     """AdamW updates the fp32 parameters in place (train.py:52-56); the next forward (training or inference program) must see them."""
     m = perturbed_model(seed=1).to(DEV).train()
