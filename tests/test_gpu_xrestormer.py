@@ -215,3 +215,47 @@ def test_x_loss_backward_matches_oracle_autograd(dt, per_lim, cos_lim):
     print(f"[x train parity] {dt}: loss {loss.item():.5f} (oracle {ref_loss.item():.5f}) flat-grad cos {cos:.6f} "
           f"rel-L2 {((fg - fr).norm() / fr.norm()).item():.4f} worst tensor {worst[1]} {worst[0]:.4f}")
     assert cos >= cos_lim and worst[0] <= per_lim, (cos, worst)
+
+
+def test_x_bf16_gradients_are_as_close_to_fp32_as_the_reference_trained_in_bf16():
+    """The 10 % per-tensor limit of the test above against what autograd of the reference algorithm delivers in bf16 on the same GPU
+    (all-bf16 tensors, and torch.autocast(bfloat16) with fp32 parameters), all three compared with fp32 autograd of the CPU oracle:
+    this build's bf16 training path has to be in the same range -- flat-gradient relative L2 error within 1.5x, worst tensor within
+    2x of the reference's own bf16 autograd (on this small network the all-bf16 run is already within a few per cent of fp32)."""
+    from oracle import xrestormer_oracle as XO
+    kw = dict(num_blocks=(1, 1, 1, 2), num_refinement_blocks=1)
+    m = _small_x_model(seed=1).to(DEV).train()
+    m.compute_dtype = torch.bfloat16
+    x, clean = O.synthetic_batch(1, 64, 64, seed=7)
+    xd, cd = x.to(DEV), clean.to(DEV)
+    l1 = torch.nn.functional.l1_loss
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    l1(XO.xrestormer_forward(sd, x, **kw), clean).backward()
+    ref = {k: v.grad for k, v in sd.items()}
+    gmax = max(r.norm().item() for r in ref.values())
+
+    def errors(grads):
+        fg, fr, worst = [], [], 0.0
+        for n, g in grads.items():
+            g, r = g.detach().cpu().float(), ref[n]
+            if r.norm().item() > 1e-3 * gmax:
+                worst = max(worst, ((g - r).norm() / r.norm()).item())
+            fg.append(g.reshape(-1))
+            fr.append(r.reshape(-1))
+        fg, fr = torch.cat(fg), torch.cat(fr)
+        return ((fg - fr).norm() / fr.norm()).item(), worst
+
+    l1(m(xd), cd).backward()
+    ours = errors({n: p.grad for n, p in m.named_parameters()})
+    sd16 = {k: v.detach().to(torch.bfloat16).requires_grad_(True) for k, v in m.state_dict().items()}
+    l1(XO.xrestormer_forward(sd16, xd.bfloat16(), **kw).float(), cd).backward()
+    eager16 = errors({k: v.grad for k, v in sd16.items()})
+    sd32 = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = XO.xrestormer_forward(sd32, xd, **kw)
+    l1(out.float(), cd).backward()
+    autocast = errors({k: v.grad for k, v in sd32.items()})
+    for name, (rel, worst) in (("this build bf16", ours), ("reference all-bf16 autograd", eager16), ("reference bf16 autocast", autocast)):
+        print(f"[x train 16-bit] {name}: flat-grad rel-L2 {rel:.4f} worst tensor {worst:.4f}")
+    # measured on B200: this build 0.44 % flat / 4.5 % worst tensor; all-bf16 autograd 0.74 % / 3.6 %; bf16 autocast 0.48 % / 2.4 %
+    assert ours[0] <= 1.5 * max(eager16[0], autocast[0]) and ours[1] <= 2.0 * max(eager16[1], autocast[1])
