@@ -51,3 +51,14 @@ def test_product_arm_has_no_cpu_fallback():
     assert p.returncode != 0
     assert p.stdout.strip() == ""                      # no JSON line is produced by a run that did not measure anything
     assert "no CPU fallback" in p.stderr or "no CUDA device" in p.stderr
+
+
+def test_reference_eager_subrecord_gating(monkeypatch, tmp_path):
+    """configs.reference_eager_b200 (tools/subbench.py): only rank 0 runs the unmodified reference on its GPU, and without the
+    baseline/_ref copy the record says so instead of silently timing something else (no oracle port, no product kernels)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import subbench
+    assert subbench.bench_reference_eager(torch.device("cpu"), 2, 1) == {"skipped": "rank 0 only"}
+    monkeypatch.setattr(subbench, "ROOT", str(tmp_path))
+    rec = subbench.bench_reference_eager(torch.device("cpu"), 1, 0)
+    assert list(rec) == ["unavailable"] and "baseline/_ref" in rec["unavailable"]
