@@ -273,6 +273,7 @@ def run_ours(args):
             got = r["y"]
             per_img = (got.clamp(0, 1) - ref.clamp(0, 1)).abs().flatten(1).max(dim=1).values
             r["parity"] = {"max_abs_clamped": float(per_img.max()), "max_abs_clamped_median_image": float(per_img.median()),
+                           "rmse_clamped": float((got.clamp(0, 1) - ref.clamp(0, 1)).pow(2).mean().sqrt()),
                            "images": BATCH, "dpsnr_db": abs(synth.psnr(got, clean) - synth.psnr(ref, clean)),
                            "tolerance": {"max_abs": 2e-3, "dpsnr_db": 0.02},
                            "oracle": f"fp32 CPU forward of the {'unmodified reference module' if kind == 'reference' else 'oracle port'}, every image of the batch"}
