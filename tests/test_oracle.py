@@ -47,6 +47,24 @@ def test_oracle_matches_reference_outputs(seeded, golden_dir, case):
         assert (flat[idx] - torch.tensor(d["sample"], dtype=torch.float64)).abs().max().item() < 2e-5, name
 
 
+@pytest.mark.parametrize("case", ["cfg2_256", "a192x320"])
+def test_oracle_matches_reference_outputs_with_upsampled_prompts(seeded, golden_dir, case):
+    """The cases above never resize a prompt UP (model.py:231: down at 32 / 40x24 / 64, identity at 128).  At the headline size
+    256x256 all three prompts are up-sampled x2, at 192x320 by x1.5 / x2.5 (oracle/make_golden_256.py, real reference)."""
+    g = np.load(os.path.join(golden_dir, "forward_seed0_up.npz"))
+    taps = {}
+    with torch.no_grad():
+        y = O.promptir_forward(seeded[1], torch.from_numpy(g[case + "_in"]), taps=taps)
+    assert (y - torch.from_numpy(g[case + "_out"])).abs().max().item() < 5e-6
+    meta = json.load(open(os.path.join(golden_dir, "taps_seed0_up.json")))[case]
+    for name, d in meta.items():
+        t = taps[name].double()
+        assert list(t.shape) == d["shape"], name
+        flat = t.flatten()
+        idx = torch.linspace(0, flat.numel() - 1, 64).long()
+        assert (flat[idx] - torch.tensor(d["sample"], dtype=torch.float64)).abs().max().item() < 2e-5, name
+
+
 def test_oracle_biasfree_with_bias(golden_dir):
     g = np.load(os.path.join(golden_dir, "forward_seed3_biasfree.npz"))
     torch.manual_seed(3)
