@@ -461,6 +461,30 @@ def test_prompt_gen(case, dt):
     report_mismatch("prompt", out, ref, *tol(dt))
 
 
+@pytest.mark.xfail(strict=False, reason="written after round 2's GPU budget was spent: not run on a B200 yet.  An XPASS in the log is the "
+                                       "first measurement; a failure would point at the align_corners=True up-sampling branch of pir_prompt_gen")
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", [(1, 256, 256, 96, 64, 64), (1, 64, 64, 384, 320, 16)], ids=lambda c: "B%dH%dW%dC%dD%dS%d" % c)
+def test_prompt_gen_align_corners_upsampling(case, dt):
+    """PromptXRestormer's PromptBlock resizes with align_corners=True (prompt_xrestormer.py:340), and at BASELINE.json configs[4]
+    (512x512) it up-samples (x4, x4, x4).  The GPU goldens of that network (64, 64x128, 128) only down-scale or keep the size, and
+    test_prompt_gen covers up-sampling for align_corners=False only: this is the missing combination, on exactly the prompt1 / prompt3
+    launch shapes of that configuration (which bench.py's xrestormer sub-record has run, checked on a 128x128 crop only)."""
+    B, H, W, Cc, D, S = case
+    torch.manual_seed(D + 1)
+    x, _ = rand_act(B, H, W, Cc, dt, Cc + D, 0)
+    prm = packing.pack_prompt(torch.rand(1, 5, D, S, S, device=DEV))
+    lw = (torch.randn(5, Cc, device=DEV) / Cc ** 0.5).contiguous()
+    lb = torch.randn(5, device=DEV) * 0.1
+    out = torch.zeros(B, H, W, D, device=DEV, dtype=dt)
+    ws = torch.zeros(ops.prompt_ws_floats(B, H * W, Cc), device=DEV)
+    ops.prompt_gen(x, prm, lw, lb, out, ws, None, align_corners=True)(stream())
+    torch.cuda.synchronize()
+    ref = torch.zeros_like(out)
+    emulator.emu_prompt(dict(x=x, prompt=prm, lin_w=lw, lin_b=lb, out=ref, align_corners=True))
+    report_mismatch("prompt(align_corners=True, up)", out, ref, *tol(dt))
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 def test_patch_embed(dt):
     B, H, W = 2, 24, 40

@@ -38,6 +38,22 @@ def test_oracle_matches_reference_golden(model, golden_dir):
             assert (y - torch.from_numpy(g[case + "_out"])).abs().max().item() <= 5e-6
 
 
+@pytest.mark.parametrize("case,shape,seed", [("x256", (1, 256, 256), 4), ("x192x320", (1, 192, 320), 6)])
+def test_oracle_matches_reference_golden_with_upsampled_prompts(model, golden_dir, case, shape, seed):
+    """The goldens above never resize a prompt UP (prompts are 64 / 32 / 16 wide at H/2, H/4, H/8); BASELINE.json configs[4] runs at
+    512x512 where PromptBlock's F.interpolate(align_corners=True) up-samples.  oracle/make_golden_x_up.py ran the real reference at
+    256x256 (x2) and 192x320 (x1.5 / x2.5); only its outputs are stored, the inputs are regenerated and checked by digest."""
+    from oracle.promptir_oracle import synthetic_batch
+    g = np.load(os.path.join(golden_dir, "xrestormer_seed0_up.npz"))
+    x, _ = synthetic_batch(*shape, seed=seed)
+    d = x.double()
+    digest = np.array([d.sum().item(), d.abs().sum().item(), d.flatten()[0].item(), d.flatten()[-1].item()])
+    assert np.array_equal(digest, g[case + "_in_digest"]), "synthetic_batch no longer reproduces the golden input"
+    with torch.no_grad():
+        y = XO.xrestormer_forward({k: v.detach() for k, v in model.state_dict().items()}, x)
+    assert (y - torch.from_numpy(g[case + "_out"])).abs().max().item() <= 5e-6
+
+
 @pytest.mark.parametrize("dt,lim", [(torch.float32, 3e-5), (torch.bfloat16, 3e-2)])
 def test_program_emulation_matches_reference(model, golden_dir, dt, lim):
     g = np.load(os.path.join(golden_dir, "xrestormer_seed0.npz"))
